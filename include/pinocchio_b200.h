@@ -1,0 +1,144 @@
+/*
+ * pinocchio_b200.h — C ABI of the B200-native batched rigid-body-dynamics engine.
+ *
+ * This is the drop-in boundary for Pinocchio's many-configuration path:
+ *   rneaInParallel   (reference: include/pinocchio/algorithm/parallel/rnea.hpp:31-83)
+ *   abaInParallel    (reference: include/pinocchio/algorithm/parallel/aba.hpp:32-84)
+ *   ModelPoolTpl     (reference: include/pinocchio/multibody/pool/model.hpp:19-165)
+ * extended by analogy to batched crba / computeRNEADerivatives / computeABADerivatives
+ *   (reference single-configuration entry points: include/pinocchio/algorithm/crba.hpp:47-51,
+ *    rnea-derivatives.hpp:110-128, aba-derivatives.hpp:52-66).
+ *
+ * Conventions (identical to the reference):
+ *   - every batched argument is a column-major block whose COLUMNS are configurations;
+ *     `ld*` is the leading dimension in elements (Eigen's outerStride()).
+ *   - free-flyer q = [x y z qx qy qz qw]; tangent vectors are body-frame (linear, angular).
+ *   - matrix outputs (M and the derivative matrices) are one col-major nv x nv matrix per configuration,
+ *     stored contiguously in one column of an (nv*nv) x B block.
+ *   - plain pointers and sizes only; no exceptions cross this boundary; every function
+ *     returns a brbd_status and brbd_last_error_string() explains the last failure of the
+ *     calling thread.
+ *   - there is NO CPU fallback: if no CUDA device is usable the calls fail with BRBD_ECUDA.
+ */
+#ifndef PINOCCHIO_B200_H
+#define PINOCCHIO_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum brbd_status {
+  BRBD_OK = 0,
+  BRBD_EINVAL = 1,            /* bad argument / size mismatch (reference: std::invalid_argument) */
+  BRBD_EUNSUPPORTED_JOINT = 2,/* joint type outside {RX,RY,RZ,PX,PY,PZ,FreeFlyer,Spherical,Planar} */
+  BRBD_ETOPOLOGY = 3,         /* parents[i] >= i, or the tree is not depth-first "compact"
+                                 (reference: CRBAChecker, crba.hxx:573-595) */
+  BRBD_ECUDA = 4,             /* CUDA runtime error or no device */
+  BRBD_ENOMEM = 5
+} brbd_status;
+
+/* Joint type tags (reference variant alternatives: multibody/joint/joint-collection.hpp:85-111). */
+typedef enum brbd_joint_type {
+  BRBD_JOINT_RX = 0, BRBD_JOINT_RY = 1, BRBD_JOINT_RZ = 2,   /* joint-revolute.hpp */
+  BRBD_JOINT_PX = 3, BRBD_JOINT_PY = 4, BRBD_JOINT_PZ = 5,   /* joint-prismatic.hpp */
+  BRBD_JOINT_FREEFLYER = 6,                                  /* joint-free-flyer.hpp (nq 7, nv 6) */
+  BRBD_JOINT_SPHERICAL = 7,                                  /* joint-spherical.hpp  (nq 4, nv 3) */
+  BRBD_JOINT_PLANAR = 8,                                     /* joint-planar.hpp     (nq 4, nv 3) */
+  BRBD_JOINT_UNIVERSE = -1                                   /* slot 0 only */
+} brbd_joint_type;
+
+/*
+ * Flattened Model: the fields of ModelTpl the five algorithms read
+ * (reference: multibody/model.hpp:97-205). Joint 0 is the universe. All arrays are
+ * borrowed for the duration of brbd_model_create only.
+ */
+typedef struct brbd_flat_model {
+  int32_t njoints;            /* including the universe                                   */
+  int32_t nq, nv;
+  const int32_t * parents;    /* [njoints]  parents[0] = 0                                */
+  const int32_t * joint_type; /* [njoints]  brbd_joint_type                               */
+  const int32_t * idx_q;      /* [njoints]                                                */
+  const int32_t * idx_v;      /* [njoints]                                                */
+  const double * placement;   /* [njoints*12] jointPlacements: R row-major (9) then p (3) */
+  const double * inertia;     /* [njoints*10] mass, lever(3), Symmetric3 packed
+                                 (xx,xy,yy,xz,yz,zz) — spatial/symmetric3.hpp:46-51      */
+  const double * armature;    /* [nv]                                                     */
+  double gravity[3];          /* linear part of model.gravity (default 0,0,-9.81)         */
+} brbd_flat_model;
+
+typedef struct brbd_model brbd_model; /* validated host copy + derived topology tables */
+typedef struct brbd_pool brbd_pool;   /* device analogue of ModelPoolTpl                 */
+
+/* flags for the *_batch calls */
+enum {
+  BRBD_PTR_HOST = 0,     /* pointers are host memory: the call stages H2D / D2H itself    */
+  BRBD_PTR_DEVICE = 1,   /* pointers are device memory on the pool's (single) device      */
+  BRBD_FP64 = 0,         /* element type double (default, parity mode)                    */
+  BRBD_FP32 = 2,         /* element type float  (tolerance documented in DESIGN.md)       */
+  BRBD_ASYNC = 4         /* device pointers only: do not synchronise before returning     */
+};
+
+const char * brbd_last_error_string(void);
+const char * brbd_version(void);
+int brbd_device_count(void);
+
+brbd_status brbd_model_create(const brbd_flat_model * flat, brbd_model ** out);
+void brbd_model_destroy(brbd_model * m);
+int brbd_model_nq(const brbd_model * m);
+int brbd_model_nv(const brbd_model * m);
+int brbd_model_njoints(const brbd_model * m);
+
+/* One staged model replica + one scratch arena + one stream per listed device
+ * (device analogue of ModelPoolTpl(model, pool_size), pool/model.hpp:41-46). */
+brbd_status brbd_pool_create(const brbd_model * m, const int * device_ids, int n_devices,
+                             brbd_pool ** out);
+void brbd_pool_destroy(brbd_pool * p);
+int brbd_pool_size(const brbd_pool * p);               /* number of devices */
+/* Replace the model held by every replica (ModelPoolTpl::update, pool/model.hpp:100-108). */
+brbd_status brbd_pool_update(brbd_pool * p, const brbd_model * m);
+/* Use an external CUDA stream (cudaStream_t as void*) for device-pointer calls on a
+ * single-device pool; NULL restores the pool's own stream. */
+brbd_status brbd_pool_set_stream(brbd_pool * p, void * cuda_stream);
+brbd_status brbd_pool_synchronize(brbd_pool * p);
+/* Number of kernels this pool has launched since creation (bench.py's gpu_launches). */
+int64_t brbd_pool_launch_count(const brbd_pool * p);
+/* CUDA-event time (ms) of the kernels of the last device-pointer call on device 0. */
+double brbd_pool_last_kernel_ms(const brbd_pool * p);
+
+/* tau[:,i] = rnea(q[:,i], v[:,i], a[:,i])     — replaces rneaInParallel (parallel/rnea.hpp:38) */
+brbd_status brbd_rnea_batch(brbd_pool * p, const void * q, int64_t ldq, const void * v, int64_t ldv,
+                            const void * a, int64_t lda, void * tau, int64_t ldtau, int64_t batch,
+                            int flags);
+/* a[:,i] = aba(q[:,i], v[:,i], tau[:,i], WORLD) — replaces abaInParallel (parallel/aba.hpp:40) */
+brbd_status brbd_aba_batch(brbd_pool * p, const void * q, int64_t ldq, const void * v, int64_t ldv,
+                           const void * tau, int64_t ldtau, void * a, int64_t lda, int64_t batch,
+                           int flags);
+/* M[:,i] = vec(crba(q[:,i])): upper triangle + armature on the diagonal, strictly-lower part
+ * written as zeros (crba.hpp:15-22; a fresh Data holds zeros there, data.hxx:43). ldM >= nv*nv. */
+brbd_status brbd_crba_batch(brbd_pool * p, const void * q, int64_t ldq, void * M, int64_t ldM,
+                            int64_t batch, int flags);
+/* computeRNEADerivatives per column (rnea-derivatives.hpp:110-128). dtau_dq, dtau_dv: full
+ * tree-sparse matrices; dtau_da: upper triangle of M (others zero). tau may be NULL. */
+brbd_status brbd_rnea_derivatives_batch(brbd_pool * p, const void * q, int64_t ldq, const void * v,
+                                        int64_t ldv, const void * a, int64_t lda, void * dtau_dq,
+                                        int64_t ld_dq, void * dtau_dv, int64_t ld_dv,
+                                        void * dtau_da, int64_t ld_da, void * tau, int64_t ldtau,
+                                        int64_t batch, int flags);
+/* computeABADerivatives per column (aba-derivatives.hpp:52-66). ddq_dtau = Minv (full
+ * symmetric). ddq may be NULL. */
+brbd_status brbd_aba_derivatives_batch(brbd_pool * p, const void * q, int64_t ldq, const void * v,
+                                       int64_t ldv, const void * tau, int64_t ldtau, void * ddq_dq,
+                                       int64_t ld_dq, void * ddq_dv, int64_t ld_dv,
+                                       void * ddq_dtau, int64_t ld_dtau, void * ddq, int64_t ldddq,
+                                       int64_t batch, int flags);
+
+/* Register-resident DFMA loop; returns achieved FP64 FLOP/s on the pool's device 0
+ * (SURVEY.md §7 hard part 4: the FP64 roofline denominator is measured, not assumed). */
+brbd_status brbd_measure_fp64_peak(brbd_pool * p, double * flops_per_s, double * elapsed_ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PINOCCHIO_B200_H */

@@ -1,0 +1,146 @@
+"""ctypes wrapper around oracle/liboracle.so (TEST INFRASTRUCTURE ONLY).
+
+Parity status: "parity unpinned" by golden vectors (the reference has none for this path);
+pinned by the reference's identity tests, see tests/test_oracle_identities.py.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+
+class _FlatModel(ctypes.Structure):
+    _fields_ = [
+        ("njoints", ctypes.c_int32), ("nq", ctypes.c_int32), ("nv", ctypes.c_int32),
+        ("parents", ctypes.POINTER(ctypes.c_int32)), ("joint_type", ctypes.POINTER(ctypes.c_int32)),
+        ("idx_q", ctypes.POINTER(ctypes.c_int32)), ("idx_v", ctypes.POINTER(ctypes.c_int32)),
+        ("placement", ctypes.POINTER(ctypes.c_double)), ("inertia", ctypes.POINTER(ctypes.c_double)),
+        ("armature", ctypes.POINTER(ctypes.c_double)), ("gravity", ctypes.c_double * 3),
+    ]
+
+
+def build_oracle(force: bool = False) -> str:
+    """Compile oracle/liboracle.so with the committed Makefile (gcc -O3 -fopenmp)."""
+    so = os.path.join(_HERE, "liboracle.so")
+    srcs = [os.path.join(_HERE, f) for f in ("oracle_capi.cpp", "rbd_oracle.hpp")]
+    stale = (not os.path.exists(so)) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs)
+    if force or stale:
+        subprocess.check_call(["make", "-C", _HERE, "-s"] + (["-B"] if force else []))
+    return so
+
+
+def _lib():
+    global _LIB
+    if _LIB is None:
+        L = ctypes.CDLL(build_oracle())
+        L.oracle_model_create.restype = ctypes.c_void_p
+        L.oracle_model_create.argtypes = [ctypes.POINTER(_FlatModel)]
+        L.oracle_model_destroy.argtypes = [ctypes.c_void_p]
+        L.oracle_max_threads.restype = ctypes.c_int
+        _LIB = L
+    return _LIB
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(ctypes.c_void_p)
+
+
+def _cols(a, rows):
+    a = np.asarray(a, dtype=np.float64)
+    if a.ndim == 1:
+        a = a.reshape(rows, 1)
+    assert a.shape[0] == rows, (a.shape, rows)
+    return np.asfortranarray(a)
+
+
+class Oracle:
+    """CPU restatement of rnea / aba(WORLD) / crba / computeRNEADerivatives / computeABADerivatives.
+
+    All batched arguments are (rows x B) arrays whose columns are configurations, as in
+    rneaInParallel (include/pinocchio/algorithm/parallel/rnea.hpp:38).
+    """
+
+    def __init__(self, model):
+        f = model.flat() if hasattr(model, "flat") else model
+        self._keep = f
+        self.nq, self.nv, self.njoints = int(f["nq"]), int(f["nv"]), int(f["njoints"])
+        fm = _FlatModel()
+        fm.njoints, fm.nq, fm.nv = self.njoints, self.nq, self.nv
+        ip = lambda k: f[k].ctypes.data_as(ctypes.POINTER(ctypes.c_int32))
+        dp = lambda k: f[k].ctypes.data_as(ctypes.POINTER(ctypes.c_double))
+        fm.parents, fm.joint_type, fm.idx_q, fm.idx_v = ip("parents"), ip("joint_type"), ip("idx_q"), ip("idx_v")
+        fm.placement, fm.inertia, fm.armature = dp("placement"), dp("inertia"), dp("armature")
+        for k in range(3):
+            fm.gravity[k] = float(f["gravity"][k])
+        self._h = ctypes.c_void_p(_lib().oracle_model_create(ctypes.byref(fm)))
+
+    def __del__(self):
+        try:
+            if self._h:
+                _lib().oracle_model_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+    @staticmethod
+    def max_threads() -> int:
+        return int(_lib().oracle_max_threads())
+
+    def rnea(self, q, v, a, nthreads=1, long_double=False):
+        q, v, a = _cols(q, self.nq), _cols(v, self.nv), _cols(a, self.nv)
+        B = q.shape[1]
+        tau = np.empty((self.nv, B), order="F")
+        _lib().oracle_rnea(self._h, _p(q), _p(v), _p(a), _p(tau), ctypes.c_int64(B), int(nthreads), int(long_double))
+        return tau
+
+    def aba(self, q, v, tau, nthreads=1, long_double=False):
+        q, v, tau = _cols(q, self.nq), _cols(v, self.nv), _cols(tau, self.nv)
+        B = q.shape[1]
+        a = np.empty((self.nv, B), order="F")
+        _lib().oracle_aba(self._h, _p(q), _p(v), _p(tau), _p(a), ctypes.c_int64(B), int(nthreads), int(long_double))
+        return a
+
+    def crba(self, q, nthreads=1, long_double=False, world=False):
+        """(nv*nv x B); each column a col-major nv x nv matrix, upper triangle + zeros."""
+        q = _cols(q, self.nq)
+        B = q.shape[1]
+        M = np.empty((self.nv * self.nv, B), order="F")
+        _lib().oracle_crba(self._h, _p(q), _p(M), ctypes.c_int64(B), int(nthreads), int(long_double), int(world))
+        return M
+
+    def rnea_derivatives(self, q, v, a, nthreads=1, long_double=False):
+        q, v, a = _cols(q, self.nq), _cols(v, self.nv), _cols(a, self.nv)
+        B = q.shape[1]
+        nn = self.nv * self.nv
+        dq, dv, da = (np.empty((nn, B), order="F") for _ in range(3))
+        tau = np.empty((self.nv, B), order="F")
+        _lib().oracle_rnea_derivatives(self._h, _p(q), _p(v), _p(a), _p(dq), _p(dv), _p(da), _p(tau),
+                                       ctypes.c_int64(B), int(nthreads), int(long_double))
+        return dq, dv, da, tau
+
+    def aba_derivatives(self, q, v, tau, nthreads=1, long_double=False):
+        q, v, tau = _cols(q, self.nq), _cols(v, self.nv), _cols(tau, self.nv)
+        B = q.shape[1]
+        nn = self.nv * self.nv
+        dq, dv, dtau = (np.empty((nn, B), order="F") for _ in range(3))
+        ddq = np.empty((self.nv, B), order="F")
+        _lib().oracle_aba_derivatives(self._h, _p(q), _p(v), _p(tau), _p(dq), _p(dv), _p(dtau), _p(ddq),
+                                      ctypes.c_int64(B), int(nthreads), int(long_double))
+        return dq, dv, dtau, ddq
+
+    ALGOS = {"rnea": 0, "aba": 1, "crba_world": 2, "crba_local": 3, "rnea_derivatives": 4, "aba_derivatives": 5}
+
+    def count_flops(self, algo: str, q, v, a):
+        """Exact operation counts of one evaluation: dict(add, mul, div, sqrt, sincos, flops)."""
+        out = (ctypes.c_uint64 * 5)()
+        q, v, a = (np.ascontiguousarray(x, dtype=np.float64) for x in (q, v, a))
+        _lib().oracle_count_flops(self._h, self.ALGOS[algo], _p(q), _p(v), _p(a), out)
+        d = dict(zip(("add", "mul", "div", "sqrt", "sincos"), (int(x) for x in out)))
+        d["flops"] = d["add"] + d["mul"] + d["div"] + d["sqrt"]
+        return d
