@@ -1,0 +1,721 @@
+// capi.cu — host side of the engine behind the C ABI declared in include/pinocchio_b200.h.
+//
+// brbd_model : validated copy of the flattened model + derived topology tables
+//              (nvSubtree / parents_fromRow: reference multibody/data.hxx:197-315; the model
+//              checks the reference runs at algorithm entry — parents[i] < i, CRBAChecker
+//              crba.hxx:573-595 — run once here).
+// brbd_pool  : device analogue of ModelPoolTpl (multibody/pool/model.hpp:19-165): one staged model
+//              replica, one stream and one grow-only staging arena per device.
+// *_batch    : the drop-in for rneaInParallel / abaInParallel (algorithm/parallel/rnea.hpp:38-83,
+//              parallel/aba.hpp:40-84) and their crba / derivative analogues.  The batch is split in
+//              contiguous column ranges over the pool's devices; there is no inter-device exchange.
+// There is no CPU fallback anywhere in this file.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/pinocchio_b200.h"
+#include "aba.cuh"
+#include "aba_derivatives.cuh"
+#include "crba.cuh"
+#include "engine.cuh"
+#include "rnea.cuh"
+#include "rnea_derivatives.cuh"
+
+using namespace brbd;
+
+namespace
+{
+thread_local std::string g_err;
+brbd_status fail(brbd_status s, const std::string & msg)
+{
+  g_err = msg;
+  return s;
+}
+#define CUDA_TRY(expr)                                                                              \
+  do                                                                                                \
+  {                                                                                                 \
+    cudaError_t e__ = (expr);                                                                       \
+    if (e__ != cudaSuccess)                                                                         \
+      return fail(BRBD_ECUDA, std::string(#expr) + ": " + cudaGetErrorString(e__));                 \
+  } while (0)
+
+int joint_nq_of(int t) { return t <= BRBD_JOINT_PZ ? 1 : (t == BRBD_JOINT_FREEFLYER ? 7 : 4); }
+int joint_nv_of(int t) { return t <= BRBD_JOINT_PZ ? 1 : (t == BRBD_JOINT_FREEFLYER ? 6 : 3); }
+
+template<class T> void fill_pod(ModelPOD<T> & P, const ModelPOD<double> & D)
+{
+  std::memset(&P, 0, sizeof(P));
+  P.njoints = D.njoints; P.nq = D.nq; P.nv = D.nv; P.maxdepth = D.maxdepth;
+  for (int i = 0; i < MAXJ; ++i)
+  {
+    P.parent[i] = D.parent[i]; P.type[i] = D.type[i]; P.idx_q[i] = D.idx_q[i]; P.idx_v[i] = D.idx_v[i];
+    P.nvj[i] = D.nvj[i]; P.nvsub[i] = D.nvsub[i]; P.depth[i] = D.depth[i];
+    for (int k = 0; k < 12; ++k) P.placement[i][k] = (T)D.placement[i][k];
+    for (int k = 0; k < 10; ++k) P.inertia[i][k] = (T)D.inertia[i][k];
+  }
+  for (int k = 0; k < MAXNV; ++k)
+  {
+    P.dof_joint[k] = D.dof_joint[k]; P.parent_row[k] = D.parent_row[k]; P.armature[k] = (T)D.armature[k];
+  }
+  for (int k = 0; k < 3; ++k) P.gravity[k] = (T)D.gravity[k];
+}
+} // namespace
+
+struct brbd_model
+{
+  ModelPOD<double> pd;
+  ModelPOD<float> pf;
+};
+
+namespace
+{
+struct DeviceCtx
+{
+  int dev = -1;
+  int sm_count = 0;
+  int max_smem_optin = 0;
+  cudaStream_t stream = nullptr;
+  cudaStream_t user_stream = nullptr;
+  bool use_user_stream = false;
+  ModelPOD<double> * d_pd = nullptr;
+  ModelPOD<float> * d_pf = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  // grow-only staging for host-pointer calls
+  void * stage[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  size_t stage_bytes[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  // grow-only device workspace (intermediates of aba-derivatives)
+  void * work = nullptr;
+  size_t work_bytes = 0;
+  cudaStream_t s() const { return use_user_stream ? user_stream : stream; }
+};
+} // namespace
+
+struct brbd_pool
+{
+  brbd_model model;
+  std::vector<DeviceCtx> devs;
+  int64_t launches = 0;
+  double last_ms = 0.0;
+};
+
+namespace
+{
+brbd_status ensure_stage(DeviceCtx & d, int slot, size_t bytes)
+{
+  if (d.stage_bytes[slot] >= bytes) return BRBD_OK;
+  if (d.stage[slot]) CUDA_TRY(cudaFree(d.stage[slot]));
+  d.stage[slot] = nullptr;
+  d.stage_bytes[slot] = 0;
+  CUDA_TRY(cudaMalloc(&d.stage[slot], bytes));
+  d.stage_bytes[slot] = bytes;
+  return BRBD_OK;
+}
+brbd_status ensure_work(DeviceCtx & d, size_t bytes)
+{
+  if (d.work_bytes >= bytes) return BRBD_OK;
+  if (d.work) CUDA_TRY(cudaFree(d.work));
+  d.work = nullptr;
+  d.work_bytes = 0;
+  CUDA_TRY(cudaMalloc(&d.work, bytes));
+  d.work_bytes = bytes;
+  return BRBD_OK;
+}
+
+// Launch geometry for the warp-tile kernels: `per_warp` bytes of dynamic shared memory per warp,
+// `static_bytes` of static shared memory per CTA. Picks the CTA size that maximises resident
+// warps per SM, and a persistent grid (CTAs loop over tiles).
+struct Geometry
+{
+  int warps_per_cta, ctas_per_sm, grid;
+  size_t dyn_bytes;
+};
+Geometry pick_geometry(const DeviceCtx & d, size_t per_warp, size_t static_bytes, int64_t batch, int max_warps_per_cta,
+                       int max_warps_per_sm)
+{
+  const size_t sm_total = 227 * 1024; // usable shared memory per SM on sm_100
+  Geometry best{1, 1, 1, per_warp};
+  int best_warps = 0;
+  for (int ctas = 1; ctas <= 8; ++ctas)
+  {
+    const size_t per_cta = sm_total / ctas;
+    if (per_cta < static_bytes + 1024 + per_warp) break;
+    int w = (int)((per_cta - static_bytes - 1024) / per_warp);
+    w = std::min(w, max_warps_per_cta);
+    w = std::min(w, std::max(1, max_warps_per_sm / ctas));
+    if (w < 1) break;
+    if ((size_t)w * per_warp + static_bytes > (size_t)d.max_smem_optin + 0) w = (int)((d.max_smem_optin - static_bytes) / per_warp);
+    if (w < 1) break;
+    if (w * ctas > best_warps)
+    {
+      best_warps = w * ctas;
+      best.warps_per_cta = w;
+      best.ctas_per_sm = ctas;
+    }
+  }
+  best.dyn_bytes = (size_t)best.warps_per_cta * per_warp;
+  const int64_t ntiles = (batch + 31) / 32;
+  const int64_t ctas_needed = (ntiles + best.warps_per_cta - 1) / best.warps_per_cta;
+  best.grid = (int)std::max<int64_t>(1, std::min<int64_t>(ctas_needed, (int64_t)d.sm_count * best.ctas_per_sm));
+  return best;
+}
+
+template<class K> brbd_status set_smem(K kernel, size_t dyn_bytes)
+{
+  CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_bytes));
+  return BRBD_OK;
+}
+
+template<class T> const ModelPOD<T> * dev_model(const DeviceCtx & d);
+template<> const ModelPOD<double> * dev_model<double>(const DeviceCtx & d) { return d.d_pd; }
+template<> const ModelPOD<float> * dev_model<float>(const DeviceCtx & d) { return d.d_pf; }
+
+// ------------------------------------------------------------------------------------------------
+// Device-pointer launches (one device)
+// ------------------------------------------------------------------------------------------------
+template<class T>
+brbd_status launch_rnea(brbd_pool * p, DeviceCtx & d, const T * q, int64_t ldq, const T * v, int64_t ldv, const T * a,
+                        int64_t lda, T * tau, int64_t ldtau, int64_t B)
+{
+  const ModelPOD<double> & M = p->model.pd;
+  const size_t per_warp = (size_t)32 * ((M.nq | 1) + 2 * (M.nv | 1)) * sizeof(T);
+  const Geometry g = pick_geometry(d, per_warp, sizeof(ModelPOD<T>), B, 16, 16);
+  brbd_status st = set_smem(rnea_kernel<T>, g.dyn_bytes);
+  if (st != BRBD_OK) return st;
+  rnea_kernel<T><<<g.grid, g.warps_per_cta * 32, g.dyn_bytes, d.s()>>>(dev_model<T>(d), q, ldq, v, ldv, a, lda, tau, ldtau, B);
+  p->launches += 1;
+  CUDA_TRY(cudaGetLastError());
+  return BRBD_OK;
+}
+
+template<class T>
+brbd_status launch_aba(brbd_pool * p, DeviceCtx & d, const T * q, int64_t ldq, const T * v, int64_t ldv, const T * tau,
+                       int64_t ldtau, T * a, int64_t lda, int64_t B)
+{
+  const ModelPOD<double> & M = p->model.pd;
+  const size_t per_warp = (size_t)32 * ((M.nq | 1) + 2 * (M.nv | 1)) * sizeof(T);
+  const Geometry g = pick_geometry(d, per_warp, sizeof(ModelPOD<T>), B, 16, 16);
+  brbd_status st = set_smem(aba_kernel<T>, g.dyn_bytes);
+  if (st != BRBD_OK) return st;
+  aba_kernel<T><<<g.grid, g.warps_per_cta * 32, g.dyn_bytes, d.s()>>>(dev_model<T>(d), q, ldq, v, ldv, tau, ldtau, a, lda, B);
+  p->launches += 1;
+  CUDA_TRY(cudaGetLastError());
+  return BRBD_OK;
+}
+
+template<class T>
+brbd_status launch_crba(brbd_pool * p, DeviceCtx & d, const T * q, int64_t ldq, T * Mout, int64_t ldM, int64_t B)
+{
+  const ModelPOD<double> & M = p->model.pd;
+  const size_t per_warp = (size_t)32 * ((M.nq | 1) + (M.nv | 1)) * sizeof(T);
+  const Geometry g = pick_geometry(d, per_warp, sizeof(ModelPOD<T>), B, 16, 16);
+  brbd_status st = set_smem(crba_kernel<T>, g.dyn_bytes);
+  if (st != BRBD_OK) return st;
+  crba_kernel<T><<<g.grid, g.warps_per_cta * 32, g.dyn_bytes, d.s()>>>(dev_model<T>(d), q, ldq, Mout, ldM, B);
+  p->launches += 1;
+  CUDA_TRY(cudaGetLastError());
+  return BRBD_OK;
+}
+
+template<class T>
+brbd_status launch_rnea_derivs(brbd_pool * p, DeviceCtx & d, const T * q, int64_t ldq, const T * v, int64_t ldv,
+                               const T * a, int64_t lda, T * dq, int64_t ld_dq, T * dv, int64_t ld_dv, T * da,
+                               int64_t ld_da, T * tau, int64_t ldtau, int64_t B)
+{
+  const ModelPOD<double> & M = p->model.pd;
+  const size_t per_warp = (size_t)32 * ((M.nq | 1) + 5 * (M.nv | 1)) * sizeof(T);
+  const Geometry g = pick_geometry(d, per_warp, sizeof(ModelPOD<T>), B, 16, 16);
+  brbd_status st = set_smem(rnea_derivatives_kernel<T>, g.dyn_bytes);
+  if (st != BRBD_OK) return st;
+  rnea_derivatives_kernel<T><<<g.grid, g.warps_per_cta * 32, g.dyn_bytes, d.s()>>>(
+    dev_model<T>(d), q, ldq, v, ldv, a, lda, dq, ld_dq, dv, ld_dv, da, ld_da, tau, ldtau, B);
+  p->launches += 1;
+  CUDA_TRY(cudaGetLastError());
+  return BRBD_OK;
+}
+
+template<class T>
+brbd_status launch_aba_derivs(brbd_pool * p, DeviceCtx & d, const T * q, int64_t ldq, const T * v, int64_t ldv,
+                              const T * tau, int64_t ldtau, T * dq, int64_t ld_dq, T * dv, int64_t ld_dv, T * dtau,
+                              int64_t ld_dtau, T * ddq, int64_t ldddq, int64_t B)
+{
+  const ModelPOD<double> & M = p->model.pd;
+  const size_t per_warp = (size_t)32 * ((M.nq | 1) + 5 * (M.nv | 1)) * sizeof(T);
+  const Geometry g = pick_geometry(d, per_warp, sizeof(ModelPOD<T>), B, 16, 16);
+  brbd_status st = set_smem(aba_derivatives_sweep_kernel<T>, g.dyn_bytes);
+  if (st != BRBD_OK) return st;
+  // thread-private workspace [entry][thread]: Minv (nv*nv) + Fcrb per tree depth ((maxdepth+1)*nv*6)
+  const size_t nthreads = (size_t)g.grid * g.warps_per_cta * 32;
+  const size_t ws_elems = ((size_t)M.nv * M.nv + (size_t)(M.maxdepth + 1) * M.nv * 6) * nthreads;
+  st = ensure_work(d, ws_elems * sizeof(T));
+  if (st != BRBD_OK) return st;
+  // pass A: sweeps -> Minv into `dtau`, dtau_dq / dtau_dv into `dq` / `dv` (all in the caller's layout)
+  aba_derivatives_sweep_kernel<T><<<g.grid, g.warps_per_cta * 32, g.dyn_bytes, d.s()>>>(
+    dev_model<T>(d), q, ldq, v, ldv, tau, ldtau, dq, ld_dq, dv, ld_dv, dtau, ld_dtau, ddq, ldddq, (T *)d.work, B);
+  p->launches += 1;
+  CUDA_TRY(cudaGetLastError());
+  // pass B: dq <- -Minv * dq, dv <- -Minv * dv, one warp per configuration (aba-derivatives.hxx:451-452)
+  {
+    const int nv = M.nv;
+    const int warps = 8;
+    const size_t dyn = (size_t)warps * 3 * nv * (nv + 1) * sizeof(T);
+    st = set_smem(aba_derivatives_gemm_kernel<T>, dyn);
+    if (st != BRBD_OK) return st;
+    const int64_t ctas = (B + warps - 1) / warps;
+    const int grid = (int)std::min<int64_t>(ctas, (int64_t)d.sm_count * 8);
+    aba_derivatives_gemm_kernel<T><<<grid, warps * 32, dyn, d.s()>>>(nv, dq, ld_dq, dv, ld_dv, dtau, ld_dtau, B);
+    p->launches += 1;
+    CUDA_TRY(cudaGetLastError());
+  }
+  return BRBD_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Generic call wrapper: argument checks, device/host pointer handling, sharding over devices.
+// ------------------------------------------------------------------------------------------------
+struct Arg
+{
+  const void * in;  // non-null for inputs
+  void * out;       // non-null for outputs
+  int64_t ld;
+  int64_t rows;
+  bool optional;
+};
+
+template<class T, class F>
+brbd_status run_call(brbd_pool * p, std::vector<Arg> & args, int64_t B, int flags, F && launch)
+{
+  if (!p) return fail(BRBD_EINVAL, "null pool");
+  if (p->devs.empty()) return fail(BRBD_EINVAL, "The pool should have at least one element"); // parallel/rnea.hpp:52
+  if (B < 0) return fail(BRBD_EINVAL, "negative batch size");
+  for (size_t k = 0; k < args.size(); ++k)
+  {
+    const Arg & a = args[k];
+    const bool present = a.in || a.out;
+    if (!present && !a.optional) return fail(BRBD_EINVAL, "null pointer argument #" + std::to_string(k));
+    if (present && a.ld < a.rows)
+      return fail(BRBD_EINVAL, "argument #" + std::to_string(k) + ": leading dimension " + std::to_string(a.ld)
+                                 + " smaller than the expected number of rows " + std::to_string(a.rows));
+  }
+  if (B == 0) return BRBD_OK;
+  const bool device_ptrs = (flags & BRBD_PTR_DEVICE) != 0;
+  if (device_ptrs)
+  {
+    if (p->devs.size() != 1) return fail(BRBD_EINVAL, "device pointers require a single-device pool");
+    DeviceCtx & d = p->devs[0];
+    CUDA_TRY(cudaSetDevice(d.dev));
+    std::vector<void *> ptrs(args.size());
+    for (size_t k = 0; k < args.size(); ++k) ptrs[k] = args[k].in ? const_cast<void *>(args[k].in) : args[k].out;
+    CUDA_TRY(cudaEventRecord(d.ev0, d.s()));
+    brbd_status st = launch(d, ptrs, B);
+    if (st != BRBD_OK) return st;
+    CUDA_TRY(cudaEventRecord(d.ev1, d.s()));
+    if (!(flags & BRBD_ASYNC))
+    {
+      CUDA_TRY(cudaStreamSynchronize(d.s()));
+      float ms = 0.f;
+      CUDA_TRY(cudaEventElapsedTime(&ms, d.ev0, d.ev1));
+      p->last_ms = ms;
+    }
+    return BRBD_OK;
+  }
+  // host pointers: shard columns contiguously over the devices, stage through device buffers
+  const int nd = (int)p->devs.size();
+  const int64_t per = (B + nd - 1) / nd;
+  if (args.size() > 8) return fail(BRBD_EINVAL, "too many arguments");
+  for (int g = 0; g < nd; ++g)
+  {
+    const int64_t c0 = (int64_t)g * per, c1 = std::min<int64_t>(B, c0 + per);
+    if (c0 >= c1) break;
+    const int64_t nb = c1 - c0;
+    DeviceCtx & d = p->devs[g];
+    CUDA_TRY(cudaSetDevice(d.dev));
+    std::vector<void *> ptrs(args.size(), nullptr);
+    for (size_t k = 0; k < args.size(); ++k)
+    {
+      const Arg & a = args[k];
+      if (!a.in && !a.out) continue;
+      const size_t bytes = (size_t)a.rows * nb * sizeof(T);
+      brbd_status st = ensure_stage(d, (int)k, bytes);
+      if (st != BRBD_OK) return st;
+      ptrs[k] = d.stage[k];
+      if (a.in)
+      {
+        const T * src = static_cast<const T *>(a.in) + c0 * a.ld;
+        CUDA_TRY(cudaMemcpy2DAsync(d.stage[k], a.rows * sizeof(T), src, a.ld * sizeof(T), a.rows * sizeof(T), nb,
+                                   cudaMemcpyHostToDevice, d.stream));
+      }
+    }
+    // staged blocks are dense: ld == rows
+    std::vector<Arg> saved = args;
+    for (size_t k = 0; k < args.size(); ++k) args[k].ld = args[k].rows;
+    brbd_status st = launch(d, ptrs, nb);
+    args = saved;
+    if (st != BRBD_OK) return st;
+    for (size_t k = 0; k < args.size(); ++k)
+    {
+      const Arg & a = args[k];
+      if (!a.out) continue;
+      T * dst = static_cast<T *>(a.out) + c0 * a.ld;
+      CUDA_TRY(cudaMemcpy2DAsync(dst, a.ld * sizeof(T), d.stage[k], a.rows * sizeof(T), a.rows * sizeof(T), nb,
+                                 cudaMemcpyDeviceToHost, d.stream));
+    }
+  }
+  for (int g = 0; g < nd; ++g)
+  {
+    CUDA_TRY(cudaSetDevice(p->devs[g].dev));
+    CUDA_TRY(cudaStreamSynchronize(p->devs[g].stream));
+  }
+  return BRBD_OK;
+}
+
+__global__ void fp64_peak_kernel(double * out, int iters)
+{
+  double a0 = threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+  const double b = 1.0000001, c = 1e-9;
+  for (int i = 0; i < iters; ++i)
+  {
+    a0 = fma(a0, b, c); a1 = fma(a1, b, c); a2 = fma(a2, b, c); a3 = fma(a3, b, c);
+    a4 = fma(a4, b, c); a5 = fma(a5, b, c); a6 = fma(a6, b, c); a7 = fma(a7, b, c);
+  }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+} // namespace
+
+// ------------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------------
+extern "C" {
+
+const char * brbd_last_error_string(void) { return g_err.c_str(); }
+const char * brbd_version(void) { return "pinocchio_b200 0.1 (sm_100a)"; }
+int brbd_device_count(void)
+{
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+  return n;
+}
+
+brbd_status brbd_model_create(const brbd_flat_model * f, brbd_model ** out)
+{
+  if (!f || !out) return fail(BRBD_EINVAL, "null argument");
+  *out = nullptr;
+  if (f->njoints < 1 || f->njoints > MAXJ)
+    return fail(BRBD_EINVAL, "njoints must be in [1, " + std::to_string(MAXJ) + "]");
+  if (f->nv > MAXNV || f->nv < 0) return fail(BRBD_EINVAL, "nv must be in [0, " + std::to_string(MAXNV) + "]");
+  brbd_model * m = new brbd_model();
+  ModelPOD<double> & P = m->pd;
+  std::memset(&P, 0, sizeof(P));
+  P.njoints = f->njoints; P.nq = f->nq; P.nv = f->nv;
+  int nq = 0, nv = 0, maxdepth = 0;
+  for (int i = 0; i < f->njoints; ++i)
+  {
+    P.parent[i] = f->parents[i];
+    P.type[i] = f->joint_type[i];
+    P.idx_q[i] = f->idx_q[i];
+    P.idx_v[i] = f->idx_v[i];
+    if (i == 0)
+    {
+      P.nvj[i] = 0; P.depth[i] = 0;
+      continue;
+    }
+    if (P.type[i] < BRBD_JOINT_RX || P.type[i] > BRBD_JOINT_PLANAR)
+    {
+      delete m;
+      return fail(BRBD_EUNSUPPORTED_JOINT, "joint " + std::to_string(i) + " has unsupported type tag " + std::to_string(f->joint_type[i]));
+    }
+    if (P.parent[i] < 0 || P.parent[i] >= i)
+    {
+      delete m;
+      return fail(BRBD_ETOPOLOGY, "parents[" + std::to_string(i) + "] must be < " + std::to_string(i));
+    }
+    if (P.idx_q[i] != nq || P.idx_v[i] != nv)
+    {
+      delete m;
+      return fail(BRBD_EINVAL, "idx_q / idx_v of joint " + std::to_string(i) + " are not cumulative");
+    }
+    P.nvj[i] = joint_nv_of(P.type[i]);
+    nq += joint_nq_of(P.type[i]);
+    nv += P.nvj[i];
+    P.depth[i] = P.depth[P.parent[i]] + 1;
+    maxdepth = std::max(maxdepth, P.depth[i]);
+    for (int k = 0; k < P.nvj[i]; ++k) P.dof_joint[P.idx_v[i] + k] = i;
+  }
+  if (nq != f->nq || nv != f->nv)
+  {
+    delete m;
+    return fail(BRBD_EINVAL, "nq / nv do not match the joint list");
+  }
+  if (maxdepth >= MAXDEPTH)
+  {
+    delete m;
+    return fail(BRBD_ETOPOLOGY, "tree depth exceeds " + std::to_string(MAXDEPTH - 1));
+  }
+  P.maxdepth = maxdepth;
+  // compact depth-first numbering (CRBAChecker, crba.hxx:573-595): the subtree of i is [i, last(i)]
+  {
+    std::vector<int> last(f->njoints);
+    for (int i = 0; i < f->njoints; ++i) last[i] = i;
+    for (int i = f->njoints - 1; i > 0; --i) last[P.parent[i]] = std::max(last[P.parent[i]], last[i]);
+    for (int i = 1; i < f->njoints; ++i)
+      for (int k = i + 1; k <= last[i]; ++k)
+      {
+        int a = k;
+        while (a > i) a = P.parent[a];
+        if (a != i)
+        {
+          delete m;
+          return fail(BRBD_ETOPOLOGY, "joints are not numbered depth-first (subtree of joint " + std::to_string(i) + " is not contiguous)");
+        }
+      }
+    for (int i = 0; i < f->njoints; ++i)
+    {
+      const int lc = last[i];
+      P.nvsub[i] = (lc == 0) ? 0 : P.idx_v[lc] + P.nvj[lc] - (i == 0 ? 0 : P.idx_v[i]);
+    }
+  }
+  for (int k = 0; k < MAXNV; ++k) P.parent_row[k] = -1;
+  for (int j = 1; j < f->njoints; ++j)
+  {
+    const int parent = P.parent[j], iv = P.idx_v[j];
+    P.parent_row[iv] = parent > 0 ? P.idx_v[parent] + P.nvj[parent] - 1 : -1;
+    for (int r = 1; r < P.nvj[j]; ++r) P.parent_row[iv + r] = iv + r - 1;
+  }
+  for (int i = 0; i < f->njoints; ++i)
+  {
+    const double * S = f->placement + 12 * i; // R row-major, p
+    double * D = P.placement[i];             // R by columns, p
+    for (int c = 0; c < 3; ++c) for (int r = 0; r < 3; ++r) D[3 * c + r] = S[3 * r + c];
+    for (int k = 0; k < 3; ++k) D[9 + k] = S[9 + k];
+    for (int k = 0; k < 10; ++k) P.inertia[i][k] = f->inertia[10 * i + k];
+  }
+  for (int k = 0; k < f->nv; ++k) P.armature[k] = f->armature[k];
+  for (int k = 0; k < 3; ++k) P.gravity[k] = f->gravity[k];
+  fill_pod(m->pf, P);
+  *out = m;
+  return BRBD_OK;
+}
+void brbd_model_destroy(brbd_model * m) { delete m; }
+int brbd_model_nq(const brbd_model * m) { return m ? m->pd.nq : -1; }
+int brbd_model_nv(const brbd_model * m) { return m ? m->pd.nv : -1; }
+int brbd_model_njoints(const brbd_model * m) { return m ? m->pd.njoints : -1; }
+
+static brbd_status upload_model(brbd_pool * p)
+{
+  for (DeviceCtx & d : p->devs)
+  {
+    CUDA_TRY(cudaSetDevice(d.dev));
+    CUDA_TRY(cudaMemcpy(d.d_pd, &p->model.pd, sizeof(ModelPOD<double>), cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(d.d_pf, &p->model.pf, sizeof(ModelPOD<float>), cudaMemcpyHostToDevice));
+  }
+  return BRBD_OK;
+}
+
+void brbd_pool_destroy(brbd_pool * p)
+{
+  if (!p) return;
+  for (DeviceCtx & d : p->devs)
+  {
+    if (cudaSetDevice(d.dev) != cudaSuccess) continue;
+    if (d.stream) cudaStreamSynchronize(d.stream);
+    for (int k = 0; k < 8; ++k) if (d.stage[k]) cudaFree(d.stage[k]);
+    if (d.work) cudaFree(d.work);
+    if (d.d_pd) cudaFree(d.d_pd);
+    if (d.d_pf) cudaFree(d.d_pf);
+    if (d.ev0) cudaEventDestroy(d.ev0);
+    if (d.ev1) cudaEventDestroy(d.ev1);
+    if (d.stream) cudaStreamDestroy(d.stream);
+  }
+  delete p;
+}
+
+brbd_status brbd_pool_create(const brbd_model * m, const int * device_ids, int n_devices, brbd_pool ** out)
+{
+  if (!m || !out) return fail(BRBD_EINVAL, "null argument");
+  *out = nullptr;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return fail(BRBD_ECUDA, std::string("no CUDA device available (there is no CPU fallback): ") + cudaGetErrorString(e));
+  std::vector<int> ids;
+  if (!device_ids || n_devices <= 0) ids.push_back(0);
+  else ids.assign(device_ids, device_ids + n_devices);
+  brbd_pool * p = new brbd_pool();
+  p->model = *m;
+  for (int id : ids)
+  {
+    if (id < 0 || id >= ndev)
+    {
+      brbd_pool_destroy(p);
+      return fail(BRBD_EINVAL, "device id " + std::to_string(id) + " out of range");
+    }
+    DeviceCtx d;
+    d.dev = id;
+    p->devs.push_back(d);
+  }
+  for (DeviceCtx & d : p->devs)
+  {
+    cudaDeviceProp prop;
+    brbd_status st = BRBD_OK;
+    auto tryc = [&](cudaError_t err, const char * what) {
+      if (err != cudaSuccess && st == BRBD_OK) st = fail(BRBD_ECUDA, std::string(what) + ": " + cudaGetErrorString(err));
+    };
+    tryc(cudaSetDevice(d.dev), "cudaSetDevice");
+    tryc(cudaGetDeviceProperties(&prop, d.dev), "cudaGetDeviceProperties");
+    if (st == BRBD_OK)
+    {
+      d.sm_count = prop.multiProcessorCount;
+      d.max_smem_optin = (int)prop.sharedMemPerBlockOptin;
+      tryc(cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking), "cudaStreamCreate");
+      tryc(cudaEventCreate(&d.ev0), "cudaEventCreate");
+      tryc(cudaEventCreate(&d.ev1), "cudaEventCreate");
+      tryc(cudaMalloc(&d.d_pd, sizeof(ModelPOD<double>)), "cudaMalloc");
+      tryc(cudaMalloc(&d.d_pf, sizeof(ModelPOD<float>)), "cudaMalloc");
+    }
+    if (st != BRBD_OK)
+    {
+      brbd_pool_destroy(p);
+      return st;
+    }
+  }
+  brbd_status st = upload_model(p);
+  if (st != BRBD_OK)
+  {
+    brbd_pool_destroy(p);
+    return st;
+  }
+  *out = p;
+  return BRBD_OK;
+}
+int brbd_pool_size(const brbd_pool * p) { return p ? (int)p->devs.size() : 0; }
+brbd_status brbd_pool_update(brbd_pool * p, const brbd_model * m)
+{
+  if (!p || !m) return fail(BRBD_EINVAL, "null argument");
+  brbd_status st = brbd_pool_synchronize(p);
+  if (st != BRBD_OK) return st;
+  p->model = *m;
+  return upload_model(p);
+}
+brbd_status brbd_pool_set_stream(brbd_pool * p, void * cuda_stream)
+{
+  if (!p) return fail(BRBD_EINVAL, "null pool");
+  if (p->devs.size() != 1) return fail(BRBD_EINVAL, "external streams require a single-device pool");
+  p->devs[0].user_stream = static_cast<cudaStream_t>(cuda_stream);
+  p->devs[0].use_user_stream = true;
+  return BRBD_OK;
+}
+brbd_status brbd_pool_synchronize(brbd_pool * p)
+{
+  if (!p) return fail(BRBD_EINVAL, "null pool");
+  for (DeviceCtx & d : p->devs)
+  {
+    CUDA_TRY(cudaSetDevice(d.dev));
+    CUDA_TRY(cudaStreamSynchronize(d.s()));
+    if (d.use_user_stream) CUDA_TRY(cudaStreamSynchronize(d.stream));
+  }
+  return BRBD_OK;
+}
+int64_t brbd_pool_launch_count(const brbd_pool * p) { return p ? p->launches : 0; }
+double brbd_pool_last_kernel_ms(const brbd_pool * p) { return p ? p->last_ms : 0.0; }
+
+#define DISPATCH(flags, CALL)                              \
+  if ((flags)&BRBD_FP32) { typedef float T; return CALL; } \
+  else { typedef double T; return CALL; }
+
+brbd_status brbd_rnea_batch(brbd_pool * p, const void * q, int64_t ldq, const void * v, int64_t ldv, const void * a,
+                            int64_t lda, void * tau, int64_t ldtau, int64_t batch, int flags)
+{
+  if (!p) return fail(BRBD_EINVAL, "null pool");
+  const int nq = p->model.pd.nq, nv = p->model.pd.nv;
+  std::vector<Arg> args = {{q, nullptr, ldq, nq, false}, {v, nullptr, ldv, nv, false}, {a, nullptr, lda, nv, false}, {nullptr, tau, ldtau, nv, false}};
+  DISPATCH(flags, (run_call<T>(p, args, batch, flags, [&](DeviceCtx & d, std::vector<void *> & P, int64_t B) {
+             return launch_rnea<T>(p, d, (const T *)P[0], args[0].ld, (const T *)P[1], args[1].ld, (const T *)P[2], args[2].ld,
+                                   (T *)P[3], args[3].ld, B);
+           })));
+}
+
+brbd_status brbd_aba_batch(brbd_pool * p, const void * q, int64_t ldq, const void * v, int64_t ldv, const void * tau,
+                           int64_t ldtau, void * a, int64_t lda, int64_t batch, int flags)
+{
+  if (!p) return fail(BRBD_EINVAL, "null pool");
+  const int nq = p->model.pd.nq, nv = p->model.pd.nv;
+  std::vector<Arg> args = {{q, nullptr, ldq, nq, false}, {v, nullptr, ldv, nv, false}, {tau, nullptr, ldtau, nv, false}, {nullptr, a, lda, nv, false}};
+  DISPATCH(flags, (run_call<T>(p, args, batch, flags, [&](DeviceCtx & d, std::vector<void *> & P, int64_t B) {
+             return launch_aba<T>(p, d, (const T *)P[0], args[0].ld, (const T *)P[1], args[1].ld, (const T *)P[2], args[2].ld,
+                                  (T *)P[3], args[3].ld, B);
+           })));
+}
+
+brbd_status brbd_crba_batch(brbd_pool * p, const void * q, int64_t ldq, void * M, int64_t ldM, int64_t batch, int flags)
+{
+  if (!p) return fail(BRBD_EINVAL, "null pool");
+  const int nq = p->model.pd.nq, nv = p->model.pd.nv;
+  std::vector<Arg> args = {{q, nullptr, ldq, nq, false}, {nullptr, M, ldM, (int64_t)nv * nv, false}};
+  DISPATCH(flags, (run_call<T>(p, args, batch, flags, [&](DeviceCtx & d, std::vector<void *> & P, int64_t B) {
+             return launch_crba<T>(p, d, (const T *)P[0], args[0].ld, (T *)P[1], args[1].ld, B);
+           })));
+}
+
+brbd_status brbd_rnea_derivatives_batch(brbd_pool * p, const void * q, int64_t ldq, const void * v, int64_t ldv,
+                                        const void * a, int64_t lda, void * dtau_dq, int64_t ld_dq, void * dtau_dv,
+                                        int64_t ld_dv, void * dtau_da, int64_t ld_da, void * tau, int64_t ldtau,
+                                        int64_t batch, int flags)
+{
+  if (!p) return fail(BRBD_EINVAL, "null pool");
+  const int nq = p->model.pd.nq, nv = p->model.pd.nv;
+  const int64_t nn = (int64_t)nv * nv;
+  std::vector<Arg> args = {{q, nullptr, ldq, nq, false},   {v, nullptr, ldv, nv, false},     {a, nullptr, lda, nv, false},
+                           {nullptr, dtau_dq, ld_dq, nn, false}, {nullptr, dtau_dv, ld_dv, nn, false}, {nullptr, dtau_da, ld_da, nn, false},
+                           {nullptr, tau, ldtau, nv, true}};
+  DISPATCH(flags, (run_call<T>(p, args, batch, flags, [&](DeviceCtx & d, std::vector<void *> & P, int64_t B) {
+             return launch_rnea_derivs<T>(p, d, (const T *)P[0], args[0].ld, (const T *)P[1], args[1].ld, (const T *)P[2],
+                                          args[2].ld, (T *)P[3], args[3].ld, (T *)P[4], args[4].ld, (T *)P[5], args[5].ld,
+                                          (T *)P[6], args[6].ld, B);
+           })));
+}
+
+brbd_status brbd_aba_derivatives_batch(brbd_pool * p, const void * q, int64_t ldq, const void * v, int64_t ldv,
+                                       const void * tau, int64_t ldtau, void * ddq_dq, int64_t ld_dq, void * ddq_dv,
+                                       int64_t ld_dv, void * ddq_dtau, int64_t ld_dtau, void * ddq, int64_t ldddq,
+                                       int64_t batch, int flags)
+{
+  if (!p) return fail(BRBD_EINVAL, "null pool");
+  const int nq = p->model.pd.nq, nv = p->model.pd.nv;
+  const int64_t nn = (int64_t)nv * nv;
+  std::vector<Arg> args = {{q, nullptr, ldq, nq, false},   {v, nullptr, ldv, nv, false},     {tau, nullptr, ldtau, nv, false},
+                           {nullptr, ddq_dq, ld_dq, nn, false}, {nullptr, ddq_dv, ld_dv, nn, false}, {nullptr, ddq_dtau, ld_dtau, nn, false},
+                           {nullptr, ddq, ldddq, nv, true}};
+  DISPATCH(flags, (run_call<T>(p, args, batch, flags, [&](DeviceCtx & d, std::vector<void *> & P, int64_t B) {
+             return launch_aba_derivs<T>(p, d, (const T *)P[0], args[0].ld, (const T *)P[1], args[1].ld, (const T *)P[2],
+                                         args[2].ld, (T *)P[3], args[3].ld, (T *)P[4], args[4].ld, (T *)P[5], args[5].ld,
+                                         (T *)P[6], args[6].ld, B);
+           })));
+}
+
+brbd_status brbd_measure_fp64_peak(brbd_pool * p, double * flops_per_s, double * elapsed_ms)
+{
+  if (!p || p->devs.empty()) return fail(BRBD_EINVAL, "null pool");
+  DeviceCtx & d = p->devs[0];
+  CUDA_TRY(cudaSetDevice(d.dev));
+  const int threads = 256, blocks = d.sm_count * 8, iters = 1 << 16;
+  brbd_status st = ensure_work(d, (size_t)threads * blocks * sizeof(double));
+  if (st != BRBD_OK) return st;
+  fp64_peak_kernel<<<blocks, threads, 0, d.stream>>>((double *)d.work, 1 << 10); // warm-up
+  CUDA_TRY(cudaEventRecord(d.ev0, d.stream));
+  fp64_peak_kernel<<<blocks, threads, 0, d.stream>>>((double *)d.work, iters);
+  CUDA_TRY(cudaEventRecord(d.ev1, d.stream));
+  CUDA_TRY(cudaStreamSynchronize(d.stream));
+  p->launches += 2;
+  float ms = 0.f;
+  CUDA_TRY(cudaEventElapsedTime(&ms, d.ev0, d.ev1));
+  const double flops = 2.0 * 8.0 * (double)iters * threads * blocks;
+  if (flops_per_s) *flops_per_s = flops / (ms * 1e-3);
+  if (elapsed_ms) *elapsed_ms = ms;
+  return BRBD_OK;
+}
+
+} // extern "C"

@@ -1,0 +1,280 @@
+"""Host-side mirror of the reference's batched interface, on top of the C ABI.
+
+Mirrors, with the same names, argument order and error behaviour:
+
+* ``ModelPool``               — ModelPoolTpl (include/pinocchio/multibody/pool/model.hpp:19-165;
+                                Python binding include/pinocchio/bindings/python/multibody/pool/model.hpp:30-80)
+* ``rneaInParallel``          — include/pinocchio/algorithm/parallel/rnea.hpp:38-83
+                                (binding bindings/python/algorithm/parallel/rnea.cpp:15-64)
+* ``abaInParallel``           — include/pinocchio/algorithm/parallel/aba.hpp:40-84
+* ``crbaInParallel``, ``computeRNEADerivativesInParallel``, ``computeABADerivativesInParallel`` —
+  batched analogues of crba (algorithm/crba.hpp:47-51), computeRNEADerivatives
+  (rnea-derivatives.hpp:110-128) and computeABADerivatives (aba-derivatives.hpp:52-66).
+
+Inputs are (rows x B) arrays whose COLUMNS are configurations: numpy arrays (host; staged over PCIe
+by the engine) or torch CUDA tensors of shape (B, rows) / Fortran-like (rows, B) views (device;
+zero-copy).  ``num_threads`` is accepted for signature compatibility and ignored by the GPU path.
+Errors the reference raises as ``std::invalid_argument`` surface as ``ValueError``.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Optional, Sequence
+
+import numpy as np
+
+from . import _capi
+from ._capi import BRBD_ASYNC, BRBD_FP32, BRBD_FP64, BRBD_PTR_DEVICE, BRBD_PTR_HOST, EngineError
+
+try:  # torch is optional plumbing (device memory / streams); numpy inputs work without it
+    import torch
+except Exception:  # pragma: no cover
+    torch = None
+
+
+def _raise(e: EngineError):
+    if e.status in (_capi.BRBD_EINVAL, _capi.BRBD_EUNSUPPORTED_JOINT, _capi.BRBD_ETOPOLOGY):
+        raise ValueError(str(e)) from None
+    raise e
+
+
+class ModelPool:
+    """Device analogue of ``pinocchio.ModelPool``: one staged model replica per GPU."""
+
+    def __init__(self, model, devices: Optional[Sequence[int]] = None):
+        self._model = model
+        self._h_model = ctypes.c_void_p()
+        self._h_pool = ctypes.c_void_p()
+        self._create_model(model)
+        L = _capi.lib()
+        if devices is None:
+            ids, n = None, 0
+        else:
+            arr = (ctypes.c_int * len(devices))(*[int(d) for d in devices])
+            ids, n = arr, len(devices)
+        try:
+            _capi.check(L.brbd_pool_create(self._h_model, ids, n, ctypes.byref(self._h_pool)))
+        except EngineError as e:
+            _raise(e)
+
+    def _create_model(self, model):
+        L = _capi.lib()
+        flat = model.flat() if hasattr(model, "flat") else model
+        fm, keep = _capi.make_flat(flat)
+        h = ctypes.c_void_p()
+        try:
+            _capi.check(L.brbd_model_create(ctypes.byref(fm), ctypes.byref(h)))
+        except EngineError as e:
+            _raise(e)
+        if self._h_model:
+            L.brbd_model_destroy(self._h_model)
+        self._h_model = h
+        self.nq, self.nv, self.njoints = L.brbd_model_nq(h), L.brbd_model_nv(h), L.brbd_model_njoints(h)
+
+    # -- ModelPoolTpl interface -----------------------------------------------------------------
+    def size(self) -> int:
+        return int(_capi.lib().brbd_pool_size(self._h_pool))
+
+    def getModel(self, index: int = 0):
+        return self._model
+
+    def update(self, model):
+        """ModelPoolTpl::update (pool/model.hpp:100-108)."""
+        self._model = model
+        self._create_model(model)
+        _capi.check(_capi.lib().brbd_pool_update(self._h_pool, self._h_model))
+
+    # -- engine extras --------------------------------------------------------------------------
+    def synchronize(self):
+        _capi.check(_capi.lib().brbd_pool_synchronize(self._h_pool))
+
+    def set_stream(self, cuda_stream: Optional[int]):
+        _capi.check(_capi.lib().brbd_pool_set_stream(self._h_pool, ctypes.c_void_p(cuda_stream or 0)))
+
+    def launch_count(self) -> int:
+        return int(_capi.lib().brbd_pool_launch_count(self._h_pool))
+
+    def last_kernel_ms(self) -> float:
+        return float(_capi.lib().brbd_pool_last_kernel_ms(self._h_pool))
+
+    def measure_fp64_peak(self):
+        f, ms = ctypes.c_double(), ctypes.c_double()
+        _capi.check(_capi.lib().brbd_measure_fp64_peak(self._h_pool, ctypes.byref(f), ctypes.byref(ms)))
+        return f.value, ms.value
+
+    def close(self):
+        L = _capi._lib
+        if L is None:
+            return
+        if self._h_pool:
+            L.brbd_pool_destroy(self._h_pool)
+            self._h_pool = ctypes.c_void_p()
+        if self._h_model:
+            L.brbd_model_destroy(self._h_model)
+            self._h_model = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+# ------------------------------------------------------------------------------------------------
+# argument marshalling
+# ------------------------------------------------------------------------------------------------
+class _Arg:
+    __slots__ = ("ptr", "ld", "rows", "cols", "device", "dtype", "keep", "writeback")
+
+
+def _is_torch(x) -> bool:
+    return torch is not None and isinstance(x, torch.Tensor)
+
+
+def _describe(x, rows: int, name: str, out: bool = False) -> _Arg:
+    """Resolve pointer / leading dimension of a (rows x B) column-per-configuration block."""
+    a = _Arg()
+    a.rows, a.writeback = rows, None
+    if _is_torch(x):
+        if x.dim() == 1:
+            x = x.view(1, -1) if rows != x.numel() else x.view(1, rows)
+        # accepted: (B, rows) row-major [natural torch batch layout] or (rows, B) column-major view
+        if x.shape[-1] == rows and x.stride(-1) == 1 and x.dim() == 2:
+            a.cols, a.ld = x.shape[0], x.stride(0) if x.shape[0] > 1 else rows
+        elif x.shape[0] == rows and x.stride(0) == 1 and x.dim() == 2:
+            a.cols, a.ld = x.shape[1], x.stride(1) if x.shape[1] > 1 else rows
+        else:
+            raise ValueError(f"{name}: expected a (B, {rows}) contiguous tensor or a ({rows}, B) column-major view, "
+                             f"got shape {tuple(x.shape)} strides {x.stride()}")
+        a.device = x.is_cuda
+        a.dtype = np.float64 if x.dtype == torch.float64 else (np.float32 if x.dtype == torch.float32 else None)
+        a.ptr, a.keep = x.data_ptr(), x
+        if a.dtype is None:
+            raise ValueError(f"{name}: dtype must be float64 or float32")
+        return a
+    arr = x
+    if not isinstance(arr, np.ndarray):
+        arr = np.asarray(arr)
+    if arr.ndim == 1:
+        arr = arr.reshape(rows, 1, order="F") if arr.size == rows else arr.reshape(-1, 1)
+    if arr.ndim != 2 or arr.shape[0] != rows:
+        # same wording family as PINOCCHIO_CHECK_ARGUMENT_SIZE (macros.hpp:185-223)
+        raise ValueError(f"wrong argument size: expected {rows} rows for {name}, got {arr.shape[0] if arr.ndim else 0}")
+    if arr.dtype not in (np.float64, np.float32):
+        if out:
+            raise ValueError(f"{name}: output dtype must be float64 or float32")
+        arr = arr.astype(np.float64)
+    if arr.strides[0] != arr.itemsize or (arr.shape[1] > 1 and arr.strides[1] < rows * arr.itemsize):
+        if out:
+            raise ValueError(f"{name}: output must be column-major (Fortran order)")
+        arr = np.asfortranarray(arr)
+    a.cols = arr.shape[1]
+    a.ld = arr.strides[1] // arr.itemsize if arr.shape[1] > 1 else rows
+    a.device, a.dtype, a.ptr, a.keep = False, arr.dtype.type, arr.ctypes.data, arr
+    return a
+
+
+def _alloc_like(ref, rows: int, cols: int):
+    if _is_torch(ref):
+        return torch.empty((cols, rows), dtype=ref.dtype, device=ref.device)
+    return np.empty((rows, cols), dtype=ref.dtype if ref.dtype in (np.float64, np.float32) else np.float64, order="F")
+
+
+def _call(pool: ModelPool, fn_name: str, ins, outs, async_: bool = False):
+    """ins / outs: lists of (_Arg or None)."""
+    args = [a for a in ins + outs if a is not None]
+    B = ins[0].cols
+    for a in args:
+        if a.cols != B:
+            raise ValueError(f"wrong argument size: all blocks must have the same number of columns ({a.cols} != {B})")
+    dev = {a.device for a in args}
+    dt = {a.dtype for a in args}
+    if len(dev) != 1:
+        raise ValueError("mixing host and device arguments in one call is not supported")
+    if len(dt) != 1:
+        raise ValueError("all arguments must share one dtype (float64 or float32)")
+    flags = (BRBD_PTR_DEVICE if dev.pop() else BRBD_PTR_HOST) | (BRBD_FP32 if dt.pop() is np.float32 else BRBD_FP64)
+    if async_:
+        flags |= BRBD_ASYNC
+    cargs = [pool._h_pool]
+    for a in ins + outs:
+        if a is None:
+            cargs += [ctypes.c_void_p(0), ctypes.c_int64(0)]
+        else:
+            cargs += [ctypes.c_void_p(a.ptr), ctypes.c_int64(a.ld)]
+    cargs += [ctypes.c_int64(B), ctypes.c_int(flags)]
+    try:
+        _capi.check(getattr(_capi.lib(), fn_name)(*cargs))
+    except EngineError as e:
+        _raise(e)
+
+
+def _check_pool(num_threads: int, pool: ModelPool):
+    # parallel/rnea.hpp:52-54 — the GPU pool has no per-thread replicas, so only emptiness is checked
+    if pool.size() <= 0:
+        raise ValueError("The pool should have at least one element")
+    if int(num_threads) < 0:
+        raise ValueError("num_threads must be non-negative")
+
+
+def rneaInParallel(num_threads: int, pool: ModelPool, q, v, a, tau=None, async_: bool = False):
+    """tau[:, i] = rnea(model, q[:, i], v[:, i], a[:, i]) — parallel/rnea.hpp:38-83."""
+    _check_pool(num_threads, pool)
+    aq, av, aa = _describe(q, pool.nq, "q"), _describe(v, pool.nv, "v"), _describe(a, pool.nv, "a")
+    if tau is None:
+        tau = _alloc_like(q, pool.nv, aq.cols)
+    _call(pool, "brbd_rnea_batch", [aq, av, aa], [_describe(tau, pool.nv, "tau", out=True)], async_)
+    return tau
+
+
+def abaInParallel(num_threads: int, pool: ModelPool, q, v, tau, a=None, async_: bool = False):
+    """a[:, i] = aba(model, q[:, i], v[:, i], tau[:, i], Convention::WORLD) — parallel/aba.hpp:40-84."""
+    _check_pool(num_threads, pool)
+    aq, av, at = _describe(q, pool.nq, "q"), _describe(v, pool.nv, "v"), _describe(tau, pool.nv, "tau")
+    if a is None:
+        a = _alloc_like(q, pool.nv, aq.cols)
+    _call(pool, "brbd_aba_batch", [aq, av, at], [_describe(a, pool.nv, "a", out=True)], async_)
+    return a
+
+
+def crbaInParallel(num_threads: int, pool: ModelPool, q, M=None, async_: bool = False):
+    """M[:, i] = vec(crba(model, q[:, i])): (nv*nv x B), upper triangle + zeros (crba.hpp:15-22)."""
+    _check_pool(num_threads, pool)
+    aq = _describe(q, pool.nq, "q")
+    nn = pool.nv * pool.nv
+    if M is None:
+        M = _alloc_like(q, nn, aq.cols)
+    _call(pool, "brbd_crba_batch", [aq], [_describe(M, nn, "M", out=True)], async_)
+    return M
+
+
+def computeRNEADerivativesInParallel(num_threads: int, pool: ModelPool, q, v, a, dtau_dq=None, dtau_dv=None,
+                                     dtau_da=None, tau=None, async_: bool = False):
+    """Per column: computeRNEADerivatives (rnea-derivatives.hpp:110-128). Returns (dtau_dq, dtau_dv, dtau_da, tau)."""
+    _check_pool(num_threads, pool)
+    aq, av, aa = _describe(q, pool.nq, "q"), _describe(v, pool.nv, "v"), _describe(a, pool.nv, "a")
+    nn, B = pool.nv * pool.nv, aq.cols
+    dtau_dq = _alloc_like(q, nn, B) if dtau_dq is None else dtau_dq
+    dtau_dv = _alloc_like(q, nn, B) if dtau_dv is None else dtau_dv
+    dtau_da = _alloc_like(q, nn, B) if dtau_da is None else dtau_da
+    tau = _alloc_like(q, pool.nv, B) if tau is None else tau
+    _call(pool, "brbd_rnea_derivatives_batch", [aq, av, aa],
+          [_describe(dtau_dq, nn, "dtau_dq", True), _describe(dtau_dv, nn, "dtau_dv", True),
+           _describe(dtau_da, nn, "dtau_da", True), _describe(tau, pool.nv, "tau", True)], async_)
+    return dtau_dq, dtau_dv, dtau_da, tau
+
+
+def computeABADerivativesInParallel(num_threads: int, pool: ModelPool, q, v, tau, ddq_dq=None, ddq_dv=None,
+                                    ddq_dtau=None, ddq=None, async_: bool = False):
+    """Per column: computeABADerivatives (aba-derivatives.hpp:52-66). Returns (ddq_dq, ddq_dv, ddq_dtau, ddq)."""
+    _check_pool(num_threads, pool)
+    aq, av, at = _describe(q, pool.nq, "q"), _describe(v, pool.nv, "v"), _describe(tau, pool.nv, "tau")
+    nn, B = pool.nv * pool.nv, aq.cols
+    ddq_dq = _alloc_like(q, nn, B) if ddq_dq is None else ddq_dq
+    ddq_dv = _alloc_like(q, nn, B) if ddq_dv is None else ddq_dv
+    ddq_dtau = _alloc_like(q, nn, B) if ddq_dtau is None else ddq_dtau
+    ddq = _alloc_like(q, pool.nv, B) if ddq is None else ddq
+    _call(pool, "brbd_aba_derivatives_batch", [aq, av, at],
+          [_describe(ddq_dq, nn, "ddq_dq", True), _describe(ddq_dv, nn, "ddq_dv", True),
+           _describe(ddq_dtau, nn, "ddq_dtau", True), _describe(ddq, pool.nv, "ddq", True)], async_)
+    return ddq_dq, ddq_dv, ddq_dtau, ddq

@@ -1,0 +1,92 @@
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+MODEL_DIR = os.path.join(ROOT, "tests", "golden", "models")
+MODEL_NAMES = ["manipulator", "humanoid", "humanoid_random", "simple_humanoid_ff", "talos_reduced_ff"]
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with `-m gpu`)")
+
+
+def load_model(name):
+    from pinocchio_b200.model import Model
+    with open(os.path.join(MODEL_DIR, name + ".json")) as fh:
+        return Model.from_json(fh.read())
+
+
+def make_extra_models():
+    """Small models covering the joint families the config models do not (prismatic, spherical, planar)."""
+    from pinocchio_b200 import model as M
+    rng = M._Rng(7)
+    out = {}
+    # planar base + prismatic + spherical + revolute branches
+    m = M.Model()
+    m.name = "mixed"
+
+    def add(jt, parent, name):
+        nqj = M.joint_nq(jt)
+        idx = m.addJoint(parent, jt, rng.se3(), name, np.full(nqj, -1.0), np.full(nqj, 1.0))
+        m.appendBodyToJoint(idx, rng.inertia(), M.SE3.Identity())
+        return idx
+    b = add(M.JOINT_PLANAR, 0, "planar_base")
+    p1 = add(M.JOINT_PX, b, "px")
+    s1 = add(M.JOINT_SPHERICAL, p1, "sph1")
+    add(M.JOINT_RZ, s1, "rz_tip")
+    p2 = add(M.JOINT_PY, b, "py")
+    r2 = add(M.JOINT_RX, p2, "rx")
+    add(M.JOINT_PZ, r2, "pz")
+    add(M.JOINT_SPHERICAL, r2, "sph2")
+    m.armature = np.abs(rng.sym(m.nv)) * 0.1
+    out["mixed"] = m
+    # two free-flyers in a chain (multi-dof joint that is NOT the root) + armature
+    m2 = M.Model()
+    m2.name = "double_ff"
+    lo7, hi7 = np.array([-1.0] * 7), np.array([1.0] * 7)
+    f1 = m2.addJoint(0, M.JOINT_FREEFLYER, rng.se3(), "ff1", lo7, hi7)
+    m2.appendBodyToJoint(f1, rng.inertia())
+    r = m2.addJoint(f1, M.JOINT_RY, rng.se3(), "ry", [-1.0], [1.0])
+    m2.appendBodyToJoint(r, rng.inertia())
+    f2 = m2.addJoint(r, M.JOINT_FREEFLYER, rng.se3(), "ff2", lo7, hi7)
+    m2.appendBodyToJoint(f2, rng.inertia())
+    t = m2.addJoint(f2, M.JOINT_RX, rng.se3(), "rx", [-1.0], [1.0])
+    m2.appendBodyToJoint(t, rng.inertia())
+    m2.armature = np.abs(rng.sym(m2.nv)) * 0.05
+    out["double_ff"] = m2
+    return out
+
+
+def random_inputs(model, B, seed):
+    """(q, v, a) with the reference benchmark's distributions (benchmark/timings-parallel.cpp:48-60)."""
+    from pinocchio_b200.joint_configuration import batched_random_configuration, batched_random_tangent
+    q = batched_random_configuration(model, B, seed)
+    v = batched_random_tangent(model, B, seed + 1)
+    a = batched_random_tangent(model, B, seed + 2)
+    return q, v, a
+
+
+def assert_close(actual, expected, rtol=1e-10, atol=1e-12, what=""):
+    """north_star tolerance: 1e-10 relative / 1e-12 absolute (element-wise, numpy allclose semantics)."""
+    actual, expected = np.asarray(actual), np.asarray(expected)
+    assert actual.shape == expected.shape, (what, actual.shape, expected.shape)
+    err = np.abs(actual - expected)
+    tol = atol + rtol * np.abs(expected)
+    bad = err > tol
+    if bad.any():
+        k = np.unravel_index(np.argmax(err - tol), err.shape)
+        raise AssertionError(f"{what}: {int(bad.sum())} entries out of tolerance; worst at {k}: "
+                             f"got {actual[k]!r} expected {expected[k]!r} (err {err[k]:.3e}, tol {tol[k]:.3e})")
+
+
+@pytest.fixture(scope="session")
+def oracle_cls():
+    from oracle import Oracle, build_oracle
+    build_oracle()
+    return Oracle

@@ -1,0 +1,215 @@
+"""Pins the CPU oracle with the reference's own identity tests.
+
+The reference ships no golden vectors for this path (unittest/rnea.cpp:5-9: "numerical values are
+not cross validated in any way"); every test of RNEA / ABA / CRBA / derivatives there is an identity.
+Each test below re-runs one of them against oracle/ and cites the reference test it restates.
+"""
+import numpy as np
+import pytest
+
+from conftest import MODEL_NAMES, load_model, make_extra_models, random_inputs
+
+ALL = MODEL_NAMES + ["mixed", "double_ff"]
+EXTRA = make_extra_models()
+
+
+def get_model(name):
+    return EXTRA[name] if name in EXTRA else load_model(name)
+
+
+def is_approx(a, b, prec=1e-12):
+    """Eigen isApprox: ||a-b|| <= prec * min(||a||, ||b||)."""
+    a, b = np.asarray(a).ravel(), np.asarray(b).ravel()
+    return np.linalg.norm(a - b) <= prec * min(np.linalg.norm(a), np.linalg.norm(b))
+
+
+def mat(col, nv):
+    return np.asarray(col).reshape(nv, nv, order="F")
+
+
+def sym_from_upper(M):
+    return np.triu(M) + np.triu(M, 1).T
+
+
+@pytest.fixture(scope="module")
+def make(oracle_cls):
+    cache = {}
+
+    def get(name):
+        if name not in cache:
+            m = get_model(name)
+            cache[name] = (m, oracle_cls(m))
+        return cache[name]
+    return get
+
+
+def test_known_dimensions():
+    """unittest/sample-models.cpp:43-44,70-71,92-93; unittest/urdf.cpp:85,252."""
+    dims = {"manipulator": (6, 6, 7), "humanoid": (35, 34, 30), "humanoid_random": (33, 32, 28),
+            "simple_humanoid_ff": (36, 35, 31), "talos_reduced_ff": (39, 38, 34)}
+    for name, (nq, nv, nj) in dims.items():
+        m = load_model(name)
+        assert (m.nq, m.nv, m.njoints) == (nq, nv, nj), name
+
+
+@pytest.mark.parametrize("name", ALL)
+def test_aba_inverts_rnea(make, name):
+    """unittest/aba.cpp:124-184: aba(q, v, rnea(q, v, a)) == a (WORLD convention), 1e-12."""
+    m, o = make(name)
+    q, v, a = random_inputs(m, 8, 1)
+    tau = o.rnea(q, v, a)
+    a2 = o.aba(q, v, tau)
+    for i in range(8):
+        assert is_approx(a2[:, i], a[:, i], 1e-11), (name, i)
+
+
+@pytest.mark.parametrize("name", ALL)
+def test_crba_vs_rnea_columns(make, name):
+    """unittest/crba.cpp:92-129: M[:, i] == rnea(q, 0, e_i) - rnea(q, 0, 0), 1e-12."""
+    m, o = make(name)
+    q, _, _ = random_inputs(m, 1, 2)
+    nv = m.nv
+    M = sym_from_upper(mat(o.crba(q)[:, 0], nv))
+    z = np.zeros(nv)
+    bias = o.rnea(q[:, 0], z, z)[:, 0]
+    for i in range(nv):
+        e = np.zeros(nv)
+        e[i] = 1.0
+        col = o.rnea(q[:, 0], z, e)[:, 0] - bias
+        assert np.linalg.norm(col - M[:, i]) <= 1e-11 * max(1.0, np.linalg.norm(col)), (name, i)
+
+
+@pytest.mark.parametrize("name", ALL)
+def test_crba_local_equals_world(make, name):
+    """unittest/crba.cpp:172-208."""
+    m, o = make(name)
+    q, _, _ = random_inputs(m, 4, 3)
+    assert is_approx(o.crba(q, world=False), o.crba(q, world=True), 1e-12)
+
+
+@pytest.mark.parametrize("name", ALL)
+def test_equation_of_motion(make, name):
+    """unittest/aba.cpp:229-263: M a + nle == rnea(q, v, a); aba(M a + nle) == a."""
+    m, o = make(name)
+    q, v, a = random_inputs(m, 2, 4)
+    for i in range(2):
+        M = sym_from_upper(mat(o.crba(q[:, i], world=True)[:, 0], m.nv))
+        nle = o.rnea(q[:, i], v[:, i], np.zeros(m.nv))[:, 0]  # unittest/rnea.cpp:79-134
+        tau = M @ a[:, i] + nle
+        assert is_approx(tau, o.rnea(q[:, i], v[:, i], a[:, i])[:, 0], 1e-12)
+        assert is_approx(o.aba(q[:, i], v[:, i], tau)[:, 0], a[:, i], 1e-11)
+
+
+def test_armature(make, oracle_cls):
+    """unittest/rnea.cpp:179-207 and unittest/crba.cpp:210-235: rotor inertia adds armature*a / diag(armature)."""
+    m = load_model("humanoid_random")
+    o0 = oracle_cls(m)
+    m2 = load_model("humanoid_random")
+    m2.armature = np.linspace(0.1, 1.0, m2.nv)
+    o1 = oracle_cls(m2)
+    q, v, a = random_inputs(m, 3, 5)
+    assert is_approx(o1.rnea(q, v, a), o0.rnea(q, v, a) + m2.armature[:, None] * a, 1e-12)
+    for i in range(3):
+        M0, M1 = mat(o0.crba(q[:, i])[:, 0], m.nv), mat(o1.crba(q[:, i])[:, 0], m.nv)
+        assert is_approx(M1, M0 + np.diag(m2.armature), 1e-12)
+    tau = o1.rnea(q, v, a)
+    assert is_approx(o1.aba(q, v, tau), a, 1e-11)  # unittest/aba.cpp:367-...
+
+
+@pytest.mark.parametrize("name", ALL)
+def test_rnea_derivatives_vs_finite_differences(make, name):
+    """unittest/rnea-derivatives.cpp:113-313: forward differences, alpha = 1e-8, tolerance sqrt(alpha);
+    dtau_da == crba (:294-299); data.tau == rnea."""
+    from pinocchio_b200.joint_configuration import integrate
+    m, o = make(name)
+    q, v, a = random_inputs(m, 1, 6)
+    q, v, a = q[:, 0], v[:, 0], a[:, 0]
+    nv = m.nv
+    dq, dv, da, tau = o.rnea_derivatives(q, v, a)
+    tau0 = o.rnea(q, v, a)[:, 0]
+    assert is_approx(tau[:, 0], tau0, 1e-12)
+    assert is_approx(mat(da[:, 0], nv), mat(o.crba(q, world=True)[:, 0], nv), 1e-12)
+    alpha = 1e-8
+    fdq, fdv = np.zeros((nv, nv)), np.zeros((nv, nv))
+    for k in range(nv):
+        e = np.zeros(nv)
+        e[k] = alpha
+        fdq[:, k] = (o.rnea(integrate(m, q, e), v, a)[:, 0] - tau0) / alpha
+        fdv[:, k] = (o.rnea(q, v + e, a)[:, 0] - tau0) / alpha
+    assert is_approx(mat(dq[:, 0], nv), fdq, np.sqrt(alpha))
+    assert is_approx(mat(dv[:, 0], nv), fdv, np.sqrt(alpha))
+
+
+@pytest.mark.parametrize("name", ALL)
+def test_aba_derivatives(make, name):
+    """unittest/aba-derivatives.cpp:23-155: ddq_dtau == Minv == inv(crba); dq/dv == -Minv * dtau_d{q,v} of
+    computeRNEADerivatives(q, v, aba(...)) (:107-108); partials vs finite differences at sqrt(alpha)."""
+    from pinocchio_b200.joint_configuration import integrate
+    m, o = make(name)
+    q, v, tau = random_inputs(m, 1, 7)
+    q, v, tau = q[:, 0], v[:, 0], tau[:, 0]
+    nv = m.nv
+    dq, dv, dtau, ddq = o.aba_derivatives(q, v, tau)
+    a0 = o.aba(q, v, tau)[:, 0]
+    assert is_approx(ddq[:, 0], a0, 1e-12)
+    Minv = mat(dtau[:, 0], nv)
+    M = sym_from_upper(mat(o.crba(q, world=True)[:, 0], nv))
+    assert is_approx(Minv, np.linalg.inv(M), 1e-9)  # unittest/aba.cpp:265-340
+    rdq, rdv, _, _ = o.rnea_derivatives(q, v, a0)
+    assert is_approx(mat(dq[:, 0], nv), -Minv @ mat(rdq[:, 0], nv), 1e-9)
+    assert is_approx(mat(dv[:, 0], nv), -Minv @ mat(rdv[:, 0], nv), 1e-9)
+    alpha = 1e-8
+    fdq, fdv, fdt = np.zeros((nv, nv)), np.zeros((nv, nv)), np.zeros((nv, nv))
+    for k in range(nv):
+        e = np.zeros(nv)
+        e[k] = alpha
+        fdq[:, k] = (o.aba(integrate(m, q, e), v, tau)[:, 0] - a0) / alpha
+        fdv[:, k] = (o.aba(q, v + e, tau)[:, 0] - a0) / alpha
+        fdt[:, k] = (o.aba(q, v, tau + e)[:, 0] - a0) / alpha
+    assert is_approx(mat(dq[:, 0], nv), fdq, 1e-3)
+    assert is_approx(mat(dv[:, 0], nv), fdv, 1e-3)
+    assert is_approx(Minv, fdt, 1e-3)
+
+
+@pytest.mark.parametrize("name", ["manipulator", "humanoid_random", "talos_reduced_ff", "mixed"])
+def test_double_vs_long_double(make, name):
+    """Independent guard (SURVEY §7 hard part 3): the double oracle agrees with its 80-bit instantiation."""
+    m, o = make(name)
+    q, v, a = random_inputs(m, 4, 8)
+    assert is_approx(o.rnea(q, v, a), o.rnea(q, v, a, long_double=True), 1e-12)
+    tau = o.rnea(q, v, a)
+    assert is_approx(o.aba(q, v, tau), o.aba(q, v, tau, long_double=True), 1e-10)
+    assert is_approx(o.crba(q, world=True), o.crba(q, world=True, long_double=True), 1e-12)
+
+
+def test_parallel_equals_serial(make):
+    """unittest/parallel-rnea.cpp:21-55 / parallel-aba.cpp:21-55: bit-exact."""
+    m, o = make("humanoid_random")
+    q, v, a = random_inputs(m, 128, 9)
+    t1, tn = o.rnea(q, v, a, nthreads=1), o.rnea(q, v, a, nthreads=4)
+    assert np.array_equal(t1, tn)
+    a1, an = o.aba(q, v, t1, nthreads=1), o.aba(q, v, t1, nthreads=3)
+    assert np.array_equal(a1, an)
+
+
+def test_pendulum_closed_form(oracle_cls):
+    """Analytic guard: a point mass m at distance l on a revolute-Y joint: tau = m l^2 a + m g l sin(q)."""
+    from pinocchio_b200 import model as M
+    mdl = M.Model()
+    j = mdl.addJoint(0, M.JOINT_RY, M.SE3.Identity(), "pend", [-3.0], [3.0])
+    mass, l = 2.0, 0.7
+    mdl.appendBodyToJoint(j, M.Inertia(mass, [0.0, 0.0, -l], np.zeros((3, 3))))
+    o = oracle_cls(mdl)
+    for qv, av in ((0.3, 0.0), (-1.1, 2.0), (2.0, -0.5)):
+        tau = o.rnea(np.array([qv]), np.array([0.4]), np.array([av]))[0, 0]
+        assert abs(tau - (mass * l * l * av + mass * 9.81 * l * np.sin(qv))) < 1e-12
+        Mq = o.crba(np.array([qv]))[0, 0]
+        assert abs(Mq - mass * l * l) < 1e-13
+
+
+def test_flop_counts_are_positive_and_ordered(make):
+    m, o = make("humanoid_random")
+    q, v, a = random_inputs(m, 1, 10)
+    c = {k: o.count_flops(k, q[:, 0], v[:, 0], a[:, 0]) for k in o.ALGOS}
+    assert c["rnea"]["flops"] < c["aba"]["flops"] < c["rnea_derivatives"]["flops"] < c["aba_derivatives"]["flops"]
+    assert c["rnea"]["sincos"] == 26
