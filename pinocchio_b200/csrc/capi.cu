@@ -261,8 +261,9 @@ brbd_status launch_aba_derivs(brbd_pool * p, DeviceCtx & d, const T * q, int64_t
   // pass B: dq <- -Minv * dq, dv <- -Minv * dv, one warp per configuration (aba-derivatives.hxx:451-452)
   {
     const int nv = M.nv;
-    const int warps = 8;
-    const size_t dyn = (size_t)warps * 3 * nv * (nv + 1) * sizeof(T);
+    const size_t per_warp_gemm = (size_t)3 * nv * (nv + 1) * sizeof(T);
+    const int warps = (int)std::max<size_t>(1, std::min<size_t>(8, (size_t)d.max_smem_optin / per_warp_gemm));
+    const size_t dyn = (size_t)warps * per_warp_gemm;
     st = set_smem(aba_derivatives_gemm_kernel<T>, dyn);
     if (st != BRBD_OK) return st;
     const int64_t ctas = (B + warps - 1) / warps;
