@@ -21,10 +21,14 @@
 #include "../../include/pinocchio_b200.h"
 #include "aba.cuh"
 #include "aba_derivatives.cuh"
+#include "aba_dfs.cuh"
 #include "crba.cuh"
+#include "crba_dfs.cuh"
 #include "engine.cuh"
 #include "rnea.cuh"
 #include "rnea_derivatives.cuh"
+#include "rnea_dfs.cuh"
+#include "tree.cuh"
 
 using namespace brbd;
 
@@ -70,6 +74,8 @@ struct brbd_model
 {
   ModelPOD<double> pd;
   ModelPOD<float> pf;
+  TreePOD<double> td; // v2 kernels: passed by value as a __grid_constant__ kernel parameter
+  TreePOD<float> tf;
 };
 
 namespace
@@ -177,16 +183,58 @@ template<> const ModelPOD<float> * dev_model<float>(const DeviceCtx & d) { retur
 // ------------------------------------------------------------------------------------------------
 // Device-pointer launches (one device)
 // ------------------------------------------------------------------------------------------------
+template<class T> const TreePOD<T> & tree_of(const brbd_pool * p);
+template<> const TreePOD<double> & tree_of<double>(const brbd_pool * p) { return p->model.td; }
+template<> const TreePOD<float> & tree_of<float>(const brbd_pool * p) { return p->model.tf; }
+
+// Launch geometry of the v2 (DFS-interleaved) kernels: `state_bytes` of shared memory per thread plus
+// `warp_bytes` per warp; as many warps per CTA as fit (<= max_warps), as many CTAs per SM as fit
+// (<= max_ctas), persistent grid.
+struct Geometry2
+{
+  int warps, ctas_per_sm, grid;
+  size_t dyn_bytes;
+};
+Geometry2 pick_geometry2(const DeviceCtx & d, size_t state_bytes, size_t warp_bytes, int64_t batch, int max_warps, int max_ctas)
+{
+  const size_t per_warp = 32 * state_bytes + warp_bytes;
+  const size_t cap = (size_t)d.max_smem_optin;
+  Geometry2 g;
+  g.warps = (int)std::max<size_t>(1, std::min<size_t>((size_t)max_warps, cap / per_warp));
+  g.dyn_bytes = (size_t)g.warps * per_warp;
+  const size_t sm_total = 228 * 1024; // per SM; every resident CTA also reserves 1 KB
+  g.ctas_per_sm = (int)std::max<size_t>(1, std::min<size_t>((size_t)max_ctas, sm_total / (g.dyn_bytes + 1024)));
+  const int64_t ctas_needed = (batch + g.warps * 32 - 1) / (g.warps * 32);
+  g.grid = (int)std::max<int64_t>(1, std::min<int64_t>(ctas_needed, (int64_t)d.sm_count * g.ctas_per_sm));
+  return g;
+}
+
+// kernels are instantiated for 1..4 warps per CTA (NT = threads per CTA is a template parameter)
+#define BRBD_SWITCH_WARPS(w)              \
+  switch (w)                              \
+  {                                       \
+  case 1: BRBD_LAUNCH(32) break;          \
+  case 2: BRBD_LAUNCH(64) break;          \
+  case 3: BRBD_LAUNCH(96) break;          \
+  default: BRBD_LAUNCH(128) break;        \
+  }
+
 template<class T>
 brbd_status launch_rnea(brbd_pool * p, DeviceCtx & d, const T * q, int64_t ldq, const T * v, int64_t ldv, const T * a,
                         int64_t lda, T * tau, int64_t ldtau, int64_t B)
 {
-  const ModelPOD<double> & M = p->model.pd;
-  const size_t per_warp = (size_t)32 * ((M.nq | 1) + 2 * (M.nv | 1)) * sizeof(T);
-  const Geometry g = pick_geometry(d, per_warp, sizeof(ModelPOD<T>), B, 16, 16);
-  brbd_status st = set_smem(rnea_kernel<T>, g.dyn_bytes);
-  if (st != BRBD_OK) return st;
-  rnea_kernel<T><<<g.grid, g.warps_per_cta * 32, g.dyn_bytes, d.s()>>>(dev_model<T>(d), q, ldq, v, ldv, a, lda, tau, ldtau, B);
+  const TreePOD<T> & t = tree_of<T>(p);
+  const RneaLayout L = rnea_layout(t.maxdepth, t.nbranch);
+  const Geometry2 g = pick_geometry2(d, (size_t)L.nstate * sizeof(T), 0, B, 4, 4);
+  brbd_status st = BRBD_OK;
+#define BRBD_LAUNCH(NT)                                                                              \
+  {                                                                                                  \
+    st = set_smem(rnea_dfs_kernel<T, NT>, g.dyn_bytes);                                              \
+    if (st != BRBD_OK) return st;                                                                    \
+    rnea_dfs_kernel<T, NT><<<g.grid, NT, g.dyn_bytes, d.s()>>>(t, L, q, ldq, v, ldv, a, lda, tau, ldtau, B); \
+  }
+  BRBD_SWITCH_WARPS(g.warps)
+#undef BRBD_LAUNCH
   p->launches += 1;
   CUDA_TRY(cudaGetLastError());
   return BRBD_OK;
@@ -196,12 +244,21 @@ template<class T>
 brbd_status launch_aba(brbd_pool * p, DeviceCtx & d, const T * q, int64_t ldq, const T * v, int64_t ldv, const T * tau,
                        int64_t ldtau, T * a, int64_t lda, int64_t B)
 {
-  const ModelPOD<double> & M = p->model.pd;
-  const size_t per_warp = (size_t)32 * ((M.nq | 1) + 2 * (M.nv | 1)) * sizeof(T);
-  const Geometry g = pick_geometry(d, per_warp, sizeof(ModelPOD<T>), B, 16, 16);
-  brbd_status st = set_smem(aba_kernel<T>, g.dyn_bytes);
+  const TreePOD<T> & t = tree_of<T>(p);
+  const AbaLayout L = aba_layout(t.maxdepth, t.nbranch);
+  const Geometry2 g = pick_geometry2(d, (size_t)L.nstate * sizeof(T), 0, B, 4, 2);
+  brbd_status st = BRBD_OK;
+  // per-thread persistent store (J, a_bias, U Dinv, Dinv, u of every joint), [slot][thread]
+  st = ensure_work(d, (size_t)g.grid * g.warps * 32 * (size_t)t.pslots * sizeof(T));
   if (st != BRBD_OK) return st;
-  aba_kernel<T><<<g.grid, g.warps_per_cta * 32, g.dyn_bytes, d.s()>>>(dev_model<T>(d), q, ldq, v, ldv, tau, ldtau, a, lda, B);
+#define BRBD_LAUNCH(NT)                                                                              \
+  {                                                                                                  \
+    st = set_smem(aba_dfs_kernel<T, NT>, g.dyn_bytes);                                               \
+    if (st != BRBD_OK) return st;                                                                    \
+    aba_dfs_kernel<T, NT><<<g.grid, NT, g.dyn_bytes, d.s()>>>(t, L, q, ldq, v, ldv, tau, ldtau, a, lda, (T *)d.work, B); \
+  }
+  BRBD_SWITCH_WARPS(g.warps)
+#undef BRBD_LAUNCH
   p->launches += 1;
   CUDA_TRY(cudaGetLastError());
   return BRBD_OK;
@@ -210,12 +267,19 @@ brbd_status launch_aba(brbd_pool * p, DeviceCtx & d, const T * q, int64_t ldq, c
 template<class T>
 brbd_status launch_crba(brbd_pool * p, DeviceCtx & d, const T * q, int64_t ldq, T * Mout, int64_t ldM, int64_t B)
 {
-  const ModelPOD<double> & M = p->model.pd;
-  const size_t per_warp = (size_t)32 * ((M.nq | 1) + (M.nv | 1)) * sizeof(T);
-  const Geometry g = pick_geometry(d, per_warp, sizeof(ModelPOD<T>), B, 16, 16);
-  brbd_status st = set_smem(crba_kernel<T>, g.dyn_bytes);
-  if (st != BRBD_OK) return st;
-  crba_kernel<T><<<g.grid, g.warps_per_cta * 32, g.dyn_bytes, d.s()>>>(dev_model<T>(d), q, ldq, Mout, ldM, B);
+  const TreePOD<T> & t = tree_of<T>(p);
+  const CrbaLayout L = crba_layout(t.maxpathdof, t.maxdepth, t.nbranch, t.nv);
+  const Geometry2 g = pick_geometry2(d, (size_t)L.nstate * sizeof(T), (size_t)32 * L.epad * sizeof(T), B, 4, 2);
+  if (ldM >= (int64_t(1) << 25)) return fail(BRBD_EINVAL, "crba: leading dimension of M too large");
+  brbd_status st = BRBD_OK;
+#define BRBD_LAUNCH(NT)                                                                              \
+  {                                                                                                  \
+    st = set_smem(crba_dfs_kernel<T, NT>, g.dyn_bytes);                                              \
+    if (st != BRBD_OK) return st;                                                                    \
+    crba_dfs_kernel<T, NT><<<g.grid, NT, g.dyn_bytes, d.s()>>>(t, L, q, ldq, Mout, ldM, B);          \
+  }
+  BRBD_SWITCH_WARPS(g.warps)
+#undef BRBD_LAUNCH
   p->launches += 1;
   CUDA_TRY(cudaGetLastError());
   return BRBD_OK;
@@ -497,6 +561,13 @@ brbd_status brbd_model_create(const brbd_flat_model * f, brbd_model ** out)
   for (int k = 0; k < f->nv; ++k) P.armature[k] = f->armature[k];
   for (int k = 0; k < 3; ++k) P.gravity[k] = f->gravity[k];
   fill_pod(m->pf, P);
+  build_tree(P, m->td);
+  build_tree(P, m->tf);
+  if (m->td.maxpathdof > MAXPATH)
+  {
+    delete m;
+    return fail(BRBD_ETOPOLOGY, "more than " + std::to_string(MAXPATH) + " degrees of freedom on one root path");
+  }
   *out = m;
   return BRBD_OK;
 }

@@ -164,7 +164,7 @@ def _describe(x, rows: int, name: str, out: bool = False) -> _Arg:
         if out:
             raise ValueError(f"{name}: output dtype must be float64 or float32")
         arr = arr.astype(np.float64)
-    if arr.strides[0] != arr.itemsize or (arr.shape[1] > 1 and arr.strides[1] < rows * arr.itemsize):
+    if arr.size > 0 and (arr.strides[0] != arr.itemsize or (arr.shape[1] > 1 and arr.strides[1] < rows * arr.itemsize)):
         if out:
             raise ValueError(f"{name}: output must be column-major (Fortran order)")
         arr = np.asfortranarray(arr)
