@@ -268,10 +268,49 @@ template<class T>
 brbd_status launch_crba(brbd_pool * p, DeviceCtx & d, const T * q, int64_t ldq, T * Mout, int64_t ldM, int64_t B)
 {
   const TreePOD<T> & t = tree_of<T>(p);
-  const CrbaLayout L = crba_layout(t.maxpathdof, t.maxdepth, t.nbranch, t.nv);
-  const Geometry2 g = pick_geometry2(d, (size_t)L.nstate * sizeof(T), (size_t)32 * L.epad * sizeof(T), B, 4, 2);
   if (ldM >= (int64_t(1) << 25)) return fail(BRBD_EINVAL, "crba: leading dimension of M too large");
   brbd_status st = BRBD_OK;
+  // preferred: oYcrb / oMi stacks in tensor memory (<= 8 warps per CTA, one CTA per SM)
+  {
+    const int wpv = (int)(sizeof(T) / 4);
+    CrbaTmemLayout L = crba_tmem_layout<T>(t.maxpathdof, t.maxdepth, t.nbranch, t.nv, 4);
+    const int cols_per_slice = L.tvals * wpv;
+    const int max_warps_tmem = cols_per_slice <= 256 ? 8 : (cols_per_slice <= 512 ? 4 : 0);
+    if (max_warps_tmem > 0)
+    {
+      Geometry2 g = pick_geometry2(d, (size_t)L.nstate * sizeof(T), (size_t)32 * L.epad * sizeof(T), B, max_warps_tmem, 1);
+      // the element -> configuration table of the emitter (32 * nv bytes) sits after the warp regions
+      while (g.warps > 1 && (size_t)g.warps * (32 * (size_t)L.nstate * sizeof(T) + 32 * (size_t)L.epad * sizeof(T)) + 32 * (size_t)t.nv + 64 > (size_t)d.max_smem_optin) --g.warps;
+      g.dyn_bytes = (size_t)g.warps * (32 * (size_t)L.nstate * sizeof(T) + 32 * (size_t)L.epad * sizeof(T)) + 32 * (size_t)t.nv;
+      const int64_t ctas_needed = (B + g.warps * 32 - 1) / (g.warps * 32);
+      g.grid = (int)std::max<int64_t>(1, std::min<int64_t>(ctas_needed, (int64_t)d.sm_count));
+      L = crba_tmem_layout<T>(t.maxpathdof, t.maxdepth, t.nbranch, t.nv, g.warps);
+#define BRBD_LAUNCH(NT)                                                                              \
+  {                                                                                                  \
+    st = set_smem(crba_tmem_kernel<T, NT>, g.dyn_bytes);                                             \
+    if (st != BRBD_OK) return st;                                                                    \
+    crba_tmem_kernel<T, NT><<<g.grid, NT, g.dyn_bytes, d.s()>>>(t, L, q, ldq, Mout, ldM, B);         \
+  }
+      switch (g.warps)
+      {
+      case 1: BRBD_LAUNCH(32) break;
+      case 2: BRBD_LAUNCH(64) break;
+      case 3: BRBD_LAUNCH(96) break;
+      case 4: BRBD_LAUNCH(128) break;
+      case 5: BRBD_LAUNCH(160) break;
+      case 6: BRBD_LAUNCH(192) break;
+      case 7: BRBD_LAUNCH(224) break;
+      default: BRBD_LAUNCH(256) break;
+      }
+#undef BRBD_LAUNCH
+      p->launches += 1;
+      CUDA_TRY(cudaGetLastError());
+      return BRBD_OK;
+    }
+  }
+  // fallback for very deep trees: all state in shared memory
+  const CrbaLayout L = crba_layout(t.maxpathdof, t.maxdepth, t.nbranch, t.nv);
+  const Geometry2 g = pick_geometry2(d, (size_t)L.nstate * sizeof(T), (size_t)32 * L.epad * sizeof(T) + 32 * t.nv, B, 4, 2);
 #define BRBD_LAUNCH(NT)                                                                              \
   {                                                                                                  \
     st = set_smem(crba_dfs_kernel<T, NT>, g.dyn_bytes);                                              \
