@@ -245,9 +245,32 @@ brbd_status launch_aba(brbd_pool * p, DeviceCtx & d, const T * q, int64_t ldq, c
                        int64_t ldtau, T * a, int64_t lda, int64_t B)
 {
   const TreePOD<T> & t = tree_of<T>(p);
+  brbd_status st = BRBD_OK;
+  // preferred: per-depth (Y, f, a_bias) in tensor memory, J of the root path + branch slots in shared memory
+  {
+    AbaTmemLayout L = aba_tmem_layout<T>(t.maxpathdof, t.maxdepth, t.nbranch, 4);
+    if (L.tvals * (int)(sizeof(T) / 4) <= 512)
+    {
+      const Geometry2 g = pick_geometry2(d, (size_t)L.nstate * sizeof(T), 0, B, 4, 1);
+      L = aba_tmem_layout<T>(t.maxpathdof, t.maxdepth, t.nbranch, g.warps);
+      st = ensure_work(d, (size_t)g.grid * g.warps * 32 * (size_t)t.pslots * sizeof(T));
+      if (st != BRBD_OK) return st;
+#define BRBD_LAUNCH(NT)                                                                              \
+  {                                                                                                  \
+    st = set_smem(aba_tmem_kernel<T, NT>, g.dyn_bytes);                                              \
+    if (st != BRBD_OK) return st;                                                                    \
+    aba_tmem_kernel<T, NT><<<g.grid, NT, g.dyn_bytes, d.s()>>>(t, L, q, ldq, v, ldv, tau, ldtau, a, lda, (T *)d.work, B); \
+  }
+      BRBD_SWITCH_WARPS(g.warps)
+#undef BRBD_LAUNCH
+      p->launches += 1;
+      CUDA_TRY(cudaGetLastError());
+      return BRBD_OK;
+    }
+  }
+  // fallback for very deep trees: per-depth state in shared memory
   const AbaLayout L = aba_layout(t.maxdepth, t.nbranch);
   const Geometry2 g = pick_geometry2(d, (size_t)L.nstate * sizeof(T), 0, B, 4, 2);
-  brbd_status st = BRBD_OK;
   // per-thread persistent store (J, a_bias, U Dinv, Dinv, u of every joint), [slot][thread]
   st = ensure_work(d, (size_t)g.grid * g.warps * 32 * (size_t)t.pslots * sizeof(T));
   if (st != BRBD_OK) return st;
