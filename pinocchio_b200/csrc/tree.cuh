@@ -137,6 +137,19 @@ template<class T, class S> BRBD_DI Inertia<T> get_inertia(const S & s, int o)
   return Y;
 }
 
+// ---- per-thread asynchronous prefetch: one element global -> this thread's shared slot (LDGSTS) -------------
+// Prefetching into registers does not survive the register pressure of the sweeps (the compiler spills the
+// loaded value at once, which waits for the load); cp.async needs no register and no scoreboard wait.
+template<class T> BRBD_DI void async_fetch(T * smem_dst, const T * __restrict__ gsrc)
+{
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+  if constexpr (sizeof(T) == 8) asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gsrc) : "memory");
+  else asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(gsrc) : "memory");
+}
+BRBD_DI void async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+BRBD_DI void async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+template<int N> BRBD_DI void async_wait_group() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
 // ---- constants of joint i out of the parameter bank ---------------------------------------------------
 template<class T> BRBD_DI SE3<T> tree_placement(const TreePOD<T> & m, int i)
 {
