@@ -134,6 +134,13 @@ brbd_status brbd_aba_derivatives_batch(brbd_pool * p, const void * q, int64_t ld
                                        void * ddq_dtau, int64_t ld_dtau, void * ddq, int64_t ldddq,
                                        int64_t batch, int flags);
 
+/* Page-lock caller-owned host memory (cudaHostRegister / cudaHostUnregister).  Host-pointer calls work on
+ * pageable memory too, but only pinned memory reaches the full link bandwidth (measured on this pool's
+ * B200 hosts: 57 GB/s pinned vs 11-22 GB/s pageable) and lets the upload / compute / download pipeline of a
+ * call overlap.  An Eigen::MatrixXd that is reused across calls should be registered once. */
+brbd_status brbd_host_register(void * ptr, uint64_t bytes);
+brbd_status brbd_host_unregister(void * ptr);
+
 /* Register-resident DFMA loop; returns achieved FP64 FLOP/s on the pool's device 0
  * (SURVEY.md §7 hard part 4: the FP64 roofline denominator is measured, not assumed). */
 brbd_status brbd_measure_fp64_peak(brbd_pool * p, double * flops_per_s, double * elapsed_ms);

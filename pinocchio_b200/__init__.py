@@ -11,6 +11,6 @@ from .model import (JOINT_FREEFLYER, JOINT_PLANAR, JOINT_PX, JOINT_PY, JOINT_PZ,
 from .joint_configuration import (LibcRand, batched_random_configuration, batched_random_tangent, integrate,  # noqa: F401
                                   neutral, randomConfiguration)
 from .pool import (ModelPool, abaInParallel, computeABADerivativesInParallel, computeRNEADerivativesInParallel,  # noqa: F401
-                   crbaInParallel, rneaInParallel)
+                   crbaInParallel, pin_host, rneaInParallel, unpin_host)
 
 __version__ = "0.1.0"

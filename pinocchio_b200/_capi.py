@@ -24,6 +24,7 @@ SYMBOLS = [
     "brbd_pool_size", "brbd_pool_update", "brbd_pool_set_stream", "brbd_pool_synchronize",
     "brbd_pool_launch_count", "brbd_pool_last_kernel_ms", "brbd_rnea_batch", "brbd_aba_batch", "brbd_crba_batch",
     "brbd_rnea_derivatives_batch", "brbd_aba_derivatives_batch", "brbd_measure_fp64_peak",
+    "brbd_host_register", "brbd_host_unregister",
 ]
 
 
@@ -81,6 +82,8 @@ def lib():
     L.brbd_crba_batch.argtypes = [vp, vp, i64, vp, i64, i64, ci]
     L.brbd_rnea_derivatives_batch.argtypes = [vp, vp, i64, vp, i64, vp, i64, vp, i64, vp, i64, vp, i64, vp, i64, i64, ci]
     L.brbd_aba_derivatives_batch.argtypes = [vp, vp, i64, vp, i64, vp, i64, vp, i64, vp, i64, vp, i64, vp, i64, i64, ci]
+    L.brbd_host_register.argtypes = [vp, ctypes.c_uint64]
+    L.brbd_host_unregister.argtypes = [vp]
     L.brbd_measure_fp64_peak.argtypes = [vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)]
     _lib = L
     return L

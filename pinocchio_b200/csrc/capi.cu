@@ -91,9 +91,14 @@ struct DeviceCtx
   ModelPOD<double> * d_pd = nullptr;
   ModelPOD<float> * d_pf = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-  // grow-only staging for host-pointer calls
-  void * stage[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-  size_t stage_bytes[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  // host-pointer calls: copy-in / copy-out streams beside the compute stream, and grow-only staging,
+  // double-buffered (slot = 2 * argument + buffer) so that chunk k+1 uploads and chunk k-1 downloads
+  // while chunk k computes
+  cudaStream_t s_in = nullptr, s_out = nullptr;
+  cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_k[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
+  void * stage[16] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr,
+                      nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  size_t stage_bytes[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
   // grow-only device workspace (intermediates of aba-derivatives)
   void * work = nullptr;
   size_t work_bytes = 0;
@@ -450,54 +455,89 @@ brbd_status run_call(brbd_pool * p, std::vector<Arg> & args, int64_t B, int flag
     }
     return BRBD_OK;
   }
-  // host pointers: shard columns contiguously over the devices, stage through device buffers
+  // host pointers: shard columns contiguously over the devices; every shard moves through the device in
+  // chunks on three streams (upload | kernels | download) with double-buffered staging
   const int nd = (int)p->devs.size();
   const int64_t per = (B + nd - 1) / nd;
   if (args.size() > 8) return fail(BRBD_EINVAL, "too many arguments");
-  for (int g = 0; g < nd; ++g)
+  size_t bytes_per_col = 0;
+  for (const Arg & a : args)
+    if (a.in || a.out) bytes_per_col += (size_t)a.rows * sizeof(T);
+  // chunk: about 48 MB of traffic, a multiple of 1024 columns, at least 4096 columns
+  int64_t chunk = (int64_t)((48u << 20) / std::max<size_t>(bytes_per_col, 1));
+  chunk = std::max<int64_t>(4096, (chunk / 1024) * 1024);
+  const std::vector<Arg> saved = args;
+  brbd_status result = BRBD_OK;
+  for (int g = 0; g < nd && result == BRBD_OK; ++g)
   {
     const int64_t c0 = (int64_t)g * per, c1 = std::min<int64_t>(B, c0 + per);
     if (c0 >= c1) break;
-    const int64_t nb = c1 - c0;
     DeviceCtx & d = p->devs[g];
     CUDA_TRY(cudaSetDevice(d.dev));
-    std::vector<void *> ptrs(args.size(), nullptr);
+    const bool user = d.use_user_stream;
+    d.use_user_stream = false; // kernels of host-pointer calls run on the pool's own stream
+    const int64_t cw = std::min<int64_t>(chunk, c1 - c0);
     for (size_t k = 0; k < args.size(); ++k)
+      if (args[k].in || args[k].out)
+        for (int b = 0; b < 2; ++b)
+        {
+          brbd_status st = ensure_stage(d, (int)(2 * k + b), (size_t)args[k].rows * cw * sizeof(T));
+          if (st != BRBD_OK) { d.use_user_stream = user; return st; }
+        }
+    int it = 0;
+    for (int64_t b0 = c0; b0 < c1; b0 += cw, ++it)
     {
-      const Arg & a = args[k];
-      if (!a.in && !a.out) continue;
-      const size_t bytes = (size_t)a.rows * nb * sizeof(T);
-      brbd_status st = ensure_stage(d, (int)k, bytes);
-      if (st != BRBD_OK) return st;
-      ptrs[k] = d.stage[k];
-      if (a.in)
+      const int buf = it & 1;
+      const int64_t nb = std::min<int64_t>(cw, c1 - b0);
+      std::vector<void *> ptrs(args.size(), nullptr);
+      // upload may start once the kernel that read this input buffer two chunks ago is done
+      if (it >= 2) CUDA_TRY(cudaStreamWaitEvent(d.s_in, d.ev_k[buf], 0));
+      for (size_t k = 0; k < args.size(); ++k)
       {
-        const T * src = static_cast<const T *>(a.in) + c0 * a.ld;
-        CUDA_TRY(cudaMemcpy2DAsync(d.stage[k], a.rows * sizeof(T), src, a.ld * sizeof(T), a.rows * sizeof(T), nb,
-                                   cudaMemcpyHostToDevice, d.stream));
+        const Arg & a = saved[k];
+        if (!a.in && !a.out) continue;
+        ptrs[k] = d.stage[2 * k + buf];
+        if (!a.in) continue;
+        const T * src = static_cast<const T *>(a.in) + b0 * a.ld;
+        // dense blocks (ld == rows, the Eigen::MatrixXd case) move as ONE copy: a pitched copy of many short
+        // rows runs at a fraction of the link bandwidth
+        if (a.ld == a.rows) CUDA_TRY(cudaMemcpyAsync(ptrs[k], src, (size_t)a.rows * nb * sizeof(T), cudaMemcpyHostToDevice, d.s_in));
+        else
+          CUDA_TRY(cudaMemcpy2DAsync(ptrs[k], a.rows * sizeof(T), src, a.ld * sizeof(T), a.rows * sizeof(T), nb,
+                                     cudaMemcpyHostToDevice, d.s_in));
       }
+      CUDA_TRY(cudaEventRecord(d.ev_in[buf], d.s_in));
+      CUDA_TRY(cudaStreamWaitEvent(d.stream, d.ev_in[buf], 0));
+      // the kernel overwrites the output buffer whose download was queued two chunks ago
+      if (it >= 2) CUDA_TRY(cudaStreamWaitEvent(d.stream, d.ev_out[buf], 0));
+      for (size_t k = 0; k < args.size(); ++k) args[k].ld = args[k].rows; // staged blocks are dense
+      result = launch(d, ptrs, nb);
+      args = saved;
+      if (result != BRBD_OK) break;
+      CUDA_TRY(cudaEventRecord(d.ev_k[buf], d.stream));
+      CUDA_TRY(cudaStreamWaitEvent(d.s_out, d.ev_k[buf], 0));
+      for (size_t k = 0; k < args.size(); ++k)
+      {
+        const Arg & a = saved[k];
+        if (!a.out) continue;
+        T * dst = static_cast<T *>(a.out) + b0 * a.ld;
+        if (a.ld == a.rows) CUDA_TRY(cudaMemcpyAsync(dst, ptrs[k], (size_t)a.rows * nb * sizeof(T), cudaMemcpyDeviceToHost, d.s_out));
+        else
+          CUDA_TRY(cudaMemcpy2DAsync(dst, a.ld * sizeof(T), ptrs[k], a.rows * sizeof(T), a.rows * sizeof(T), nb,
+                                     cudaMemcpyDeviceToHost, d.s_out));
+      }
+      CUDA_TRY(cudaEventRecord(d.ev_out[buf], d.s_out));
     }
-    // staged blocks are dense: ld == rows
-    std::vector<Arg> saved = args;
-    for (size_t k = 0; k < args.size(); ++k) args[k].ld = args[k].rows;
-    brbd_status st = launch(d, ptrs, nb);
-    args = saved;
-    if (st != BRBD_OK) return st;
-    for (size_t k = 0; k < args.size(); ++k)
-    {
-      const Arg & a = args[k];
-      if (!a.out) continue;
-      T * dst = static_cast<T *>(a.out) + c0 * a.ld;
-      CUDA_TRY(cudaMemcpy2DAsync(dst, a.ld * sizeof(T), d.stage[k], a.rows * sizeof(T), a.rows * sizeof(T), nb,
-                                 cudaMemcpyDeviceToHost, d.stream));
-    }
+    d.use_user_stream = user;
   }
   for (int g = 0; g < nd; ++g)
   {
     CUDA_TRY(cudaSetDevice(p->devs[g].dev));
+    CUDA_TRY(cudaStreamSynchronize(p->devs[g].s_in));
     CUDA_TRY(cudaStreamSynchronize(p->devs[g].stream));
+    CUDA_TRY(cudaStreamSynchronize(p->devs[g].s_out));
   }
-  return BRBD_OK;
+  return result;
 }
 
 __global__ void fp64_peak_kernel(double * out, int iters)
@@ -656,7 +696,15 @@ void brbd_pool_destroy(brbd_pool * p)
   {
     if (cudaSetDevice(d.dev) != cudaSuccess) continue;
     if (d.stream) cudaStreamSynchronize(d.stream);
-    for (int k = 0; k < 8; ++k) if (d.stage[k]) cudaFree(d.stage[k]);
+    for (int k = 0; k < 16; ++k) if (d.stage[k]) cudaFree(d.stage[k]);
+    for (int b = 0; b < 2; ++b)
+    {
+      if (d.ev_in[b]) cudaEventDestroy(d.ev_in[b]);
+      if (d.ev_k[b]) cudaEventDestroy(d.ev_k[b]);
+      if (d.ev_out[b]) cudaEventDestroy(d.ev_out[b]);
+    }
+    if (d.s_in) cudaStreamDestroy(d.s_in);
+    if (d.s_out) cudaStreamDestroy(d.s_out);
     if (d.work) cudaFree(d.work);
     if (d.d_pd) cudaFree(d.d_pd);
     if (d.d_pf) cudaFree(d.d_pf);
@@ -705,6 +753,14 @@ brbd_status brbd_pool_create(const brbd_model * m, const int * device_ids, int n
       d.sm_count = prop.multiProcessorCount;
       d.max_smem_optin = (int)prop.sharedMemPerBlockOptin;
       tryc(cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking), "cudaStreamCreate");
+      tryc(cudaStreamCreateWithFlags(&d.s_in, cudaStreamNonBlocking), "cudaStreamCreate");
+      tryc(cudaStreamCreateWithFlags(&d.s_out, cudaStreamNonBlocking), "cudaStreamCreate");
+      for (int b = 0; b < 2; ++b)
+      {
+        tryc(cudaEventCreateWithFlags(&d.ev_in[b], cudaEventDisableTiming), "cudaEventCreate");
+        tryc(cudaEventCreateWithFlags(&d.ev_k[b], cudaEventDisableTiming), "cudaEventCreate");
+        tryc(cudaEventCreateWithFlags(&d.ev_out[b], cudaEventDisableTiming), "cudaEventCreate");
+      }
       tryc(cudaEventCreate(&d.ev0), "cudaEventCreate");
       tryc(cudaEventCreate(&d.ev1), "cudaEventCreate");
       tryc(cudaMalloc(&d.d_pd, sizeof(ModelPOD<double>)), "cudaMalloc");
@@ -828,6 +884,19 @@ brbd_status brbd_aba_derivatives_batch(brbd_pool * p, const void * q, int64_t ld
                                          args[2].ld, (T *)P[3], args[3].ld, (T *)P[4], args[4].ld, (T *)P[5], args[5].ld,
                                          (T *)P[6], args[6].ld, B);
            })));
+}
+
+brbd_status brbd_host_register(void * ptr, uint64_t bytes)
+{
+  if (!ptr || bytes == 0) return fail(BRBD_EINVAL, "null host block");
+  CUDA_TRY(cudaHostRegister(ptr, (size_t)bytes, cudaHostRegisterPortable));
+  return BRBD_OK;
+}
+brbd_status brbd_host_unregister(void * ptr)
+{
+  if (!ptr) return fail(BRBD_EINVAL, "null host block");
+  CUDA_TRY(cudaHostUnregister(ptr));
+  return BRBD_OK;
 }
 
 brbd_status brbd_measure_fp64_peak(brbd_pool * p, double * flops_per_s, double * elapsed_ms)

@@ -209,6 +209,17 @@ def _call(pool: ModelPool, fn_name: str, ins, outs, async_: bool = False):
         _raise(e)
 
 
+def pin_host(array: np.ndarray) -> np.ndarray:
+    """Page-lock a caller-owned numpy block in place (brbd_host_register); returns it.  Host-pointer calls on
+    pinned blocks run at the full PCIe rate and overlap upload / compute / download."""
+    _capi.check(_capi.lib().brbd_host_register(ctypes.c_void_p(array.ctypes.data), ctypes.c_uint64(array.nbytes)))
+    return array
+
+
+def unpin_host(array: np.ndarray) -> None:
+    _capi.check(_capi.lib().brbd_host_unregister(ctypes.c_void_p(array.ctypes.data)))
+
+
 def _check_pool(num_threads: int, pool: ModelPool):
     # parallel/rnea.hpp:52-54 — the GPU pool has no per-thread replicas, so only emptiness is checked
     if pool.size() <= 0:
