@@ -27,6 +27,7 @@
 #include "engine.cuh"
 #include "rnea.cuh"
 #include "rnea_derivatives.cuh"
+#include "deriv_coop.cuh"
 #include "rnea_dfs.cuh"
 #include "tree.cuh"
 
@@ -76,6 +77,7 @@ struct brbd_model
   ModelPOD<float> pf;
   TreePOD<double> td; // v2 kernels: passed by value as a __grid_constant__ kernel parameter
   TreePOD<float> tf;
+  CoopTables coop; // warp-cooperative derivative kernels: level lists, ancestor masks
 };
 
 namespace
@@ -352,18 +354,50 @@ brbd_status launch_crba(brbd_pool * p, DeviceCtx & d, const T * q, int64_t ldq, 
   return BRBD_OK;
 }
 
+// Launch geometry of the warp-cooperative kernels: G lanes per configuration, `per_group` elements of shared
+// memory per configuration, one CTA per SM with as many warps as fit (<= 8), persistent grid.
+struct GeometryCoop
+{
+  int warps, grid;
+  size_t dyn_bytes;
+};
+inline int coop_group_size(int nv) { return nv <= 8 ? 8 : (nv <= 16 ? 16 : 32); }
+GeometryCoop pick_geometry_coop(const DeviceCtx & d, size_t group_bytes, int G, size_t static_bytes, int64_t batch)
+{
+  const size_t per_warp = group_bytes * (size_t)(32 / G);
+  const size_t cap = (size_t)d.max_smem_optin - static_bytes;
+  GeometryCoop g;
+  g.warps = (int)std::max<size_t>(1, std::min<size_t>(8, cap / per_warp));
+  g.dyn_bytes = (size_t)g.warps * per_warp;
+  const int64_t per_cta = (int64_t)g.warps * (32 / G);
+  g.grid = (int)std::max<int64_t>(1, std::min<int64_t>((batch + per_cta - 1) / per_cta, (int64_t)d.sm_count));
+  return g;
+}
+
 template<class T>
 brbd_status launch_rnea_derivs(brbd_pool * p, DeviceCtx & d, const T * q, int64_t ldq, const T * v, int64_t ldv,
                                const T * a, int64_t lda, T * dq, int64_t ld_dq, T * dv, int64_t ld_dv, T * da,
                                int64_t ld_da, T * tau, int64_t ldtau, int64_t B)
 {
   const ModelPOD<double> & M = p->model.pd;
-  const size_t per_warp = (size_t)32 * ((M.nq | 1) + 5 * (M.nv | 1)) * sizeof(T);
-  const Geometry g = pick_geometry(d, per_warp, sizeof(ModelPOD<T>), B, 16, 16);
-  brbd_status st = set_smem(rnea_derivatives_kernel<T>, g.dyn_bytes);
-  if (st != BRBD_OK) return st;
-  rnea_derivatives_kernel<T><<<g.grid, g.warps_per_cta * 32, g.dyn_bytes, d.s()>>>(
-    dev_model<T>(d), q, ldq, v, ldv, a, lda, dq, ld_dq, dv, ld_dv, da, ld_da, tau, ldtau, B);
+  const CoopLayout L = coop_layout(M.nq, M.nv, M.njoints);
+  const int G = coop_group_size(M.nv);
+  const size_t static_bytes = sizeof(ModelPOD<T>) + sizeof(CoopTables) + 1024;
+  const GeometryCoop g = pick_geometry_coop(d, (size_t)L.per_group * sizeof(T), G, static_bytes, B);
+  if (g.dyn_bytes + static_bytes > (size_t)d.max_smem_optin + 1024)
+    return fail(BRBD_EINVAL, "computeRNEADerivatives: model too large for the shared-memory state of one configuration");
+  brbd_status st = BRBD_OK;
+#define BRBD_LAUNCH_COOP(GG)                                                                                     \
+  {                                                                                                              \
+    st = set_smem(rnea_derivatives_coop_kernel<T, GG>, g.dyn_bytes);                                             \
+    if (st != BRBD_OK) return st;                                                                                \
+    rnea_derivatives_coop_kernel<T, GG><<<g.grid, g.warps * 32, g.dyn_bytes, d.s()>>>(                           \
+      dev_model<T>(d), p->model.coop, L, q, ldq, v, ldv, a, lda, dq, ld_dq, dv, ld_dv, da, ld_da, tau, ldtau, B); \
+  }
+  if (G == 8) BRBD_LAUNCH_COOP(8)
+  else if (G == 16) BRBD_LAUNCH_COOP(16)
+  else BRBD_LAUNCH_COOP(32)
+#undef BRBD_LAUNCH_COOP
   p->launches += 1;
   CUDA_TRY(cudaGetLastError());
   return BRBD_OK;
@@ -665,6 +699,7 @@ brbd_status brbd_model_create(const brbd_flat_model * f, brbd_model ** out)
   fill_pod(m->pf, P);
   build_tree(P, m->td);
   build_tree(P, m->tf);
+  build_coop_tables(P, m->coop);
   if (m->td.maxpathdof > MAXPATH)
   {
     delete m;

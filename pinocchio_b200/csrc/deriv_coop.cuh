@@ -1,0 +1,401 @@
+// deriv_coop.cuh — batched computeRNEADerivatives, warp-cooperative: G lanes work on ONE configuration.
+//
+// Why not one configuration per thread (rnea_derivatives.cuh, v1): the backward sweep of
+// impl::computeRNEADerivatives (reference: include/pinocchio/algorithm/rnea-derivatives.hxx:378-459) needs, for
+// every column, the J / dFda / dYtJ columns of the whole subtree and the root path — about 25 KB of FP64 state
+// per configuration for a humanoid.  Per thread that is thread-local memory (v1: 6.9 ms for 65 536
+// configurations of simple_humanoid, 4 % of the HBM roofline); per warp it fits in shared memory, and the
+// work inside one configuration is wide enough for 32 lanes:
+//
+//   phase 1  level-synchronous forward kinematics (lanes = joints of one tree level):
+//            oMi, J = oMi.act(S), ov, oa_gf                       rnea-derivatives.hxx:280-317 (world-frame form)
+//   phase 2  lanes = joints: oYcrb = oMi.act(I), oh, of, doYcrb    :303-317, :335-351
+//   phase 3  lanes = components: subtree sums of (oYcrb, doYcrb, of) — the `[parent] +=` of :452-456; the
+//            inertia is kept in its linear form (m, m c, I about the origin) so that the sum is a plain sum
+//   phase 4  lanes = tangent columns: dVdq, dAdq, dAdv (:319-332), dFda, dFdq, dFdv, dYtJ (:412-431), tau (:409)
+//   phase 5  lanes = matrix rows: every entry of dtau_dq / dtau_dv / dtau_da is one or two 6-D dot products of
+//            a row record and a column record (:420-451); rows of a column are contiguous in the caller's
+//            col-major matrix, so each column leaves with one coalesced store per matrix, zeros included
+//            (the reference requires pre-zeroed outputs, rnea-derivatives.hpp:104-106).
+//
+// Small models use sub-warp groups (G = 8 or 16 lanes per configuration, 4 or 2 configurations per warp).
+#pragma once
+
+#include "engine.cuh"
+#include "rnea.cuh"
+#include "rnea_derivatives.cuh"
+
+namespace brbd
+{
+
+// lane-varying lookups (kept in shared memory; the constant bank serialises divergent indices)
+struct CoopTables
+{
+  short lvl_start[MAXDEPTH + 2]; // joints of depth l are lvl_joint[lvl_start[l] .. lvl_start[l + 1])
+  short lvl_joint[MAXJ];
+  unsigned long long anc_mask[MAXNV]; // bit r: row r belongs to an ancestor-or-self joint of the joint owning this column
+};
+inline void build_coop_tables(const ModelPOD<double> & M, CoopTables & C)
+{
+  memset(&C, 0, sizeof(C));
+  int n = 0;
+  for (int l = 1; l <= M.maxdepth; ++l)
+  {
+    C.lvl_start[l] = (short)n;
+    for (int i = 1; i < M.njoints; ++i)
+      if (M.depth[i] == l) C.lvl_joint[n++] = (short)i;
+  }
+  for (int l = M.maxdepth + 1; l < MAXDEPTH + 2; ++l) C.lvl_start[l] = (short)n;
+  for (int i = 1; i < M.njoints; ++i)
+  {
+    unsigned long long mask = 0;
+    for (int a = i; a > 0; a = M.parent[a])
+      for (int k = 0; k < M.nvj[a]; ++k) mask |= 1ull << (M.idx_v[a] + k);
+    for (int k = 0; k < M.nvj[i]; ++k) C.anc_mask[M.idx_v[i] + k] = mask;
+  }
+}
+
+// Per-joint record (JR_STRIDE values, odd => lanes = joints are conflict-free):
+//   [0] m  [1..3] h = m c  [4..9] I about the world origin (xx,xy,yy,xz,yz,zz)   <- summed over the subtree
+//   [10..36] doYcrb (LA, AL, AA)                                                 <- summed (oMi sits here until phase 2)
+//   [37..42] of                                                                  <- summed
+//   [43..48] ov   [49..54] oa_gf
+constexpr int JR_STRIDE = 55, JR_DY = 10, JR_OF = 37, JR_OV = 43, JR_OA = 49, JR_NSUM = 43;
+// Per-column record (CB_STRIDE values, even => 16-byte aligned pairs):
+constexpr int CB_STRIDE = 54, CB_DFDQ = 0, CB_DFDQP = 6, CB_DFDV = 12, CB_DFDA = 18, CB_DADQ = 24, CB_DVDQ = 30,
+              CB_DADV = 36, CB_J = 42, CB_DYTJ = 48;
+
+struct CoopLayout
+{
+  int oq, ov, oa, ojr, ocb; // offsets (elements) inside one group's region
+  int per_group;            // elements, even
+};
+inline CoopLayout coop_layout(int nq, int nv, int nj)
+{
+  CoopLayout L;
+  L.ocb = 0;
+  L.ojr = L.ocb + CB_STRIDE * nv;
+  L.oq = L.ojr + JR_STRIDE * nj;
+  L.ov = L.oq + nq;
+  L.oa = L.ov + nv;
+  L.per_group = (L.oa + nv + 1) & ~1;
+  return L;
+}
+
+template<class T> struct Pair;
+template<> struct Pair<double> { typedef double2 type; };
+template<> struct Pair<float> { typedef float2 type; };
+// 6 values from an address that is aligned to 2 elements
+template<class T> BRBD_DI void ld6(const T * p, T * x)
+{
+  typedef typename Pair<T>::type P;
+  const P * q = reinterpret_cast<const P *>(p);
+  const P a = q[0], b = q[1], c = q[2];
+  x[0] = a.x; x[1] = a.y; x[2] = b.x; x[3] = b.y; x[4] = c.x; x[5] = c.y;
+}
+template<class T> BRBD_DI void st6(T * p, const T * x)
+{
+  typedef typename Pair<T>::type P;
+  P * q = reinterpret_cast<P *>(p);
+  P a, b, c;
+  a.x = x[0]; a.y = x[1]; b.x = x[2]; b.y = x[3]; c.x = x[4]; c.y = x[5];
+  q[0] = a; q[1] = b; q[2] = c;
+}
+template<class T> BRBD_DI void st6(T * p, const Motion<T> & m) { const T x[6] = {m.lin.x, m.lin.y, m.lin.z, m.ang.x, m.ang.y, m.ang.z}; st6(p, x); }
+template<class T> BRBD_DI void st6(T * p, const Force<T> & m) { const T x[6] = {m.lin.x, m.lin.y, m.lin.z, m.ang.x, m.ang.y, m.ang.z}; st6(p, x); }
+template<class T> BRBD_DI Motion<T> ld6m(const T * p) { T x[6]; ld6(p, x); Motion<T> m; m.lin = Vec3<T>(x[0], x[1], x[2]); m.ang = Vec3<T>(x[3], x[4], x[5]); return m; }
+template<class T> BRBD_DI T dot6a(const T * a, const T * b)
+{
+  return a[0] * b[0] + a[1] * b[1] + a[2] * b[2] + a[3] * b[3] + a[4] * b[4] + a[5] * b[5];
+}
+
+// composite inertia in linear form: (m, h = m c, Io = I_c - m [c]x^2)
+template<class T> struct LinInertia
+{
+  T m;
+  Vec3<T> h;
+  Sym3<T> Io;
+  BRBD_DI Force<T> operator*(const Motion<T> & v) const
+  {
+    Force<T> f;
+    f.lin = m * v.lin + cross(v.ang, h);
+    f.ang = Io.mul(v.ang) + cross(h, v.lin);
+    return f;
+  }
+};
+template<class T> BRBD_DI void store_lin_inertia(T * d, const Inertia<T> & Y)
+{
+  const T m = Y.m, cx = Y.c.x, cy = Y.c.y, cz = Y.c.z;
+  d[0] = m; d[1] = m * cx; d[2] = m * cy; d[3] = m * cz;
+  d[4] = Y.I.xx + m * (cy * cy + cz * cz);
+  d[5] = Y.I.xy - m * cx * cy;
+  d[6] = Y.I.yy + m * (cx * cx + cz * cz);
+  d[7] = Y.I.xz - m * cx * cz;
+  d[8] = Y.I.yz - m * cy * cz;
+  d[9] = Y.I.zz + m * (cx * cx + cy * cy);
+}
+template<class T> BRBD_DI LinInertia<T> load_lin_inertia(const T * d)
+{
+  LinInertia<T> Y;
+  Y.m = d[0]; Y.h = Vec3<T>(d[1], d[2], d[3]);
+  Y.Io.xx = d[4]; Y.Io.xy = d[5]; Y.Io.yy = d[6]; Y.Io.xz = d[7]; Y.Io.yz = d[8]; Y.Io.zz = d[9];
+  return Y;
+}
+
+// ---- phase 1: level-synchronous forward kinematics ------------------------------------------------------
+// oa_gf of the reference (a_i = S a + v_i x v_J + liMi^-1 a_parent, oa_gf = oMi.act(a_i) - g) in world form:
+// oa_gf_i = oa_gf_parent + J_i a_i + ov_i x (J_i v_i), oa_gf_0 = -g.
+template<class T, int G, bool WITH_ACC>
+BRBD_DI void coop_forward(const ModelPOD<T> & m, const CoopTables & tb, const T * sq, const T * sv, const T * sa, T * jr, T * cb, int gl)
+{
+  const int maxdepth = m.maxdepth;
+  for (int l = 1; l <= maxdepth; ++l)
+  {
+    const int k1 = tb.lvl_start[l + 1];
+    for (int k = tb.lvl_start[l] + gl; k < k1; k += G)
+    {
+      const int i = tb.lvl_joint[k];
+      const int type = m.type[i], parent = m.parent[i], iq = m.idx_q[i], iv = m.idx_v[i], nvj = m.nvj[i];
+      SE3<T> X = joint_liMi(m, i, type, sq + iq);
+      Motion<T> ov = mzero<T>(), oa = mzero<T>();
+      if (parent > 0)
+      {
+        const T * pr = jr + parent * JR_STRIDE;
+        X = load_se3(pr + JR_DY) * X;
+        ov = load_motion(pr + JR_OV);
+        if (WITH_ACC) oa = load_motion(pr + JR_OA);
+      }
+      else if (WITH_ACC)
+        oa.lin = Vec3<T>(-m.gravity[0], -m.gravity[1], -m.gravity[2]);
+      Motion<T> w = mzero<T>();
+      for (int kk = 0; kk < nvj; ++kk)
+      {
+        const Motion<T> J = act_S_col(X, type, kk);
+        st6(cb + (iv + kk) * CB_STRIDE + CB_J, J);
+        const T vk = sv[iv + kk];
+        w.lin += vk * J.lin; w.ang += vk * J.ang;
+        if (WITH_ACC)
+        {
+          const T ak = sa[iv + kk];
+          oa.lin += ak * J.lin; oa.ang += ak * J.ang;
+        }
+      }
+      ov += w;
+      T * r = jr + i * JR_STRIDE;
+      store_se3(r + JR_DY, X);
+      store6(r + JR_OV, ov);
+      if (WITH_ACC)
+      {
+        oa += mcross(ov, w);
+        store6(r + JR_OA, oa);
+      }
+    }
+    __syncwarp();
+  }
+}
+
+// ---- phase 2: per-joint world inertia, momentum, force, inertia variation --------------------------------
+template<class T, int G>
+BRBD_DI void coop_joint_quantities(const ModelPOD<T> & m, T * jr, int gl)
+{
+  const int nj = m.njoints;
+  for (int i = 1 + gl; i < nj; i += G)
+  {
+    T * r = jr + i * JR_STRIDE;
+    const SE3<T> X = load_se3(r + JR_DY);
+    const Motion<T> ov = load_motion(r + JR_OV), oa = load_motion(r + JR_OA);
+    const Inertia<T> Y = act(X, model_inertia(m, i));
+    const Force<T> oh = Y * ov;
+    Force<T> of = Y * oa;
+    of += fcross(ov, oh);
+    store_lin_inertia(r, Y);
+    store_dy(r + JR_DY, inertia_variation(Y, ov, oh));
+    store6(r + JR_OF, of);
+  }
+  __syncwarp();
+}
+
+// ---- phase 3: subtree sums, lanes = components ------------------------------------------------------------
+template<class T, int G>
+BRBD_DI void coop_subtree_sums(const ModelPOD<T> & m, T * jr, int gl)
+{
+  const int nj = m.njoints;
+  for (int comp = gl; comp < JR_NSUM; comp += G)
+  {
+    T carry = T(0);
+    int carry_idx = -1;
+    for (int i = nj - 1; i > 0; --i)
+    {
+      const int p = m.parent[i];
+      if (p > 0)
+      {
+        const T x = (carry_idx == i) ? carry : jr[i * JR_STRIDE + comp];
+        carry = jr[p * JR_STRIDE + comp] + x;
+        jr[p * JR_STRIDE + comp] = carry;
+        carry_idx = p;
+      }
+    }
+  }
+  __syncwarp();
+}
+
+// ---- phase 4: column records ------------------------------------------------------------------------------
+// tau_io: in = a (RNEA derivatives) and out = tau (rnea-derivatives.hxx:409 + armature :538-539); may be null.
+template<class T, int G>
+BRBD_DI void coop_columns(const ModelPOD<T> & m, const T * jr, T * cb, T * tau_io, int gl)
+{
+  const int nv = m.nv;
+  for (int c = gl; c < nv; c += G)
+  {
+    const int j = m.dof_joint[c], p = m.parent[j];
+    const T * r = jr + j * JR_STRIDE;
+    T * P = cb + c * CB_STRIDE;
+    const Motion<T> J = ld6m(P + CB_J);
+    const LinInertia<T> Y = load_lin_inertia(r);
+    const DY<T> dY = load_dy(r + JR_DY);
+    const Force<T> of = load_force(r + JR_OF);
+    const Motion<T> ovj = load_motion(r + JR_OV);
+    Motion<T> dVdq = mzero<T>(), dAdq;
+    if (p > 0)
+    {
+      const T * pr = jr + p * JR_STRIDE;
+      const Motion<T> ovp = load_motion(pr + JR_OV), oap = load_motion(pr + JR_OA);
+      dVdq = mcross(ovp, J);
+      dAdq = mcross(oap, J);
+      dAdq += mcross(ovp, dVdq);
+    }
+    else
+    {
+      Motion<T> g0 = mzero<T>();
+      g0.lin = Vec3<T>(-m.gravity[0], -m.gravity[1], -m.gravity[2]);
+      dAdq = mcross(g0, J);
+    }
+    Motion<T> dAdv = mcross(ovj, J);
+    dAdv += dVdq;
+    const Force<T> dFda = Y * J;
+    Force<T> dFdq = Y * dAdq;
+    if (p > 0) dFdq += dY.mul(dVdq);
+    Force<T> dFdv = dY.mul(J);
+    dFdv += Y * dAdv;
+    if (tau_io) tau_io[c] = dot6(J, of) + m.armature[c] * tau_io[c];
+    st6(P + CB_DFDQ, dFdq);
+    dFdq += fcross(J, of); // motionSet::act<ADDTO>(J_cols, of[i], dFdq_cols) (:440)
+    st6(P + CB_DFDQP, dFdq);
+    st6(P + CB_DFDV, dFdv);
+    st6(P + CB_DFDA, dFda);
+    st6(P + CB_DADQ, dAdq);
+    st6(P + CB_DVDQ, dVdq);
+    st6(P + CB_DADV, dAdv);
+    st6(P + CB_DYTJ, dY.tmul(J));
+  }
+  __syncwarp();
+}
+
+// ---- phase 5: matrix entries ------------------------------------------------------------------------------
+// Row block of R <= G rows x C = G / R column slices; a lane keeps its row record (J_r, dFda_r, dYtJ_r) in
+// registers and walks the columns of its slice.  Entry (r, c):
+//   r on the root path of joint(c):  J_r . dFdq_c (own joint) | J_r . dFdq_c+ (strict ancestor)        (:437-440)
+//                                    J_r . dFdv_c (:450-451),  J_r . dFda_c (:420-421, + armature on the diagonal)
+//   r in the strict subtree:         dFda_r . dAdq_c + dYtJ_r . dVdq_c (:433-435),  dFda_r . dAdv_c + dYtJ_r . J_c (:446-448)
+//   otherwise 0.
+template<class T, int G, bool WITH_DA>
+BRBD_DI void coop_entries(const ModelPOD<T> & m, const CoopTables & tb, const T * cb, T * __restrict__ gq, T * __restrict__ gv,
+                          T * __restrict__ ga, int gl, bool active)
+{
+  const int nv = m.nv;
+  for (int rb = 0; rb < nv; rb += G)
+  {
+    const int R = (nv - rb) < G ? (nv - rb) : G;
+    const int C = G / R;
+    const int rl = gl % R, slice = gl / R;
+    const int r = rb + rl;
+    const bool lane_on = slice < C;
+    T Jr[6], Fd[6], Yd[6];
+    {
+      const T * Pr = cb + r * CB_STRIDE;
+      ld6(Pr + CB_J, Jr); ld6(Pr + CB_DFDA, Fd); ld6(Pr + CB_DYTJ, Yd);
+    }
+    for (int c0 = 0; c0 < nv; c0 += C)
+    {
+      const int c = c0 + slice;
+      const bool valid = lane_on && c < nv;
+      const int cc = valid ? c : 0;
+      const int jc = m.dof_joint[cc];
+      const int ivc = m.idx_v[jc], own_end = ivc + m.nvj[jc], sub_end = ivc + m.nvsub[jc];
+      const bool own = r >= ivc && r < own_end;
+      const bool up = (tb.anc_mask[cc] >> r) & 1ull;
+      const bool low = r >= own_end && r < sub_end;
+      const T * P = cb + cc * CB_STRIDE;
+      T x[6], y[6];
+      ld6(P + (own ? CB_DFDQ : CB_DFDQP), x);
+      const T Aq = dot6a(Jr, x);
+      ld6(P + CB_DADQ, x); ld6(P + CB_DVDQ, y);
+      const T Bq = dot6a(Fd, x) + dot6a(Yd, y);
+      ld6(P + CB_DFDV, x);
+      const T Av = dot6a(Jr, x);
+      ld6(P + CB_DADV, x); ld6(P + CB_J, y);
+      const T Bv = dot6a(Fd, x) + dot6a(Yd, y);
+      const T vq = up ? Aq : (low ? Bq : T(0));
+      const T vv = up ? Av : (low ? Bv : T(0));
+      if (valid && active)
+      {
+        gq[cc * nv + r] = vq;
+        gv[cc * nv + r] = vv;
+      }
+      if (WITH_DA)
+      {
+        ld6(P + CB_DFDA, x);
+        T va = up ? dot6a(Jr, x) : T(0);
+        if (r == cc) va += m.armature[cc];
+        if (valid && active) ga[cc * nv + r] = va;
+      }
+    }
+  }
+}
+
+template<class T, int G>
+__global__ void __launch_bounds__(256, 1)
+rnea_derivatives_coop_kernel(const ModelPOD<T> * __restrict__ gm, const __grid_constant__ CoopTables gtb, const CoopLayout L,
+                             const T * __restrict__ q, int64_t ldq, const T * __restrict__ v, int64_t ldv,
+                             const T * __restrict__ a, int64_t lda, T * __restrict__ dq, int64_t ld_dq, T * __restrict__ dv,
+                             int64_t ld_dv, T * __restrict__ da, int64_t ld_da, T * __restrict__ tau, int64_t ldtau, int64_t B)
+{
+  __shared__ ModelPOD<T> m;
+  __shared__ CoopTables tb;
+  extern __shared__ __align__(16) unsigned char dyn_smem[];
+  copy_model_to_smem(&m, gm);
+  {
+    const int n = (int)(sizeof(CoopTables) / 4);
+    const int * s = reinterpret_cast<const int *>(&gtb);
+    int * d = reinterpret_cast<int *>(&tb);
+    for (int k = threadIdx.x; k < n; k += blockDim.x) d[k] = s[k];
+  }
+  __syncthreads();
+  constexpr int GPW = 32 / G; // configurations per warp
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const int gl = lane % G, grp = lane / G;
+  T * base = reinterpret_cast<T *>(dyn_smem) + (size_t)(warp * GPW + grp) * L.per_group;
+  T * sq = base + L.oq, * sv = base + L.ov, * sa = base + L.oa, * jr = base + L.ojr, * cb = base + L.ocb;
+  const int nq = m.nq, nv = m.nv;
+  const int64_t ntiles = (B + GPW - 1) / GPW;
+  for (int64_t tile = (int64_t)blockIdx.x * nw + warp; tile < ntiles; tile += (int64_t)gridDim.x * nw)
+  {
+    int64_t cfg = tile * GPW + grp;
+    const bool active = cfg < B;
+    if (!active) cfg = B - 1; // idle groups shadow the last configuration (stores suppressed)
+    const T * gq_in = q + cfg * ldq, * gv_in = v + cfg * ldv, * ga_in = a + cfg * lda;
+    for (int k = gl; k < nq; k += G) sq[k] = gq_in[k];
+    for (int k = gl; k < nv; k += G) { sv[k] = gv_in[k]; sa[k] = ga_in[k]; }
+    __syncwarp();
+    coop_forward<T, G, true>(m, tb, sq, sv, sa, jr, cb, gl);
+    coop_joint_quantities<T, G>(m, jr, gl);
+    coop_subtree_sums<T, G>(m, jr, gl);
+    coop_columns<T, G>(m, jr, cb, sa, gl);
+    coop_entries<T, G, true>(m, tb, cb, dq + cfg * ld_dq, dv + cfg * ld_dv, da + cfg * ld_da, gl, active);
+    if (tau && active)
+      for (int k = gl; k < nv; k += G) tau[cfg * ldtau + k] = sa[k];
+    __syncwarp();
+  }
+}
+
+} // namespace brbd
