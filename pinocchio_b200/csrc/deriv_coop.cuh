@@ -7,7 +7,7 @@
 // configurations of simple_humanoid, 4 % of the HBM roofline); per warp it fits in shared memory, and the
 // work inside one configuration is wide enough for 32 lanes:
 //
-//   phase 1  level-synchronous forward kinematics (lanes = joints of one tree level):
+//   phase 1  forward kinematics by pointer jumping along the root paths (lanes = joints, log2(depth) rounds):
 //            oMi, J = oMi.act(S), ov, oa_gf                       rnea-derivatives.hxx:280-317 (world-frame form)
 //   phase 2  lanes = joints: oYcrb = oMi.act(I), oh, of, doYcrb    :303-317, :335-351
 //   phase 3  lanes = components: subtree sums of (oYcrb, doYcrb, of) — the `[parent] +=` of :452-456; the
@@ -34,6 +34,9 @@ struct CoopTables
   short lvl_start[MAXDEPTH + 2]; // joints of depth l are lvl_joint[lvl_start[l] .. lvl_start[l + 1])
   short lvl_joint[MAXJ];
   unsigned long long anc_mask[MAXNV]; // bit r: row r belongs to an ancestor-or-self joint of the joint owning this column
+  unsigned int colinfo[MAXNV];        // idx_v | (idx_v + nv) << 8 | (idx_v + nvSubtree) << 16 of the joint owning this column
+  short anc[5][MAXJ];                 // anc[s][i] = 2^s-th ancestor of joint i (0 = none): pointer jumping along the root path
+  int nsteps;                         // number of pointer-jumping rounds = ceil(log2(maxdepth))
 };
 inline void build_coop_tables(const ModelPOD<double> & M, CoopTables & C)
 {
@@ -51,8 +54,17 @@ inline void build_coop_tables(const ModelPOD<double> & M, CoopTables & C)
     unsigned long long mask = 0;
     for (int a = i; a > 0; a = M.parent[a])
       for (int k = 0; k < M.nvj[a]; ++k) mask |= 1ull << (M.idx_v[a] + k);
-    for (int k = 0; k < M.nvj[i]; ++k) C.anc_mask[M.idx_v[i] + k] = mask;
+    for (int k = 0; k < M.nvj[i]; ++k)
+    {
+      C.anc_mask[M.idx_v[i] + k] = mask;
+      C.colinfo[M.idx_v[i] + k] = (unsigned)M.idx_v[i] | ((unsigned)(M.idx_v[i] + M.nvj[i]) << 8) | ((unsigned)(M.idx_v[i] + M.nvsub[i]) << 16);
+    }
+    C.anc[0][i] = (short)M.parent[i];
   }
+  C.nsteps = 0;
+  while ((1 << C.nsteps) < M.maxdepth) ++C.nsteps;
+  for (int s = 1; s < 5; ++s)
+    for (int i = 1; i < M.njoints; ++i) C.anc[s][i] = C.anc[s - 1][C.anc[s - 1][i]];
 }
 
 // Per-joint record (JR_STRIDE values, odd => lanes = joints are conflict-free):
@@ -142,68 +154,128 @@ template<class T> BRBD_DI LinInertia<T> load_lin_inertia(const T * d)
   return Y;
 }
 
-// ---- phase 1: level-synchronous forward kinematics ------------------------------------------------------
-// oa_gf of the reference (a_i = S a + v_i x v_J + liMi^-1 a_parent, oa_gf = oMi.act(a_i) - g) in world form:
-// oa_gf_i = oa_gf_parent + J_i a_i + ov_i x (J_i v_i), oa_gf_0 = -g.
-template<class T, int G, bool WITH_ACC>
-BRBD_DI void coop_forward(const ModelPOD<T> & m, const CoopTables & tb, const T * sq, const T * sv, const T * sa, T * jr, T * cb, int gl)
+// ---- phase 1: forward kinematics by pointer jumping along the root paths ---------------------------------
+// oMi_i = prod_{a on path(i)} liMi_a, ov_i = sum_path J_a v_a, oa_gf_i = -g + sum_path (J_a a_a + ov_a x (J_a v_a))
+// (the world-frame form of a_i = S a + v_i x v_J + liMi^-1 a_parent, oa_gf = oMi.act(a_i) - g, rnea-derivatives.hxx
+// :295-317).  A level-by-level walk would issue the per-joint code once per tree level (11 times for a humanoid)
+// with a handful of active lanes; pointer jumping composes every joint with its 2^s-th ancestor's partial
+// product, all lanes active, in ceil(log2(depth)) rounds.  Buffers ping-pong inside the joint record:
+//   oMi: [JR_DY, JR_DY+12) <-> [JR_DY+12, JR_DY+24);  ov: JR_OV <-> JR_OF;  oa: JR_OA <-> JR_OF.
+// On return: oMi at jr[i] + xoff (returned), ov final at JR_OV, oa WITHOUT gravity at jr[i] + *oa_off.
+template<class T, int G>
+BRBD_DI void coop_scan6(const CoopTables & tb, T * jr, int nj, int gl, int oA, int oB)
 {
-  const int maxdepth = m.maxdepth;
-  for (int l = 1; l <= maxdepth; ++l)
+  // prefix sums along the root path of a 6-vector; source oA, result ends in (nsteps even ? oA : oB)
+  for (int s = 0; s < tb.nsteps; ++s)
   {
-    const int k1 = tb.lvl_start[l + 1];
-    for (int k = tb.lvl_start[l] + gl; k < k1; k += G)
+    const int src = (s & 1) ? oB : oA, dst = (s & 1) ? oA : oB;
+    for (int i = 1 + gl; i < nj; i += G)
     {
-      const int i = tb.lvl_joint[k];
-      const int type = m.type[i], parent = m.parent[i], iq = m.idx_q[i], iv = m.idx_v[i], nvj = m.nvj[i];
-      SE3<T> X = joint_liMi(m, i, type, sq + iq);
-      Motion<T> ov = mzero<T>(), oa = mzero<T>();
-      if (parent > 0)
+      const int a = tb.anc[s][i];
+      const T * ri = jr + i * JR_STRIDE + src;
+      T x[6] = {ri[0], ri[1], ri[2], ri[3], ri[4], ri[5]};
+      if (a > 0)
       {
-        const T * pr = jr + parent * JR_STRIDE;
-        X = load_se3(pr + JR_DY) * X;
-        ov = load_motion(pr + JR_OV);
-        if (WITH_ACC) oa = load_motion(pr + JR_OA);
+        const T * ra = jr + a * JR_STRIDE + src;
+#pragma unroll
+        for (int k = 0; k < 6; ++k) x[k] += ra[k];
       }
-      else if (WITH_ACC)
-        oa.lin = Vec3<T>(-m.gravity[0], -m.gravity[1], -m.gravity[2]);
-      Motion<T> w = mzero<T>();
-      for (int kk = 0; kk < nvj; ++kk)
-      {
-        const Motion<T> J = act_S_col(X, type, kk);
-        st6(cb + (iv + kk) * CB_STRIDE + CB_J, J);
-        const T vk = sv[iv + kk];
-        w.lin += vk * J.lin; w.ang += vk * J.ang;
-        if (WITH_ACC)
-        {
-          const T ak = sa[iv + kk];
-          oa.lin += ak * J.lin; oa.ang += ak * J.ang;
-        }
-      }
-      ov += w;
-      T * r = jr + i * JR_STRIDE;
-      store_se3(r + JR_DY, X);
-      store6(r + JR_OV, ov);
-      if (WITH_ACC)
-      {
-        oa += mcross(ov, w);
-        store6(r + JR_OA, oa);
-      }
+      T * d = jr + i * JR_STRIDE + dst;
+#pragma unroll
+      for (int k = 0; k < 6; ++k) d[k] = x[k];
     }
     __syncwarp();
   }
 }
 
+template<class T, int G, bool WITH_ACC>
+BRBD_DI int coop_forward(const ModelPOD<T> & m, const CoopTables & tb, const T * sq, const T * sv, const T * sa, T * jr, T * cb, int gl,
+                         int * oa_off)
+{
+  const int nj = m.njoints, nsteps = tb.nsteps;
+  // 1a: liMi
+  for (int i = 1 + gl; i < nj; i += G)
+    store_se3(jr + i * JR_STRIDE + JR_DY, joint_liMi(m, i, m.type[i], sq + m.idx_q[i]));
+  __syncwarp();
+  // 1b: oMi
+  for (int s = 0; s < nsteps; ++s)
+  {
+    const int src = JR_DY + ((s & 1) ? 12 : 0), dst = JR_DY + ((s & 1) ? 0 : 12);
+    for (int i = 1 + gl; i < nj; i += G)
+    {
+      const int a = tb.anc[s][i];
+      SE3<T> X = load_se3(jr + i * JR_STRIDE + src);
+      if (a > 0) X = load_se3(jr + a * JR_STRIDE + src) * X;
+      store_se3(jr + i * JR_STRIDE + dst, X);
+    }
+    __syncwarp();
+  }
+  const int xoff = JR_DY + ((nsteps & 1) ? 12 : 0);
+  // 1c: J = oMi.act(S), w = J v, u = J a
+  for (int i = 1 + gl; i < nj; i += G)
+  {
+    const int type = m.type[i], iv = m.idx_v[i], nvj = m.nvj[i];
+    T * r = jr + i * JR_STRIDE;
+    const SE3<T> X = load_se3(r + xoff);
+    Motion<T> w = mzero<T>(), u = mzero<T>();
+    for (int kk = 0; kk < nvj; ++kk)
+    {
+      const Motion<T> J = act_S_col(X, type, kk);
+      st6(cb + (iv + kk) * CB_STRIDE + CB_J, J);
+      const T vk = sv[iv + kk];
+      w.lin += vk * J.lin; w.ang += vk * J.ang;
+      if (WITH_ACC)
+      {
+        const T ak = sa[iv + kk];
+        u.lin += ak * J.lin; u.ang += ak * J.ang;
+      }
+    }
+    store6(r, w);
+    store6(r + JR_OV, w);
+    if (WITH_ACC) store6(r + JR_OA, u);
+  }
+  __syncwarp();
+  // 1d: ov
+  coop_scan6<T, G>(tb, jr, nj, gl, JR_OV, JR_OF);
+  const int ov_res = (nsteps & 1) ? JR_OF : JR_OV;
+  if (WITH_ACC || ov_res != JR_OV)
+  {
+    // 1e: t = u + ov x w
+    for (int i = 1 + gl; i < nj; i += G)
+    {
+      T * r = jr + i * JR_STRIDE;
+      const Motion<T> ov = load_motion(r + ov_res);
+      if (ov_res != JR_OV) store6(r + JR_OV, ov);
+      if (WITH_ACC)
+      {
+        Motion<T> t = load_motion(r + JR_OA);
+        t += mcross(ov, load_motion(r));
+        store6(r + JR_OA, t);
+      }
+    }
+    __syncwarp();
+  }
+  if (WITH_ACC)
+  {
+    coop_scan6<T, G>(tb, jr, nj, gl, JR_OA, JR_OF);
+    *oa_off = (nsteps & 1) ? JR_OF : JR_OA;
+  }
+  return xoff;
+}
+
 // ---- phase 2: per-joint world inertia, momentum, force, inertia variation --------------------------------
 template<class T, int G>
-BRBD_DI void coop_joint_quantities(const ModelPOD<T> & m, T * jr, int gl)
+BRBD_DI void coop_joint_quantities(const ModelPOD<T> & m, T * jr, int gl, int xoff, int oa_off)
 {
   const int nj = m.njoints;
   for (int i = 1 + gl; i < nj; i += G)
   {
     T * r = jr + i * JR_STRIDE;
-    const SE3<T> X = load_se3(r + JR_DY);
-    const Motion<T> ov = load_motion(r + JR_OV), oa = load_motion(r + JR_OA);
+    const SE3<T> X = load_se3(r + xoff);
+    const Motion<T> ov = load_motion(r + JR_OV);
+    Motion<T> oa = load_motion(r + oa_off);
+    oa.lin -= Vec3<T>(m.gravity[0], m.gravity[1], m.gravity[2]); // oa_gf[0] = -gravity (:504)
+    store6(r + JR_OA, oa);
     const Inertia<T> Y = act(X, model_inertia(m, i));
     const Force<T> oh = Y * ov;
     Force<T> of = Y * oa;
@@ -216,24 +288,35 @@ BRBD_DI void coop_joint_quantities(const ModelPOD<T> & m, T * jr, int gl)
 }
 
 // ---- phase 3: subtree sums, lanes = components ------------------------------------------------------------
+// Joints are numbered depth-first, so walking i = nj-1 .. 1 and adding record i into record parent(i) completes
+// every subtree sum; a lane owns NC components for the whole walk (no cross-lane dependency, no barrier), and the
+// running sum of a chain (parent(i) == i - 1) stays in registers.
 template<class T, int G>
 BRBD_DI void coop_subtree_sums(const ModelPOD<T> & m, T * jr, int gl)
 {
+  constexpr int NC = (JR_NSUM + G - 1) / G;
   const int nj = m.njoints;
-  for (int comp = gl; comp < JR_NSUM; comp += G)
+  T carry[NC];
+  bool on[NC];
+#pragma unroll
+  for (int t = 0; t < NC; ++t) { on[t] = gl + t * G < JR_NSUM; carry[t] = T(0); }
+  T * col = jr + gl;
+  int carry_idx = -1;
+  for (int i = nj - 1; i > 0; --i)
   {
-    T carry = T(0);
-    int carry_idx = -1;
-    for (int i = nj - 1; i > 0; --i)
+    const int p = m.parent[i];
+    if (p > 0)
     {
-      const int p = m.parent[i];
-      if (p > 0)
-      {
-        const T x = (carry_idx == i) ? carry : jr[i * JR_STRIDE + comp];
-        carry = jr[p * JR_STRIDE + comp] + x;
-        jr[p * JR_STRIDE + comp] = carry;
-        carry_idx = p;
-      }
+      const bool have = carry_idx == i;
+#pragma unroll
+      for (int t = 0; t < NC; ++t)
+        if (on[t])
+        {
+          const T x = have ? carry[t] : col[i * JR_STRIDE + t * G];
+          carry[t] = col[p * JR_STRIDE + t * G] + x;
+          col[p * JR_STRIDE + t * G] = carry[t];
+        }
+      carry_idx = p;
     }
   }
   __syncwarp();
@@ -298,6 +381,35 @@ BRBD_DI void coop_columns(const ModelPOD<T> & m, const T * jr, T * cb, T * tau_i
 //                                    J_r . dFdv_c (:450-451),  J_r . dFda_c (:420-421, + armature on the diagonal)
 //   r in the strict subtree:         dFda_r . dAdq_c + dYtJ_r . dVdq_c (:433-435),  dFda_r . dAdv_c + dYtJ_r . J_c (:446-448)
 //   otherwise 0.
+template<class T, bool WITH_DA>
+BRBD_DI void coop_entry(const ModelPOD<T> & m, const CoopTables & tb, const T * cb, const T * Jr, const T * Fd, const T * Yd, int r, int c,
+                        T & vq, T & vv, T & va)
+{
+  const unsigned info = tb.colinfo[c];
+  const int ivc = info & 0xff, own_end = (info >> 8) & 0xff, sub_end = info >> 16;
+  const bool own = r >= ivc && r < own_end;
+  const bool up = (tb.anc_mask[c] >> r) & 1ull;
+  const bool low = r >= own_end && r < sub_end;
+  const T * P = cb + c * CB_STRIDE;
+  T x[6], y[6];
+  ld6(P + (own ? CB_DFDQ : CB_DFDQP), x);
+  const T Aq = dot6a(Jr, x);
+  ld6(P + CB_DADQ, x); ld6(P + CB_DVDQ, y);
+  const T Bq = dot6a(Fd, x) + dot6a(Yd, y);
+  ld6(P + CB_DFDV, x);
+  const T Av = dot6a(Jr, x);
+  ld6(P + CB_DADV, x); ld6(P + CB_J, y);
+  const T Bv = dot6a(Fd, x) + dot6a(Yd, y);
+  vq = up ? Aq : (low ? Bq : T(0));
+  vv = up ? Av : (low ? Bv : T(0));
+  if (WITH_DA)
+  {
+    ld6(P + CB_DFDA, x);
+    va = up ? dot6a(Jr, x) : T(0);
+    if (r == c) va += m.armature[c];
+  }
+}
+
 template<class T, int G, bool WITH_DA>
 BRBD_DI void coop_entries(const ModelPOD<T> & m, const CoopTables & tb, const T * cb, T * __restrict__ gq, T * __restrict__ gv,
                           T * __restrict__ ga, int gl, bool active)
@@ -306,48 +418,47 @@ BRBD_DI void coop_entries(const ModelPOD<T> & m, const CoopTables & tb, const T 
   for (int rb = 0; rb < nv; rb += G)
   {
     const int R = (nv - rb) < G ? (nv - rb) : G;
-    const int C = G / R;
-    const int rl = gl % R, slice = gl / R;
-    const int r = rb + rl;
-    const bool lane_on = slice < C;
     T Jr[6], Fd[6], Yd[6];
+    if (R == G)
     {
+      // full row block: one column per step, the column record is a broadcast
+      const int r = rb + gl;
       const T * Pr = cb + r * CB_STRIDE;
       ld6(Pr + CB_J, Jr); ld6(Pr + CB_DFDA, Fd); ld6(Pr + CB_DYTJ, Yd);
-    }
-    for (int c0 = 0; c0 < nv; c0 += C)
-    {
-      const int c = c0 + slice;
-      const bool valid = lane_on && c < nv;
-      const int cc = valid ? c : 0;
-      const int jc = m.dof_joint[cc];
-      const int ivc = m.idx_v[jc], own_end = ivc + m.nvj[jc], sub_end = ivc + m.nvsub[jc];
-      const bool own = r >= ivc && r < own_end;
-      const bool up = (tb.anc_mask[cc] >> r) & 1ull;
-      const bool low = r >= own_end && r < sub_end;
-      const T * P = cb + cc * CB_STRIDE;
-      T x[6], y[6];
-      ld6(P + (own ? CB_DFDQ : CB_DFDQP), x);
-      const T Aq = dot6a(Jr, x);
-      ld6(P + CB_DADQ, x); ld6(P + CB_DVDQ, y);
-      const T Bq = dot6a(Fd, x) + dot6a(Yd, y);
-      ld6(P + CB_DFDV, x);
-      const T Av = dot6a(Jr, x);
-      ld6(P + CB_DADV, x); ld6(P + CB_J, y);
-      const T Bv = dot6a(Fd, x) + dot6a(Yd, y);
-      const T vq = up ? Aq : (low ? Bq : T(0));
-      const T vv = up ? Av : (low ? Bv : T(0));
-      if (valid && active)
+      T * pq = gq + r, * pv = gv + r, * pa = ga + r;
+      for (int c = 0; c < nv; ++c)
       {
-        gq[cc * nv + r] = vq;
-        gv[cc * nv + r] = vv;
+        T vq, vv, va;
+        coop_entry<T, WITH_DA>(m, tb, cb, Jr, Fd, Yd, r, c, vq, vv, va);
+        if (active)
+        {
+          *pq = vq; *pv = vv;
+          if (WITH_DA) *pa = va;
+        }
+        pq += nv; pv += nv; pa += nv;
       }
-      if (WITH_DA)
+    }
+    else
+    {
+      // tail rows: R rows x C = G / R column slices
+      const int C = G / R;
+      const int rl = gl % R, slice = gl / R;
+      const int r = rb + rl;
+      const bool lane_on = slice < C;
+      const T * Pr = cb + r * CB_STRIDE;
+      ld6(Pr + CB_J, Jr); ld6(Pr + CB_DFDA, Fd); ld6(Pr + CB_DYTJ, Yd);
+      for (int c0 = 0; c0 < nv; c0 += C)
       {
-        ld6(P + CB_DFDA, x);
-        T va = up ? dot6a(Jr, x) : T(0);
-        if (r == cc) va += m.armature[cc];
-        if (valid && active) ga[cc * nv + r] = va;
+        const int c = c0 + slice;
+        const bool valid = lane_on && c < nv;
+        const int cc = valid ? c : 0;
+        T vq, vv, va;
+        coop_entry<T, WITH_DA>(m, tb, cb, Jr, Fd, Yd, r, cc, vq, vv, va);
+        if (valid && active)
+        {
+          gq[cc * nv + r] = vq; gv[cc * nv + r] = vv;
+          if (WITH_DA) ga[cc * nv + r] = va;
+        }
       }
     }
   }
@@ -387,8 +498,9 @@ rnea_derivatives_coop_kernel(const ModelPOD<T> * __restrict__ gm, const __grid_c
     for (int k = gl; k < nq; k += G) sq[k] = gq_in[k];
     for (int k = gl; k < nv; k += G) { sv[k] = gv_in[k]; sa[k] = ga_in[k]; }
     __syncwarp();
-    coop_forward<T, G, true>(m, tb, sq, sv, sa, jr, cb, gl);
-    coop_joint_quantities<T, G>(m, jr, gl);
+    int oa_off = JR_OA;
+    const int xoff = coop_forward<T, G, true>(m, tb, sq, sv, sa, jr, cb, gl, &oa_off);
+    coop_joint_quantities<T, G>(m, jr, gl, xoff, oa_off);
     coop_subtree_sums<T, G>(m, jr, gl);
     coop_columns<T, G>(m, jr, cb, sa, gl);
     coop_entries<T, G, true>(m, tb, cb, dq + cfg * ld_dq, dv + cfg * ld_dv, da + cfg * ld_da, gl, active);

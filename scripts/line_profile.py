@@ -21,14 +21,20 @@ for k, l in enumerate(dis):
 assert start is not None, "kernel not found in disassembly"
 off2line = {}
 cur = None
+inner = os.environ.get("INNER") == "1"   # INNER=1: innermost frame in the file (default: outermost)
+fresh = True
 for l in dis[start + 1:]:
     if l.startswith("//---") and ".text." in l: break
     m = re.match(r'\s*//## File "([^"]+)", line (\d+)', l)
     if m:
-        if os.path.basename(m.group(1)) == srcfile: cur = int(m.group(2))   # last such frame = outermost in that file
+        if os.path.basename(m.group(1)) == srcfile and (not inner or fresh):
+            cur = int(m.group(2))   # last such frame = outermost in that file
+            fresh = False
         continue
     m = re.match(r'\s*/\*([0-9a-f]+)\*/', l)
-    if m: off2line[int(m.group(1), 16)] = cur
+    if m:
+        off2line[int(m.group(1), 16)] = cur
+        fresh = True
 rows = [r for r in csv.reader(open(ncu_csv))]
 hdr = rows[1]; data = [r for r in rows[2:] if len(r) == len(hdr) and r[0] != "Address"]
 iA, iN, iS = hdr.index("Address"), hdr.index("Instructions Executed"), hdr.index("# Samples")
