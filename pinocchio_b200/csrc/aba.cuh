@@ -329,11 +329,11 @@ aba_kernel(const ModelPOD<T> * __restrict__ gm, const T * __restrict__ q, int64_
     tile_load(sq, qpad, q + c0 * ldq, ldq, m.nq, nc, lane);
     tile_load(sv, vpad, v + c0 * ldv, ldv, m.nv, nc, lane);
     tile_load(st, vpad, tau + c0 * ldtau, ldtau, m.nv, nc, lane);
-    __syncwarp();
+    BRBD_SYNCWARP();
     if (lane < nc) aba_thread(m, sq + lane * qpad, sv + lane * vpad, st + lane * vpad);
-    __syncwarp();
+    BRBD_SYNCWARP();
     tile_store(a + c0 * lda, lda, st, vpad, m.nv, nc, lane);
-    __syncwarp();
+    BRBD_SYNCWARP();
   }
 }
 

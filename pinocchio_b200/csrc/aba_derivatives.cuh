@@ -301,16 +301,16 @@ aba_derivatives_sweep_kernel(const ModelPOD<T> * __restrict__ gmod, const T * __
     tile_load(sq, qpad, q + c0 * ldq, ldq, m.nq, nc, lane);
     tile_load(sv, vpad, v + c0 * ldv, ldv, m.nv, nc, lane);
     tile_load(su, vpad, tau + c0 * ldtau, ldtau, m.nv, nc, lane);
-    __syncwarp();
+    BRBD_SYNCWARP();
     pad_tile_rows(sq, qpad, m.nq, nc, lane);
     pad_tile_rows(sv, vpad, m.nv, nc, lane);
     pad_tile_rows(su, vpad, m.nv, nc, lane);
-    __syncwarp();
+    BRBD_SYNCWARP();
     aba_derivatives_thread(m, sq + lane * qpad, sv + lane * vpad, su + lane * vpad, eq, ev, em, dq + c0 * ld_dq, ld_dq,
                            dv + c0 * ld_dv, ld_dv, dtau + c0 * ld_dtau, ld_dtau, minv, fd, nc);
-    __syncwarp();
+    BRBD_SYNCWARP();
     if (ddq) tile_store(ddq + c0 * ldddq, ldddq, su, vpad, m.nv, nc, lane);
-    __syncwarp();
+    BRBD_SYNCWARP();
   }
 }
 
@@ -344,7 +344,7 @@ aba_derivatives_gemm_kernel(int nv, T * __restrict__ dq, int64_t ld_dq, T * __re
         while (r >= nv) { r -= nv; ++c; }
       }
     }
-    __syncwarp();
+    BRBD_SYNCWARP();
     for (int rb = 0; rb < nv; rb += 32)
     {
       const int r = rb + lane;
@@ -367,7 +367,7 @@ aba_derivatives_gemm_kernel(int nv, T * __restrict__ dq, int64_t ld_dq, T * __re
         }
       }
     }
-    __syncwarp();
+    BRBD_SYNCWARP();
   }
 }
 

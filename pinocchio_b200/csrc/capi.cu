@@ -21,10 +21,12 @@
 #include "../../include/pinocchio_b200.h"
 #include "aba.cuh"
 #include "aba_derivatives.cuh"
+#include "aba_deriv_coop.cuh"
 #include "aba_dfs.cuh"
 #include "crba.cuh"
 #include "crba_dfs.cuh"
 #include "engine.cuh"
+#include "model_build.hpp"
 #include "rnea.cuh"
 #include "rnea_derivatives.cuh"
 #include "deriv_coop.cuh"
@@ -49,26 +51,6 @@ brbd_status fail(brbd_status s, const std::string & msg)
       return fail(BRBD_ECUDA, std::string(#expr) + ": " + cudaGetErrorString(e__));                 \
   } while (0)
 
-int joint_nq_of(int t) { return t <= BRBD_JOINT_PZ ? 1 : (t == BRBD_JOINT_FREEFLYER ? 7 : 4); }
-int joint_nv_of(int t) { return t <= BRBD_JOINT_PZ ? 1 : (t == BRBD_JOINT_FREEFLYER ? 6 : 3); }
-
-template<class T> void fill_pod(ModelPOD<T> & P, const ModelPOD<double> & D)
-{
-  std::memset(&P, 0, sizeof(P));
-  P.njoints = D.njoints; P.nq = D.nq; P.nv = D.nv; P.maxdepth = D.maxdepth;
-  for (int i = 0; i < MAXJ; ++i)
-  {
-    P.parent[i] = D.parent[i]; P.type[i] = D.type[i]; P.idx_q[i] = D.idx_q[i]; P.idx_v[i] = D.idx_v[i];
-    P.nvj[i] = D.nvj[i]; P.nvsub[i] = D.nvsub[i]; P.depth[i] = D.depth[i];
-    for (int k = 0; k < 12; ++k) P.placement[i][k] = (T)D.placement[i][k];
-    for (int k = 0; k < 10; ++k) P.inertia[i][k] = (T)D.inertia[i][k];
-  }
-  for (int k = 0; k < MAXNV; ++k)
-  {
-    P.dof_joint[k] = D.dof_joint[k]; P.parent_row[k] = D.parent_row[k]; P.armature[k] = (T)D.armature[k];
-  }
-  for (int k = 0; k < 3; ++k) P.gravity[k] = (T)D.gravity[k];
-}
 } // namespace
 
 struct brbd_model
@@ -409,6 +391,32 @@ brbd_status launch_aba_derivs(brbd_pool * p, DeviceCtx & d, const T * q, int64_t
                               int64_t ld_dtau, T * ddq, int64_t ldddq, int64_t B)
 {
   const ModelPOD<double> & M = p->model.pd;
+  // preferred: one kernel, G lanes per configuration, everything in shared memory (aba_deriv_coop.cuh)
+  {
+    const int G = coop_group_size(M.nv);
+    const AbaCoopLayout L = aba_coop_layout(M.nq, M.nv, M.njoints, G);
+    const size_t static_bytes = sizeof(ModelPOD<T>) + sizeof(CoopTables) + 1024;
+    const GeometryCoop g = pick_geometry_coop(d, (size_t)L.per_group * sizeof(T), G, static_bytes, B);
+    if (p->model.coop.nbranch <= A_MAXBRANCH && g.dyn_bytes + static_bytes <= (size_t)d.max_smem_optin + 1024)
+    {
+      brbd_status st = BRBD_OK;
+#define BRBD_LAUNCH_COOP(GG)                                                                                     \
+  {                                                                                                              \
+    st = set_smem(aba_derivatives_coop_kernel<T, GG>, g.dyn_bytes);                                              \
+    if (st != BRBD_OK) return st;                                                                                \
+    aba_derivatives_coop_kernel<T, GG><<<g.grid, g.warps * 32, g.dyn_bytes, d.s()>>>(                            \
+      dev_model<T>(d), p->model.coop, L, q, ldq, v, ldv, tau, ldtau, dq, ld_dq, dv, ld_dv, dtau, ld_dtau, ddq, ldddq, B); \
+  }
+      if (G == 8) BRBD_LAUNCH_COOP(8)
+      else if (G == 16) BRBD_LAUNCH_COOP(16)
+      else BRBD_LAUNCH_COOP(32)
+#undef BRBD_LAUNCH_COOP
+      p->launches += 1;
+      CUDA_TRY(cudaGetLastError());
+      return BRBD_OK;
+    }
+  }
+  // fallback (very large models, more than A_MAXBRANCH branching joints): v1, one configuration per thread
   const size_t per_warp = (size_t)32 * ((M.nq | 1) + 5 * (M.nv | 1)) * sizeof(T);
   const Geometry g = pick_geometry(d, per_warp, sizeof(ModelPOD<T>), B, 16, 16);
   brbd_status st = set_smem(aba_derivatives_sweep_kernel<T>, g.dyn_bytes);
@@ -605,97 +613,15 @@ brbd_status brbd_model_create(const brbd_flat_model * f, brbd_model ** out)
 {
   if (!f || !out) return fail(BRBD_EINVAL, "null argument");
   *out = nullptr;
-  if (f->njoints < 1 || f->njoints > MAXJ)
-    return fail(BRBD_EINVAL, "njoints must be in [1, " + std::to_string(MAXJ) + "]");
-  if (f->nv > MAXNV || f->nv < 0) return fail(BRBD_EINVAL, "nv must be in [0, " + std::to_string(MAXNV) + "]");
   brbd_model * m = new brbd_model();
-  ModelPOD<double> & P = m->pd;
-  std::memset(&P, 0, sizeof(P));
-  P.njoints = f->njoints; P.nq = f->nq; P.nv = f->nv;
-  int nq = 0, nv = 0, maxdepth = 0;
-  for (int i = 0; i < f->njoints; ++i)
-  {
-    P.parent[i] = f->parents[i];
-    P.type[i] = f->joint_type[i];
-    P.idx_q[i] = f->idx_q[i];
-    P.idx_v[i] = f->idx_v[i];
-    if (i == 0)
-    {
-      P.nvj[i] = 0; P.depth[i] = 0;
-      continue;
-    }
-    if (P.type[i] < BRBD_JOINT_RX || P.type[i] > BRBD_JOINT_PLANAR)
-    {
-      delete m;
-      return fail(BRBD_EUNSUPPORTED_JOINT, "joint " + std::to_string(i) + " has unsupported type tag " + std::to_string(f->joint_type[i]));
-    }
-    if (P.parent[i] < 0 || P.parent[i] >= i)
-    {
-      delete m;
-      return fail(BRBD_ETOPOLOGY, "parents[" + std::to_string(i) + "] must be < " + std::to_string(i));
-    }
-    if (P.idx_q[i] != nq || P.idx_v[i] != nv)
-    {
-      delete m;
-      return fail(BRBD_EINVAL, "idx_q / idx_v of joint " + std::to_string(i) + " are not cumulative");
-    }
-    P.nvj[i] = joint_nv_of(P.type[i]);
-    nq += joint_nq_of(P.type[i]);
-    nv += P.nvj[i];
-    P.depth[i] = P.depth[P.parent[i]] + 1;
-    maxdepth = std::max(maxdepth, P.depth[i]);
-    for (int k = 0; k < P.nvj[i]; ++k) P.dof_joint[P.idx_v[i] + k] = i;
-  }
-  if (nq != f->nq || nv != f->nv)
+  std::string err;
+  const brbd_status bst = build_model_pod(f, m->pd, err);
+  if (bst != BRBD_OK)
   {
     delete m;
-    return fail(BRBD_EINVAL, "nq / nv do not match the joint list");
+    return fail(bst, err);
   }
-  if (maxdepth >= MAXDEPTH)
-  {
-    delete m;
-    return fail(BRBD_ETOPOLOGY, "tree depth exceeds " + std::to_string(MAXDEPTH - 1));
-  }
-  P.maxdepth = maxdepth;
-  // compact depth-first numbering (CRBAChecker, crba.hxx:573-595): the subtree of i is [i, last(i)]
-  {
-    std::vector<int> last(f->njoints);
-    for (int i = 0; i < f->njoints; ++i) last[i] = i;
-    for (int i = f->njoints - 1; i > 0; --i) last[P.parent[i]] = std::max(last[P.parent[i]], last[i]);
-    for (int i = 1; i < f->njoints; ++i)
-      for (int k = i + 1; k <= last[i]; ++k)
-      {
-        int a = k;
-        while (a > i) a = P.parent[a];
-        if (a != i)
-        {
-          delete m;
-          return fail(BRBD_ETOPOLOGY, "joints are not numbered depth-first (subtree of joint " + std::to_string(i) + " is not contiguous)");
-        }
-      }
-    for (int i = 0; i < f->njoints; ++i)
-    {
-      const int lc = last[i];
-      P.nvsub[i] = (lc == 0) ? 0 : P.idx_v[lc] + P.nvj[lc] - (i == 0 ? 0 : P.idx_v[i]);
-    }
-  }
-  for (int k = 0; k < MAXNV; ++k) P.parent_row[k] = -1;
-  for (int j = 1; j < f->njoints; ++j)
-  {
-    const int parent = P.parent[j], iv = P.idx_v[j];
-    P.parent_row[iv] = parent > 0 ? P.idx_v[parent] + P.nvj[parent] - 1 : -1;
-    for (int r = 1; r < P.nvj[j]; ++r) P.parent_row[iv + r] = iv + r - 1;
-  }
-  for (int i = 0; i < f->njoints; ++i)
-  {
-    const double * S = f->placement + 12 * i; // R row-major, p
-    double * D = P.placement[i];             // R by columns, p
-    for (int c = 0; c < 3; ++c) for (int r = 0; r < 3; ++r) D[3 * c + r] = S[3 * r + c];
-    for (int k = 0; k < 3; ++k) D[9 + k] = S[9 + k];
-    for (int k = 0; k < 10; ++k) P.inertia[i][k] = f->inertia[10 * i + k];
-  }
-  for (int k = 0; k < f->nv; ++k) P.armature[k] = f->armature[k];
-  for (int k = 0; k < 3; ++k) P.gravity[k] = f->gravity[k];
+  const ModelPOD<double> & P = m->pd;
   fill_pod(m->pf, P);
   build_tree(P, m->td);
   build_tree(P, m->tf);

@@ -106,11 +106,11 @@ crba_kernel(const ModelPOD<T> * __restrict__ gm, const T * __restrict__ q, int64
     const int64_t c0 = tile * 32;
     const int nc = (int)((B - c0) < 32 ? (B - c0) : 32);
     tile_load(sq, qpad, q + c0 * ldq, ldq, m.nq, nc, lane);
-    __syncwarp();
+    BRBD_SYNCWARP();
     pad_tile_rows(sq, qpad, m.nq, nc, lane);
-    __syncwarp();
+    BRBD_SYNCWARP();
     crba_thread(m, sq + lane * qpad, em, Mout + c0 * ldM, ldM, nc);
-    __syncwarp();
+    BRBD_SYNCWARP();
   }
 }
 

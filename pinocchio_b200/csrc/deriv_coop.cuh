@@ -37,6 +37,9 @@ struct CoopTables
   unsigned int colinfo[MAXNV];        // idx_v | (idx_v + nv) << 8 | (idx_v + nvSubtree) << 16 of the joint owning this column
   short anc[5][MAXJ];                 // anc[s][i] = 2^s-th ancestor of joint i (0 = none): pointer jumping along the root path
   int nsteps;                         // number of pointer-jumping rounds = ceil(log2(maxdepth))
+  short jlast[MAXJ];                  // last joint of the subtree of i (depth-first numbering: subtree = [i, jlast[i]])
+  short bslot[MAXJ];                  // save slot of a joint with two or more children (-1 otherwise), see aba_deriv_coop.cuh
+  int nbranch;                        // number of such joints
 };
 inline void build_coop_tables(const ModelPOD<double> & M, CoopTables & C)
 {
@@ -60,6 +63,16 @@ inline void build_coop_tables(const ModelPOD<double> & M, CoopTables & C)
       C.colinfo[M.idx_v[i] + k] = (unsigned)M.idx_v[i] | ((unsigned)(M.idx_v[i] + M.nvj[i]) << 8) | ((unsigned)(M.idx_v[i] + M.nvsub[i]) << 16);
     }
     C.anc[0][i] = (short)M.parent[i];
+  }
+  for (int i = 0; i < M.njoints; ++i) C.jlast[i] = (short)i;
+  for (int i = M.njoints - 1; i > 0; --i)
+    if (C.jlast[i] > C.jlast[M.parent[i]]) C.jlast[M.parent[i]] = C.jlast[i];
+  C.nbranch = 0;
+  for (int i = 0; i < M.njoints; ++i)
+  {
+    int nchild = 0;
+    for (int k = i + 1; k < M.njoints; ++k) nchild += (M.parent[k] == i);
+    C.bslot[i] = (short)((i > 0 && nchild >= 2) ? C.nbranch++ : -1);
   }
   C.nsteps = 0;
   while ((1 << C.nsteps) < M.maxdepth) ++C.nsteps;
@@ -184,7 +197,7 @@ BRBD_DI void coop_scan6(const CoopTables & tb, T * jr, int nj, int gl, int oA, i
 #pragma unroll
       for (int k = 0; k < 6; ++k) d[k] = x[k];
     }
-    __syncwarp();
+    BRBD_SYNCWARP();
   }
 }
 
@@ -196,7 +209,7 @@ BRBD_DI int coop_forward(const ModelPOD<T> & m, const CoopTables & tb, const T *
   // 1a: liMi
   for (int i = 1 + gl; i < nj; i += G)
     store_se3(jr + i * JR_STRIDE + JR_DY, joint_liMi(m, i, m.type[i], sq + m.idx_q[i]));
-  __syncwarp();
+  BRBD_SYNCWARP();
   // 1b: oMi
   for (int s = 0; s < nsteps; ++s)
   {
@@ -208,7 +221,7 @@ BRBD_DI int coop_forward(const ModelPOD<T> & m, const CoopTables & tb, const T *
       if (a > 0) X = load_se3(jr + a * JR_STRIDE + src) * X;
       store_se3(jr + i * JR_STRIDE + dst, X);
     }
-    __syncwarp();
+    BRBD_SYNCWARP();
   }
   const int xoff = JR_DY + ((nsteps & 1) ? 12 : 0);
   // 1c: J = oMi.act(S), w = J v, u = J a
@@ -234,7 +247,7 @@ BRBD_DI int coop_forward(const ModelPOD<T> & m, const CoopTables & tb, const T *
     store6(r + JR_OV, w);
     if (WITH_ACC) store6(r + JR_OA, u);
   }
-  __syncwarp();
+  BRBD_SYNCWARP();
   // 1d: ov
   coop_scan6<T, G>(tb, jr, nj, gl, JR_OV, JR_OF);
   const int ov_res = (nsteps & 1) ? JR_OF : JR_OV;
@@ -253,7 +266,7 @@ BRBD_DI int coop_forward(const ModelPOD<T> & m, const CoopTables & tb, const T *
         store6(r + JR_OA, t);
       }
     }
-    __syncwarp();
+    BRBD_SYNCWARP();
   }
   if (WITH_ACC)
   {
@@ -264,7 +277,7 @@ BRBD_DI int coop_forward(const ModelPOD<T> & m, const CoopTables & tb, const T *
 }
 
 // ---- phase 2: per-joint world inertia, momentum, force, inertia variation --------------------------------
-template<class T, int G>
+template<class T, int G, bool SUB_GRAVITY = true>
 BRBD_DI void coop_joint_quantities(const ModelPOD<T> & m, T * jr, int gl, int xoff, int oa_off)
 {
   const int nj = m.njoints;
@@ -274,8 +287,11 @@ BRBD_DI void coop_joint_quantities(const ModelPOD<T> & m, T * jr, int gl, int xo
     const SE3<T> X = load_se3(r + xoff);
     const Motion<T> ov = load_motion(r + JR_OV);
     Motion<T> oa = load_motion(r + oa_off);
-    oa.lin -= Vec3<T>(m.gravity[0], m.gravity[1], m.gravity[2]); // oa_gf[0] = -gravity (:504)
-    store6(r + JR_OA, oa);
+    if (SUB_GRAVITY)
+    {
+      oa.lin -= Vec3<T>(m.gravity[0], m.gravity[1], m.gravity[2]); // oa_gf[0] = -gravity (:504)
+      store6(r + JR_OA, oa);
+    }
     const Inertia<T> Y = act(X, model_inertia(m, i));
     const Force<T> oh = Y * ov;
     Force<T> of = Y * oa;
@@ -284,7 +300,7 @@ BRBD_DI void coop_joint_quantities(const ModelPOD<T> & m, T * jr, int gl, int xo
     store_dy(r + JR_DY, inertia_variation(Y, ov, oh));
     store6(r + JR_OF, of);
   }
-  __syncwarp();
+  BRBD_SYNCWARP();
 }
 
 // ---- phase 3: subtree sums, lanes = components ------------------------------------------------------------
@@ -319,7 +335,7 @@ BRBD_DI void coop_subtree_sums(const ModelPOD<T> & m, T * jr, int gl)
       carry_idx = p;
     }
   }
-  __syncwarp();
+  BRBD_SYNCWARP();
 }
 
 // ---- phase 4: column records ------------------------------------------------------------------------------
@@ -371,7 +387,7 @@ BRBD_DI void coop_columns(const ModelPOD<T> & m, const T * jr, T * cb, T * tau_i
     st6(P + CB_DADV, dAdv);
     st6(P + CB_DYTJ, dY.tmul(J));
   }
-  __syncwarp();
+  BRBD_SYNCWARP();
 }
 
 // ---- phase 5: matrix entries ------------------------------------------------------------------------------
@@ -497,7 +513,7 @@ rnea_derivatives_coop_kernel(const ModelPOD<T> * __restrict__ gm, const __grid_c
     const T * gq_in = q + cfg * ldq, * gv_in = v + cfg * ldv, * ga_in = a + cfg * lda;
     for (int k = gl; k < nq; k += G) sq[k] = gq_in[k];
     for (int k = gl; k < nv; k += G) { sv[k] = gv_in[k]; sa[k] = ga_in[k]; }
-    __syncwarp();
+    BRBD_SYNCWARP();
     int oa_off = JR_OA;
     const int xoff = coop_forward<T, G, true>(m, tb, sq, sv, sa, jr, cb, gl, &oa_off);
     coop_joint_quantities<T, G>(m, jr, gl, xoff, oa_off);
@@ -506,7 +522,7 @@ rnea_derivatives_coop_kernel(const ModelPOD<T> * __restrict__ gm, const __grid_c
     coop_entries<T, G, true>(m, tb, cb, dq + cfg * ld_dq, dv + cfg * ld_dv, da + cfg * ld_da, gl, active);
     if (tau && active)
       for (int k = gl; k < nv; k += G) tau[cfg * ldtau + k] = sa[k];
-    __syncwarp();
+    BRBD_SYNCWARP();
   }
 }
 

@@ -255,7 +255,7 @@ template<class T> struct ColumnEmitter
   {
     s = buf; pad = pad_; nv = nv_; lane = lane_;
     for (int k = lane; k < 32 * pad; k += 32) s[k] = T(0);
-    __syncwarp();
+    BRBD_SYNCWARP();
   }
   BRBD_DI void put(int row, T val) { s[lane * pad + row] = val; }
   BRBD_DI void add(int row, T val) { s[lane * pad + row] += val; }
@@ -264,12 +264,12 @@ template<class T> struct ColumnEmitter
   // consecutive configurations.
   BRBD_DI void flush(T * g, int64_t ld, int ncols)
   {
-    __syncwarp();
+    BRBD_SYNCWARP();
     for (int c = 0; c < ncols; ++c)
       for (int r = lane; r < nv; r += 32) g[(int64_t)c * ld + r] = s[c * pad + r];
-    __syncwarp();
+    BRBD_SYNCWARP();
     for (int k = lane; k < 32 * pad; k += 32) s[k] = T(0);
-    __syncwarp();
+    BRBD_SYNCWARP();
   }
 };
 

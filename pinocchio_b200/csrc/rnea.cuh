@@ -111,11 +111,11 @@ rnea_kernel(const ModelPOD<T> * __restrict__ gm, const T * __restrict__ q, int64
     tile_load(sq, qpad, q + c0 * ldq, ldq, m.nq, nc, lane);
     tile_load(sv, vpad, v + c0 * ldv, ldv, m.nv, nc, lane);
     tile_load(sa, vpad, a + c0 * lda, lda, m.nv, nc, lane);
-    __syncwarp();
+    BRBD_SYNCWARP();
     if (lane < nc) rnea_thread(m, sq + lane * qpad, sv + lane * vpad, sa + lane * vpad);
-    __syncwarp();
+    BRBD_SYNCWARP();
     tile_store(tau + c0 * ldtau, ldtau, sa, vpad, m.nv, nc, lane);
-    __syncwarp();
+    BRBD_SYNCWARP();
   }
 }
 

@@ -342,16 +342,16 @@ rnea_derivatives_kernel(const ModelPOD<T> * __restrict__ gm, const T * __restric
     tile_load(sq, qpad, q + c0 * ldq, ldq, m.nq, nc, lane);
     tile_load(sv, vpad, v + c0 * ldv, ldv, m.nv, nc, lane);
     tile_load(sa, vpad, a + c0 * lda, lda, m.nv, nc, lane);
-    __syncwarp();
+    BRBD_SYNCWARP();
     pad_tile_rows(sq, qpad, m.nq, nc, lane);
     pad_tile_rows(sv, vpad, m.nv, nc, lane);
     pad_tile_rows(sa, vpad, m.nv, nc, lane);
-    __syncwarp();
+    BRBD_SYNCWARP();
     rnea_derivatives_thread(m, sq + lane * qpad, sv + lane * vpad, sa + lane * vpad, eq, ev, ea, dq + c0 * ld_dq, ld_dq,
                             dv + c0 * ld_dv, ld_dv, da + c0 * ld_da, ld_da, nc);
-    __syncwarp();
+    BRBD_SYNCWARP();
     if (tau) tile_store(tau + c0 * ldtau, ldtau, sa, vpad, m.nv, nc, lane);
-    __syncwarp();
+    BRBD_SYNCWARP();
   }
 }
 

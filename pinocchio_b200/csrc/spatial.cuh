@@ -11,7 +11,13 @@
 namespace brbd
 {
 
+#ifndef BRBD_DI
 #define BRBD_DI __device__ __forceinline__
+#endif
+// warp barrier of the warp-cooperative kernels; the CPU lane emulator of tests/cpp/coop_emu.cu overrides it
+#ifndef BRBD_SYNCWARP
+#define BRBD_SYNCWARP() __syncwarp()
+#endif
 
 template<class T> struct Vec3
 {

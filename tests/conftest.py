@@ -76,6 +76,7 @@ def assert_close(actual, expected, rtol=1e-10, atol=1e-12, what=""):
     """north_star tolerance: 1e-10 relative / 1e-12 absolute (element-wise, numpy allclose semantics)."""
     actual, expected = np.asarray(actual), np.asarray(expected)
     assert actual.shape == expected.shape, (what, actual.shape, expected.shape)
+    assert np.isfinite(actual).all(), f"{what}: non-finite entries in the result"
     err = np.abs(actual - expected)
     tol = atol + rtol * np.abs(expected)
     bad = err > tol
