@@ -35,10 +35,12 @@ namespace brbd
 //   per joint, in the record of its first column: articulated inertia left for the parent (21), pa (6)
 //   A5: Fcrb save slots of column c, 6 values per branching joint, reuse [18, 42)
 constexpr int A_U = 0, A_UD = 6, A_DINV = 12, A_IACC = 18, A_PA = 48, A_FD = 18, A_MAXBRANCH = 4;
+constexpr int SC_SIZE = 128; // scratch of the multi-dof joint step
 
 struct AbaCoopLayout
 {
   int oq, ov, ou, ojr, ocb, ominv; // offsets (elements) inside one group's region
+  int osc;                         // scratch of the multi-dof joint step (aliases Minv, which is written later, when large enough)
   int mld;                         // leading dimension of Minv (odd)
   int per_group;                   // elements, even
 };
@@ -64,19 +66,175 @@ inline AbaCoopLayout aba_coop_layout(int nq, int nv, int nj, int G)
   L.ov = L.oq + nq;
   L.ou = L.ov + nv;
   L.per_group = (L.ou + nv + 1) & ~1;
+  if (L.mld * nv + 8 >= SC_SIZE) L.osc = L.ominv;
+  else
+  {
+    L.osc = L.per_group;
+    L.per_group += SC_SIZE;
+  }
   return L;
 }
 
 // ---- A2: articulated-body inertia, leaf -> root -----------------------------------------------------------
+// Multi-dof joint (free-flyer, spherical, planar): all lanes of the group work on the one joint — the 6 x 6 / nvj x nvj
+// pieces live in a 128-value scratch block, Dinv by Cholesky (PerformStYSInversion, joint-common-operations.hpp:23-33):
+// factor by lane 0, the columns of the inverse by nvj lanes.
+constexpr int SC_IA = 0, SC_F = 36, SC_S = 42, SC_D = 78, SC_INVD = 114, SC_AB = 120;
+BRBD_DI int sym6_index(int a, int b)
+{
+  const int lo = a < b ? a : b, hi = a < b ? b : a;
+  return lo * 6 - (lo * (lo - 1)) / 2 + (hi - lo);
+}
 template<class T, int G>
-BRBD_DI void coop_aba_backward(const ModelPOD<T> & m, const CoopTables & tb, T * jr, T * cb, T * su, int gl, int xoff)
+BRBD_DI void coop_aba_multidof(const ModelPOD<T> & m, const CoopTables & tb, T * jr, T * cb, T * su, T * sc, int gl, int i, int xoff)
+{
+  const int parent = m.parent[i], iv = m.idx_v[i], nvj = m.nvj[i];
+  T * r = jr + i * JR_STRIDE;
+  T * P0 = cb + iv * CB_STRIDE;
+  if (gl == 0)
+  {
+    const SE3<T> X = load_se3(r + xoff);
+    const Motion<T> ov = load_motion(r + JR_OV);
+    const Inertia<T> Y = act(X, model_inertia(m, i));
+    T Ia[21], f[6];
+    inertia_to_sym6(Y, Ia);
+    f2a(fcross(ov, Y * ov), f);
+#pragma unroll
+    for (int a = 0; a < 6; ++a)
+#pragma unroll
+      for (int b = 0; b < 6; ++b) sc[SC_IA + a * 6 + b] = Ia[a <= b ? a * 6 - (a * (a - 1)) / 2 + (b - a) : b * 6 - (b * (b - 1)) / 2 + (a - b)];
+    Motion<T> ab = mzero<T>();
+    if (parent > 0) ab = mcross(load_motion(jr + parent * JR_STRIDE + JR_OV), ov);
+    store6(r + JR_OA, ab);
+    store6(sc + SC_AB, ab);
+#pragma unroll
+    for (int k = 0; k < 6; ++k) sc[SC_F + k] = f[k];
+  }
+  BRBD_SYNCWARP();
+  // contributions of the children
+  const int last = tb.jlast[i];
+  for (int e = gl; e < 42; e += G)
+  {
+    const int off = e < 36 ? A_IACC + sym6_index(e / 6, e % 6) : A_PA + (e - 36);
+    T * dst = sc + (e < 36 ? SC_IA + e : SC_F + (e - 36));
+    T acc = *dst;
+    for (int c = i + 1; c <= last; c = tb.jlast[c] + 1) acc += cb[m.idx_v[c] * CB_STRIDE + off];
+    *dst = acc;
+  }
+  BRBD_SYNCWARP();
+  // U = Ia J
+  for (int e = gl; e < 6 * nvj; e += G)
+  {
+    const int a = e % 6, k = e / 6;
+    const T * Jk = P0 + k * CB_STRIDE + CB_J;
+    const T * Ir = sc + SC_IA + a * 6;
+    T acc = Ir[0] * Jk[0];
+#pragma unroll
+    for (int b = 1; b < 6; ++b) acc += Ir[b] * Jk[b];
+    P0[k * CB_STRIDE + A_U + a] = acc;
+  }
+  BRBD_SYNCWARP();
+  // StU = J^T U + armature;  u = tau - J^T f
+  for (int e = gl; e < nvj * nvj + nvj; e += G)
+  {
+    if (e < nvj * nvj)
+    {
+      const int a = e / nvj, b = e % nvj;
+      const T * Ja = P0 + a * CB_STRIDE + CB_J, * Ub = P0 + b * CB_STRIDE + A_U;
+      T acc = dot6a(Ja, Ub);
+      if (a == b) acc += m.armature[iv + a];
+      sc[SC_S + a * 6 + b] = acc;
+    }
+    else
+    {
+      const int k = e - nvj * nvj;
+      su[iv + k] -= dot6a(P0 + k * CB_STRIDE + CB_J, sc + SC_F);
+    }
+  }
+  BRBD_SYNCWARP();
+  if (gl == 0)
+  {
+    T * S = sc + SC_S;
+    for (int a = 0; a < nvj; ++a)
+      for (int b = 0; b <= a; ++b)
+      {
+        T acc = S[a * 6 + b];
+        for (int k = 0; k < b; ++k) acc -= S[a * 6 + k] * S[b * 6 + k];
+        if (a == b)
+        {
+          const T d = sqrt_t(acc);
+          S[a * 6 + a] = d;
+          sc[SC_INVD + a] = T(1) / d;
+        }
+        else
+          S[a * 6 + b] = acc * sc[SC_INVD + b];
+      }
+  }
+  BRBD_SYNCWARP();
+  if (gl < nvj)
+  {
+    const T * S = sc + SC_S;
+    T * D = sc + SC_D + gl; // column gl of the inverse, D[a * 6]
+    for (int a = 0; a < nvj; ++a)
+    {
+      T acc = (a == gl) ? T(1) : T(0);
+      for (int k = 0; k < a; ++k) acc -= S[a * 6 + k] * D[k * 6];
+      D[a * 6] = acc * sc[SC_INVD + a];
+    }
+    for (int a = nvj - 1; a >= 0; --a)
+    {
+      T acc = D[a * 6];
+      for (int k = a + 1; k < nvj; ++k) acc -= S[k * 6 + a] * D[k * 6];
+      D[a * 6] = acc * sc[SC_INVD + a];
+    }
+  }
+  BRBD_SYNCWARP();
+  // U Dinv, rows of Dinv (zero-padded to 6)
+  for (int e = gl; e < 6 * nvj; e += G)
+  {
+    const int a = e % 6, k = e / 6;
+    T acc = T(0);
+    for (int c = 0; c < nvj; ++c) acc += P0[c * CB_STRIDE + A_U + a] * sc[SC_D + c * 6 + k];
+    P0[k * CB_STRIDE + A_UD + a] = acc;
+    P0[k * CB_STRIDE + A_DINV + a] = a < nvj ? sc[SC_D + k * 6 + a] : T(0);
+  }
+  BRBD_SYNCWARP();
+  if (parent > 0)
+  {
+    // Ia -= U Dinv U^T, left for the parent together with pa = f + Ia a_bias + U Dinv u
+    for (int e = gl; e < 36; e += G)
+    {
+      const int a = e / 6, b = e % 6;
+      T acc = T(0);
+      for (int k = 0; k < nvj; ++k) acc += P0[k * CB_STRIDE + A_UD + a] * P0[k * CB_STRIDE + A_U + b];
+      const T val = sc[SC_IA + e] - acc;
+      sc[SC_IA + e] = val;
+      if (a <= b) P0[A_IACC + sym6_index(a, b)] = val;
+    }
+    BRBD_SYNCWARP();
+    for (int a = gl; a < 6; a += G)
+    {
+      T acc = sc[SC_F + a];
+#pragma unroll
+      for (int b = 0; b < 6; ++b) acc += sc[SC_IA + a * 6 + b] * sc[SC_AB + b];
+      for (int k = 0; k < nvj; ++k) acc += P0[k * CB_STRIDE + A_UD + a] * su[iv + k];
+      P0[A_PA + a] = acc;
+    }
+  }
+  BRBD_SYNCWARP();
+}
+
+template<class T, int G>
+BRBD_DI void coop_aba_backward(const ModelPOD<T> & m, const CoopTables & tb, T * jr, T * cb, T * su, T * sc, int gl, int xoff)
 {
   for (int l = m.maxdepth; l >= 1; --l)
   {
+    // 1-dof joints of this depth: one lane each
     for (int s = tb.lvl_start[l] + gl; s < tb.lvl_start[l + 1]; s += G)
     {
       const int i = tb.lvl_joint[s];
-      const int parent = m.parent[i], iv = m.idx_v[i], nvj = m.nvj[i];
+      const int parent = m.parent[i], iv = m.idx_v[i];
+      if (m.nvj[i] != 1) continue;
       T * r = jr + i * JR_STRIDE;
       T * P0 = cb + iv * CB_STRIDE;
       const SE3<T> X = load_se3(r + xoff);
@@ -100,172 +258,134 @@ BRBD_DI void coop_aba_backward(const ModelPOD<T> & m, const CoopTables & tb, T *
       Motion<T> ab = mzero<T>();
       if (parent > 0) ab = mcross(load_motion(jr + parent * JR_STRIDE + JR_OV), ov); // a_gf bias (:66)
       store6(r + JR_OA, ab);
-      if (nvj == 1)
+      T Jv[6], U[6], UD[6];
+      ld6(P0 + CB_J, Jv);
+      sym6_mul(Ia, Jv, U);
+      const T D = dot6a(Jv, U) + m.armature[iv];
+      const T Dinv = T(1) / D;
+#pragma unroll
+      for (int k = 0; k < 6; ++k) UD[k] = U[k] * Dinv;
+      const T u = su[iv] - dot6a(Jv, f);
+      su[iv] = u;
+      st6(P0 + A_U, U);
+      st6(P0 + A_UD, UD);
+      P0[A_DINV] = Dinv;
+      if (parent > 0)
       {
-        T Jv[6], U[6], UD[6];
-        ld6(P0 + CB_J, Jv);
-        sym6_mul(Ia, Jv, U);
-        const T D = dot6a(Jv, U) + m.armature[iv];
-        const T Dinv = T(1) / D;
 #pragma unroll
-        for (int k = 0; k < 6; ++k) UD[k] = U[k] * Dinv;
-        const T u = su[iv] - dot6a(Jv, f);
-        su[iv] = u;
-        st6(P0 + A_U, U);
-        st6(P0 + A_UD, UD);
-        P0[A_DINV] = Dinv;
-        if (parent > 0)
-        {
+        for (int a = 0; a < 6; ++a)
 #pragma unroll
-          for (int a = 0; a < 6; ++a)
+          for (int b = a; b < 6; ++b) Ia[a * 6 - (a * (a - 1)) / 2 + (b - a)] -= UD[a] * U[b];
+        T abv[6], Iab[6];
+        m2a(ab, abv);
+        sym6_mul(Ia, abv, Iab);
 #pragma unroll
-            for (int b = a; b < 6; ++b) Ia[a * 6 - (a * (a - 1)) / 2 + (b - a)] -= UD[a] * U[b];
-          T abv[6], Iab[6];
-          m2a(ab, abv);
-          sym6_mul(Ia, abv, Iab);
+        for (int k = 0; k < 6; ++k) f[k] += Iab[k] + UD[k] * u;
 #pragma unroll
-          for (int k = 0; k < 6; ++k) f[k] += Iab[k] + UD[k] * u;
-#pragma unroll
-          for (int k = 0; k < 21; ++k) P0[A_IACC + k] = Ia[k];
-          st6(P0 + A_PA, f);
-        }
-      }
-      else
-      {
-        // multi-dof joint (free-flyer, spherical, planar): Dinv by Cholesky (joint-common-operations.hpp:23-33)
-        T U[6][6], StU[6][6], Di[6][6], UD[6][6], uj[6];
-        for (int k = 0; k < nvj; ++k)
-        {
-          T Jv[6], Uk[6];
-          ld6(P0 + k * CB_STRIDE + CB_J, Jv);
-          sym6_mul(Ia, Jv, Uk);
-          uj[k] = su[iv + k] - dot6a(Jv, f);
-          su[iv + k] = uj[k];
-          for (int a = 0; a < 6; ++a) U[a][k] = Uk[a];
-          st6(P0 + k * CB_STRIDE + A_U, Uk);
-        }
-        for (int a = 0; a < nvj; ++a)
-        {
-          T Jv[6];
-          ld6(P0 + a * CB_STRIDE + CB_J, Jv);
-          for (int b = 0; b < nvj; ++b)
-          {
-            T acc = Jv[0] * U[0][b];
-            for (int k = 1; k < 6; ++k) acc += Jv[k] * U[k][b];
-            StU[a][b] = acc;
-          }
-          StU[a][a] += m.armature[iv + a];
-        }
-        llt_inverse(nvj, StU, Di);
-        for (int k = 0; k < nvj; ++k)
-        {
-          T UDk[6], Dk[6];
-          for (int a = 0; a < 6; ++a)
-          {
-            T acc = U[a][0] * Di[0][k];
-            for (int c = 1; c < nvj; ++c) acc += U[a][c] * Di[c][k];
-            UD[a][k] = acc;
-            UDk[a] = acc;
-            Dk[a] = a < nvj ? Di[k][a] : T(0);
-          }
-          st6(P0 + k * CB_STRIDE + A_UD, UDk);
-          st6(P0 + k * CB_STRIDE + A_DINV, Dk);
-        }
-        if (parent > 0)
-        {
-          for (int a = 0; a < 6; ++a)
-            for (int b = a; b < 6; ++b)
-            {
-              T acc = UD[a][0] * U[b][0];
-              for (int k = 1; k < nvj; ++k) acc += UD[a][k] * U[b][k];
-              Ia[a * 6 - (a * (a - 1)) / 2 + (b - a)] -= acc;
-            }
-          T abv[6], Iab[6];
-          m2a(ab, abv);
-          sym6_mul(Ia, abv, Iab);
-          for (int a = 0; a < 6; ++a)
-          {
-            T acc = UD[a][0] * uj[0];
-            for (int k = 1; k < nvj; ++k) acc += UD[a][k] * uj[k];
-            f[a] += Iab[a] + acc;
-          }
-          for (int k = 0; k < 21; ++k) P0[A_IACC + k] = Ia[k];
-          st6(P0 + A_PA, f);
-        }
+        for (int k = 0; k < 21; ++k) P0[A_IACC + k] = Ia[k];
+        st6(P0 + A_PA, f);
       }
     }
+    // multi-dof joints of this depth: all lanes together, one joint after the other
+    if (tb.lvl_multi & (1u << l))
+      for (int s = tb.lvl_start[l]; s < tb.lvl_start[l + 1]; ++s)
+      {
+        const int i = tb.lvl_joint[s];
+        if (m.nvj[i] > 1) coop_aba_multidof<T, G>(m, tb, jr, cb, su, sc, gl, i, xoff);
+      }
     BRBD_SYNCWARP();
   }
 }
 
-// ---- A3: upper rows of Minv, lanes = columns -------------------------------------------------------------
+// ---- A3: upper rows of Minv, lanes = columns (NCB columns per lane, interleaved) -------------------------
 // For column c and every joint i on the root path of joint(c), leaf to root (aba-derivatives.hxx:131-166):
 //   own block:      Minv(i, c) = Dinv
 //   ancestors:      Minv(i, c) = -(J_i Dinv_i)^T F,   then   F += U_i Minv(i, c),   F = Fcrb[0](:, c)
-template<class T, int G>
-BRBD_DI void coop_minv_upper(const ModelPOD<T> & m, const T * cb, T * Minv, int mld, int gl)
+template<class T, int G, int NCB>
+BRBD_DI void coop_minv_upper(const ModelPOD<T> & m, const CoopTables & tb, const T * cb, T * Minv, int mld, int gl)
 {
-  const int nv = m.nv, nj = m.njoints;
-  for (int cblk = 0; cblk < nv; cblk += G)
-  {
-    const int c = cblk + gl;
-    T F[6] = {T(0), T(0), T(0), T(0), T(0), T(0)};
-    for (int i = nj - 1; i > 0; --i)
-    {
-      const int iv = m.idx_v[i], nvj = m.nvj[i], nsub = m.nvsub[i], parent = m.parent[i];
-      if (iv + nsub <= cblk || iv >= cblk + G) continue; // no column of this block below joint i
-      if (c < iv || c >= iv + nsub) continue;
-      const T * P0 = cb + iv * CB_STRIDE;
-      const bool own = c < iv + nvj;
-      if (nvj == 1)
-      {
-        T Jv[6], U[6];
-        const T Dinv = P0[A_DINV];
-        T mk = Dinv;
-        if (!own)
-        {
-          ld6(P0 + CB_J, Jv);
-          mk = -(Dinv * dot6a(Jv, F));
-        }
-        Minv[iv * mld + c] = mk;
-        if (parent > 0)
-        {
-          ld6(P0 + A_U, U);
+  const int nj = m.njoints;
+  T F[NCB][6];
 #pragma unroll
-          for (int k = 0; k < 6; ++k) F[k] += U[k] * mk;
+  for (int b = 0; b < NCB; ++b)
+#pragma unroll
+    for (int k = 0; k < 6; ++k) F[b][k] = T(0);
+  for (int i = nj - 1; i > 0; --i)
+  {
+    const unsigned info = tb.jinfo[i]; // idx_v | nv_joint << 8 | (idx_v + nvSubtree) << 16 | (parent > 0) << 24
+    const int iv = info & 0xff, nvj = (info >> 8) & 0xff, end = (info >> 16) & 0xff;
+    const bool hp = (info >> 24) != 0;
+    const T * P0 = cb + iv * CB_STRIDE;
+    if (nvj == 1)
+    {
+      T Jv[6], U[6];
+      const T Dinv = P0[A_DINV];
+      ld6(P0 + CB_J, Jv);
+      if (hp) ld6(P0 + A_U, U);
+#pragma unroll
+      for (int b = 0; b < NCB; ++b)
+      {
+        const int c = gl + b * G;
+        if (c >= iv && c < end)
+        {
+          const T mk = (c == iv) ? Dinv : -(Dinv * dot6a(Jv, F[b]));
+          Minv[iv * mld + c] = mk;
+          if (hp)
+          {
+#pragma unroll
+            for (int k = 0; k < 6; ++k) F[b][k] += U[k] * mk;
+          }
         }
       }
-      else
+    }
+    else
+    {
+#pragma unroll
+      for (int b = 0; b < NCB; ++b)
       {
-        T jf[6], mk[6];
-        if (!own)
-          for (int a = 0; a < nvj; ++a)
-          {
-            T Jv[6];
-            ld6(P0 + a * CB_STRIDE + CB_J, Jv);
-            jf[a] = dot6a(Jv, F);
-          }
-        for (int k = 0; k < nvj; ++k)
+        const int c = gl + b * G;
+        if (c >= iv && c < end)
         {
-          const T * Dk = P0 + k * CB_STRIDE + A_DINV; // row k of Dinv (symmetric)
-          T val;
-          if (own) val = Dk[c - iv];
-          else
+          const bool own = c < iv + nvj;
+          T jf[6], mk[6];
+#pragma unroll
+          for (int a = 0; a < 6; ++a)
           {
-            val = Dk[0] * jf[0];
-            for (int a = 1; a < nvj; ++a) val += Dk[a] * jf[a];
-            val = -val;
+            jf[a] = T(0);
+            if (a < nvj && !own)
+            {
+              T Jv[6];
+              ld6(P0 + a * CB_STRIDE + CB_J, Jv);
+              jf[a] = dot6a(Jv, F[b]);
+            }
           }
-          mk[k] = val;
-          Minv[(iv + k) * mld + c] = val;
+#pragma unroll
+          for (int k = 0; k < 6; ++k)
+          {
+            mk[k] = T(0);
+            if (k < nvj)
+            {
+              const T * Dk = P0 + k * CB_STRIDE + A_DINV; // row k of Dinv (symmetric), zero-padded to 6
+              T Dr[6];
+              ld6(Dk, Dr);
+              const T val = own ? Dk[c - iv] : -dot6a(Dr, jf);
+              mk[k] = val;
+              Minv[(iv + k) * mld + c] = val;
+            }
+          }
+          if (hp)
+          {
+#pragma unroll
+            for (int k = 0; k < 6; ++k)
+              if (k < nvj)
+              {
+                T U[6];
+                ld6(P0 + k * CB_STRIDE + A_U, U);
+#pragma unroll
+                for (int a = 0; a < 6; ++a) F[b][a] += U[a] * mk[k];
+              }
+          }
         }
-        if (parent > 0)
-          for (int k = 0; k < nvj; ++k)
-          {
-            T U[6];
-            ld6(P0 + k * CB_STRIDE + A_U, U);
-            for (int a = 0; a < 6; ++a) F[a] += U[a] * mk[k];
-          }
       }
     }
   }
@@ -310,23 +430,31 @@ BRBD_DI void coop_aba_forward2(const ModelPOD<T> & m, const CoopTables & tb, T *
       }
       else
       {
-        T dd[6];
-        for (int k = 0; k < nvj; ++k)
+        T dd[6], uu[6];
+#pragma unroll
+        for (int k = 0; k < 6; ++k) uu[k] = k < nvj ? su[iv + k] : T(0);
+#pragma unroll
+        for (int k = 0; k < 6; ++k)
         {
-          T UD[6];
-          ld6(P0 + k * CB_STRIDE + A_UD, UD);
-          const T * Dk = P0 + k * CB_STRIDE + A_DINV;
-          T t1 = Dk[0] * su[iv];
-          for (int c = 1; c < nvj; ++c) t1 += Dk[c] * su[iv + c];
-          dd[k] = t1 - dot6a(UD, ag);
+          dd[k] = T(0);
+          if (k < nvj)
+          {
+            T UD[6], Dr[6];
+            ld6(P0 + k * CB_STRIDE + A_UD, UD);
+            ld6(P0 + k * CB_STRIDE + A_DINV, Dr);
+            dd[k] = dot6a(Dr, uu) - dot6a(UD, ag);
+          }
         }
-        for (int k = 0; k < nvj; ++k)
-        {
-          T Jv[6];
-          ld6(P0 + k * CB_STRIDE + CB_J, Jv);
-          su[iv + k] = dd[k];
-          for (int a = 0; a < 6; ++a) ag[a] += Jv[a] * dd[k];
-        }
+#pragma unroll
+        for (int k = 0; k < 6; ++k)
+          if (k < nvj)
+          {
+            T Jv[6];
+            ld6(P0 + k * CB_STRIDE + CB_J, Jv);
+            su[iv + k] = dd[k];
+#pragma unroll
+            for (int a = 0; a < 6; ++a) ag[a] += Jv[a] * dd[k];
+          }
       }
 #pragma unroll
       for (int k = 0; k < 6; ++k) r[JR_OA + k] = ag[k];
@@ -335,71 +463,80 @@ BRBD_DI void coop_aba_forward2(const ModelPOD<T> & m, const CoopTables & tb, T *
   }
 }
 
-// ---- A5: completion of Minv, lanes = columns (aba-derivatives.hxx:220-234), then the mirror (:448-449) -----
-template<class T, int G>
+// ---- A5: completion of Minv, lanes = columns, one tangent row per step (aba-derivatives.hxx:220-234) -------
+//   Minv(r, c) -= UDinv_r^T Fcrb[parent](:, c)   for every column c >= idx_v of the joint owning row r
+//   Fcrb[i](:, c) = Fcrb[parent](:, c) + sum over the joint's rows of J_r Minv(r, c)
+// Fcrb of the current chain stays in registers; it is saved at joints with several children and reloaded when the
+// depth-first order returns to them.  Entries right of the joint's own block are mirrored into the lower triangle
+// as they become final (:448-449); the own blocks of multi-dof joints are mirrored at the end.
+template<class T, int G, int NCB>
 BRBD_DI void coop_minv_complete(const ModelPOD<T> & m, const CoopTables & tb, T * cb, T * Minv, int mld, int gl)
 {
   const int nv = m.nv, nj = m.njoints;
-  for (int cblk = 0; cblk < nv; cblk += G)
-  {
-    const int c = cblk + gl;
-    const int cs = c < nv ? c : nv - 1; // idle lanes shadow the last column's save slots (never read back as active)
-    T * save = cb + cs * CB_STRIDE + A_FD;
-    T Fd[6] = {T(0), T(0), T(0), T(0), T(0), T(0)};
-    for (int i = 1; i < nj; ++i)
-    {
-      const int iv = m.idx_v[i], nvj = m.nvj[i], parent = m.parent[i];
-      if (iv >= cblk + G) break;
-      const bool active = c >= iv && c < nv;
-      if (active)
-      {
-        if (parent > 0 && parent != i - 1) ld6(save + 6 * tb.bslot[parent], Fd);
-        const T * P0 = cb + iv * CB_STRIDE;
-        const bool in_sub = c < iv + m.nvsub[i]; // right of the subtree the upper triangle starts at zero (:414)
-        if (nvj == 1)
-        {
-          T Jv[6];
-          T mv = in_sub ? Minv[iv * mld + c] : T(0);
-          if (parent > 0)
-          {
-            T UD[6];
-            ld6(P0 + A_UD, UD);
-            mv -= dot6a(UD, Fd);
-          }
-          Minv[iv * mld + c] = mv;
-          ld6(P0 + CB_J, Jv);
+  T Fd[NCB][6], acc[NCB][6];
+  T * save[NCB];
 #pragma unroll
-          for (int k = 0; k < 6; ++k) Fd[k] = (parent > 0 ? Fd[k] : T(0)) + Jv[k] * mv;
-        }
-        else
+  for (int b = 0; b < NCB; ++b)
+  {
+    const int c = gl + b * G;
+    save[b] = cb + (c < nv ? c : nv - 1) * CB_STRIDE + A_FD;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) { Fd[b][k] = T(0); acc[b][k] = T(0); }
+  }
+  for (int r = 0; r < nv; ++r)
+  {
+    const unsigned info = tb.rinfo[r]; // idx_v | own_end << 8 | sub_end << 16 | flags << 24 (1 first row, 2 last row, 4 parent > 0)
+    const int slots = tb.rslots[r];    // load slot | save slot << 8 (0xff = none)
+    const int iv = info & 0xff, own_end = (info >> 8) & 0xff, sub_end = (info >> 16) & 0xff;
+    const bool first = (info >> 24) & 1, last = (info >> 24) & 2, hp = (info >> 24) & 4;
+    const int lslot = slots & 0xff, sslot = (slots >> 8) & 0xff;
+    const T * Pr = cb + r * CB_STRIDE;
+    T Jv[6], UD[6];
+    ld6(Pr + CB_J, Jv);
+    if (hp) ld6(Pr + A_UD, UD);
+#pragma unroll
+    for (int b = 0; b < NCB; ++b)
+    {
+      const int c = gl + b * G;
+      if (c >= iv && c < nv)
+      {
+        if (first)
         {
-          T acc[6];
-          for (int a = 0; a < 6; ++a) acc[a] = parent > 0 ? Fd[a] : T(0);
-          for (int k = 0; k < nvj; ++k)
-          {
-            T mv = in_sub ? Minv[(iv + k) * mld + c] : T(0);
-            if (parent > 0)
-            {
-              T UD[6];
-              ld6(P0 + k * CB_STRIDE + A_UD, UD);
-              mv -= dot6a(UD, Fd);
-            }
-            Minv[(iv + k) * mld + c] = mv;
-            T Jv[6];
-            ld6(P0 + k * CB_STRIDE + CB_J, Jv);
-            for (int a = 0; a < 6; ++a) acc[a] += Jv[a] * mv;
-          }
-          for (int a = 0; a < 6; ++a) Fd[a] = acc[a];
+          if (lslot != 0xff) ld6(save[b] + 6 * lslot, Fd[b]);
+#pragma unroll
+          for (int k = 0; k < 6; ++k) acc[b][k] = hp ? Fd[b][k] : T(0);
         }
-        if (tb.bslot[i] >= 0) st6(save + 6 * tb.bslot[i], Fd);
+        T mv = c < sub_end ? Minv[r * mld + c] : T(0); // right of the subtree the upper triangle starts at zero (:414)
+        if (hp) mv -= dot6a(UD, Fd[b]);
+        Minv[r * mld + c] = mv;
+        if (c >= own_end) Minv[c * mld + r] = mv;
+#pragma unroll
+        for (int k = 0; k < 6; ++k) acc[b][k] += Jv[k] * mv;
+        if (last)
+        {
+#pragma unroll
+          for (int k = 0; k < 6; ++k) Fd[b][k] = acc[b][k];
+          if (sslot != 0xff) st6(save[b] + 6 * sslot, Fd[b]);
+        }
       }
     }
   }
   BRBD_SYNCWARP();
-  // lower triangle := upper triangle
-  for (int r = 0; r < nv; ++r)
-    for (int c = r + 1 + gl; c < nv; c += G) Minv[c * mld + r] = Minv[r * mld + c];
-  BRBD_SYNCWARP();
+  if (tb.lvl_multi)
+  {
+    for (int i = 1; i < nj; ++i)
+    {
+      const unsigned info = tb.jinfo[i];
+      const int iv = info & 0xff, nvj = (info >> 8) & 0xff;
+      if (nvj > 1)
+        for (int e = gl; e < nvj * nvj; e += G)
+        {
+          const int a = e / nvj, b = e % nvj;
+          if (a > b) Minv[(iv + a) * mld + iv + b] = Minv[(iv + b) * mld + iv + a];
+        }
+    }
+    BRBD_SYNCWARP();
+  }
 }
 
 // ---- C: blocks of dtau_dq / dtau_dv columns -> shared memory -> -Minv * block -> global ---------------------
@@ -535,10 +672,19 @@ BRBD_DI void aba_derivatives_coop_config(const ModelPOD<T> & m, const CoopTables
   const int nv = m.nv, mld = L.mld;
   int oa_unused = JR_OA;
   const int xoff = coop_forward<T, G, false>(m, tb, sq, sv, (const T *)nullptr, jr, cb, gl, &oa_unused);
-  coop_aba_backward<T, G>(m, tb, jr, cb, su, gl, xoff);
-  coop_minv_upper<T, G>(m, cb, Minv, mld, gl);
-  coop_aba_forward2<T, G>(m, tb, jr, cb, su, gl);
-  coop_minv_complete<T, G>(m, tb, cb, Minv, mld, gl);
+  coop_aba_backward<T, G>(m, tb, jr, cb, su, base + L.osc, gl, xoff);
+  if (G == 32 && nv > G)
+  {
+    coop_minv_upper<T, G, (G == 32 ? 2 : 1)>(m, tb, cb, Minv, mld, gl);
+    coop_aba_forward2<T, G>(m, tb, jr, cb, su, gl);
+    coop_minv_complete<T, G, (G == 32 ? 2 : 1)>(m, tb, cb, Minv, mld, gl);
+  }
+  else
+  {
+    coop_minv_upper<T, G, 1>(m, tb, cb, Minv, mld, gl);
+    coop_aba_forward2<T, G>(m, tb, jr, cb, su, gl);
+    coop_minv_complete<T, G, 1>(m, tb, cb, Minv, mld, gl);
+  }
   coop_joint_quantities<T, G, false>(m, jr, gl, xoff, JR_OA);
   coop_subtree_sums<T, G>(m, jr, gl);
   coop_columns<T, G>(m, jr, cb, (T *)nullptr, gl);
@@ -551,8 +697,14 @@ BRBD_DI void aba_derivatives_coop_config(const ModelPOD<T> & m, const CoopTables
   }
   if (active)
   {
-    for (int c = 0; c < nv; ++c)
-      for (int r = gl; r < nv; r += G) gm[c * nv + r] = Minv[c * mld + r];
+    int c = 0, r = gl;
+    while (r >= nv) { r -= nv; ++c; }
+    for (int e = gl; e < nv * nv; e += G)
+    {
+      gm[e] = Minv[c * mld + r];
+      r += G;
+      while (r >= nv) { r -= nv; ++c; }
+    }
     if (gddq)
       for (int k = gl; k < nv; k += G) gddq[k] = su[k];
   }

@@ -40,6 +40,10 @@ struct CoopTables
   short jlast[MAXJ];                  // last joint of the subtree of i (depth-first numbering: subtree = [i, jlast[i]])
   short bslot[MAXJ];                  // save slot of a joint with two or more children (-1 otherwise), see aba_deriv_coop.cuh
   int nbranch;                        // number of such joints
+  unsigned lvl_multi;                 // bit l: depth l has a joint with more than one degree of freedom
+  unsigned jinfo[MAXJ];               // idx_v | nv_joint << 8 | (idx_v + nvSubtree) << 16 | (parent > 0) << 24
+  unsigned rinfo[MAXNV];              // per tangent row: idx_v | own_end << 8 | sub_end << 16 | flags << 24 (1 first row of its joint, 2 last, 4 parent > 0)
+  unsigned short rslots[MAXNV];       // per tangent row: load slot (first row, parent is not the previous joint) | save slot << 8 (last row); 0xff = none
 };
 inline void build_coop_tables(const ModelPOD<double> & M, CoopTables & C)
 {
@@ -73,6 +77,21 @@ inline void build_coop_tables(const ModelPOD<double> & M, CoopTables & C)
     int nchild = 0;
     for (int k = i + 1; k < M.njoints; ++k) nchild += (M.parent[k] == i);
     C.bslot[i] = (short)((i > 0 && nchild >= 2) ? C.nbranch++ : -1);
+  }
+  C.lvl_multi = 0;
+  for (int i = 1; i < M.njoints; ++i)
+  {
+    const int iv = M.idx_v[i], nvj = M.nvj[i], p = M.parent[i];
+    if (nvj > 1) C.lvl_multi |= 1u << M.depth[i];
+    C.jinfo[i] = (unsigned)iv | ((unsigned)nvj << 8) | ((unsigned)(iv + M.nvsub[i]) << 16) | ((unsigned)(p > 0) << 24);
+    for (int k = 0; k < nvj; ++k)
+    {
+      const unsigned flags = (k == 0 ? 1u : 0u) | (k == nvj - 1 ? 2u : 0u) | (p > 0 ? 4u : 0u);
+      C.rinfo[iv + k] = (unsigned)iv | ((unsigned)(iv + nvj) << 8) | ((unsigned)(iv + M.nvsub[i]) << 16) | (flags << 24);
+      const unsigned lslot = (k == 0 && p > 0 && p != i - 1) ? (unsigned)C.bslot[p] : 0xffu;
+      const unsigned sslot = (k == nvj - 1 && C.bslot[i] >= 0) ? (unsigned)C.bslot[i] : 0xffu;
+      C.rslots[iv + k] = (unsigned short)(lslot | (sslot << 8));
+    }
   }
   C.nsteps = 0;
   while ((1 << C.nsteps) < M.maxdepth) ++C.nsteps;
