@@ -31,8 +31,10 @@ MODEL = "simple_humanoid_ff"
 BATCH = 65536
 L2_BYTES = 126 * 1024 * 1024
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures
-# (profiles/README.md); None until a capture of the current kernel exists
-NCU_TRAFFIC = {"crba": None, "aba": None}
+# (profiles/r1_v3_step_ncu_full.csv: crba_tmem_kernel<double,192> 37.9 MB read + 593.9 MB written, aba_tmem_kernel<double,128>
+# 367.3 MB read + 434.9 MB written — the ABA figure is 11x its 74 MB of algorithmic bytes: the pass-3 record store
+# does not stay L2-resident next to the 642 MB CRBA output); bytes per launch of 65536 configurations
+NCU_TRAFFIC = {"crba": 631.85e6, "aba": 802.21e6}
 
 
 def load_model(name):

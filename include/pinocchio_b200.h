@@ -134,6 +134,28 @@ brbd_status brbd_aba_derivatives_batch(brbd_pool * p, const void * q, int64_t ld
                                        void * ddq_dtau, int64_t ld_dtau, void * ddq, int64_t ldddq,
                                        int64_t batch, int flags);
 
+/* ---- the callers' other needs, on the same sweeps ---------------------------------------- */
+/* nle[:,i] = nonLinearEffects(q[:,i], v[:,i])  (algorithm/rnea.hpp:105, rnea.hxx:227-343) = rnea(q, v, 0) */
+brbd_status brbd_nle_batch(brbd_pool * p, const void * q, int64_t ldq, const void * v, int64_t ldv,
+                           void * nle, int64_t ldn, int64_t batch, int flags);
+/* g[:,i] = computeGeneralizedGravity(q[:,i])   (algorithm/rnea.hpp:133, rnea.hxx:346-452) = rnea(q, 0, 0) */
+brbd_status brbd_gravity_batch(brbd_pool * p, const void * q, int64_t ldq, void * g, int64_t ldg,
+                               int64_t batch, int flags);
+/* Minv[:,i] = vec(computeMinverse(q[:,i]))      (algorithm/aba.hpp:106, aba.hxx:613-902): upper triangle of
+ * M^-1, strictly-lower part written as zeros (a fresh data.Minv). ldM >= nv*nv. */
+brbd_status brbd_minverse_batch(brbd_pool * p, const void * q, int64_t ldq, void * Minv, int64_t ldM,
+                                int64_t batch, int flags);
+/* qout[:,i] = integrate(model, q[:,i], v[:,i])  (algorithm/joint-configuration.hpp:49-74) */
+brbd_status brbd_integrate_batch(brbd_pool * p, const void * q, int64_t ldq, const void * v, int64_t ldv,
+                                 void * qout, int64_t ldqo, int64_t batch, int flags);
+/* One semi-implicit Euler step of forward dynamics, entirely on the device:
+ *   a = aba(q, v, tau);  v_next = v + dt a;  q_next = integrate(q, dt v_next)
+ * (the loop of examples/simulation-pendulum.py:153-157: a = aba(...); v += a dt; q = integrate(model, q, v dt)).
+ * q_next / v_next must not alias q / v. */
+brbd_status brbd_aba_euler_step_batch(brbd_pool * p, const void * q, int64_t ldq, const void * v, int64_t ldv,
+                                      const void * tau, int64_t ldtau, double dt, void * q_next,
+                                      int64_t ldqn, void * v_next, int64_t ldvn, int64_t batch, int flags);
+
 /* Page-lock caller-owned host memory (cudaHostRegister / cudaHostUnregister).  Host-pointer calls work on
  * pageable memory too, but only pinned memory reaches the full link bandwidth (measured on this pool's
  * B200 hosts: 57 GB/s pinned vs 11-22 GB/s pageable) and lets the upload / compute / download pipeline of a

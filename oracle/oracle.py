@@ -134,6 +134,38 @@ class Oracle:
                                       ctypes.c_int64(B), int(nthreads), int(long_double))
         return dq, dv, dtau, ddq
 
+    # ---- the callers' other needs ----
+    def nle(self, q, v, nthreads=1):
+        """nonLinearEffects (algorithm/rnea.hxx:227-343): the same two sweeps as rnea with the S*a term dropped, i.e.
+        rnea(q, v, 0) — the identity the reference asserts in unittest/rnea.cpp:201-206."""
+        q, v = _cols(q, self.nq), _cols(v, self.nv)
+        return self.rnea(q, v, np.zeros_like(v), nthreads=nthreads)
+
+    def gravity(self, q, nthreads=1):
+        """computeGeneralizedGravity (algorithm/rnea.hxx:346-452) == rnea(q, 0, 0), unittest/rnea.cpp:225-228."""
+        q = _cols(q, self.nq)
+        z = np.zeros((self.nv, q.shape[1]), order="F")
+        return self.rnea(q, z, z, nthreads=nthreads)
+
+    def minverse(self, q, nthreads=1):
+        """computeMinverse (algorithm/aba.hxx:613-902): upper triangle of M^-1, strictly-lower part zero (a fresh
+        data.Minv).  Taken from the Minv recursion of abaDerivatives, which the reference asserts equal to
+        computeMinverse (unittest/aba-derivatives.cpp:96-100); it does not depend on v or tau."""
+        q = _cols(q, self.nq)
+        z = np.zeros((self.nv, q.shape[1]), order="F")
+        Minv = self.aba_derivatives(q, z, z, nthreads=nthreads)[2]
+        nv = self.nv
+        mask = np.triu(np.ones((nv, nv), dtype=bool)).reshape(-1, order="F")
+        return np.asfortranarray(Minv * mask[:, None])
+
+    def integrate(self, q, v, long_double=False):
+        """integrate(model, q, v) (algorithm/joint-configuration.hpp:49-74), column by column."""
+        q, v = _cols(q, self.nq), _cols(v, self.nv)
+        B = q.shape[1]
+        out = np.empty((self.nq, B), order="F")
+        _lib().oracle_integrate(self._h, _p(q), _p(v), _p(out), ctypes.c_int64(B), int(long_double))
+        return out
+
     ALGOS = {"rnea": 0, "aba": 1, "crba_world": 2, "crba_local": 3, "rnea_derivatives": 4, "aba_derivatives": 5}
 
     def count_flops(self, algo: str, q, v, a):

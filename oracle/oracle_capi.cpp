@@ -182,6 +182,25 @@ void oracle_aba_derivatives(const oracle_model * m, const double * q, const doub
   else aba_derivs_batch(m->md, q, v, tau, dq, dv, dtau, ddq, B, nthreads);
 }
 
+// qout[:, i] = integrate(model, q[:, i], v[:, i])  (algorithm/joint-configuration.hpp:49-74)
+void oracle_integrate(const oracle_model * m, const double * q, const double * v, double * qout, int64_t B, int precision)
+{
+  for (int64_t i = 0; i < B; ++i)
+  {
+    if (precision)
+    {
+      const Model<long double> & ml = m->ml;
+      std::vector<long double> tq(ml.nq), tv(ml.nv), to(ml.nq);
+      for (int k = 0; k < ml.nq; ++k) tq[k] = q[i * ml.nq + k];
+      for (int k = 0; k < ml.nv; ++k) tv[k] = v[i * ml.nv + k];
+      integrate(ml, tq.data(), tv.data(), to.data());
+      for (int k = 0; k < ml.nq; ++k) qout[i * ml.nq + k] = (double)to[k];
+    }
+    else
+      integrate(m->md, q + i * m->md.nq, v + i * m->md.nv, qout + i * m->md.nq);
+  }
+}
+
 // Exact algorithmic operation counts of one evaluation: out = {add, mul, div, sqrt, sincos}.
 // algo: 0 rnea, 1 aba(world), 2 crba(world), 3 crba(local), 4 rnea-derivatives, 5 aba-derivatives
 void oracle_count_flops(const oracle_model * m, int algo, const double * q, const double * v, const double * a,

@@ -1254,4 +1254,135 @@ void abaDerivatives(const Model<S> & model, Data<S> & data, const S * q, const S
 #undef DTV
 }
 
+// ---------------------------------------------------------------------------------------------
+// integrate(model, q, v) — algorithm/joint-configuration.hpp:49-74 -> IntegrateStep -> per-joint Lie group
+// integrate_impl (multibody/liegroup/liegroup-algo.hxx).  Quaternions are stored (x, y, z, w) as in the
+// configuration vector; the Eigen operations of the reference (quaternion product, quaternion * vector,
+// AngleAxis -> quaternion) are restated from their Eigen 3.4 definitions.
+// ---------------------------------------------------------------------------------------------
+template<class S> inline S taylor_precision3() { return S(0.0001220703125); } // pow(epsilon, 1/4), math/taylor-expansion.hpp:30-36 (2^-13 for double)
+template<> inline float taylor_precision3<float>() { return std::pow(std::numeric_limits<float>::epsilon(), 0.25f); }
+template<> inline long double taylor_precision3<long double>() { return powl(std::numeric_limits<long double>::epsilon(), 0.25L); }
+
+// Eigen::Quaternion operator* (Eigen/src/Geometry/Quaternion.h, quat_product)
+template<class S> inline void quatMul(const S * a, const S * b, S * r)
+{
+  const S ax = a[0], ay = a[1], az = a[2], aw = a[3], bx = b[0], by = b[1], bz = b[2], bw = b[3];
+  r[3] = aw * bw - ax * bx - ay * by - az * bz;
+  r[0] = aw * bx + ax * bw + ay * bz - az * by;
+  r[1] = aw * by + ay * bw + az * bx - ax * bz;
+  r[2] = aw * bz + az * bw + ax * by - ay * bx;
+}
+// Eigen::QuaternionBase::_transformVector: v + w * (2 q x v) + q x (2 q x v)
+template<class S> inline V3<S> quatRotate(const S * q, const V3<S> & v)
+{
+  const V3<S> qv(q[0], q[1], q[2]);
+  V3<S> uv = cross(qv, v);
+  uv += uv;
+  return v + q[3] * uv + cross(qv, uv);
+}
+// quaternion::exp3 — spatial/explog-quaternion.hpp:25-64
+template<class S> inline void quatExp3(const V3<S> & w, S * quat)
+{
+  const S eps = eps_s<S>();
+  const S t2 = dot(w, w);
+  const S t = sqrt_s(t2 + eps * eps);
+  const S ts_prec = taylor_precision3<S>();
+  if (t2 > ts_prec)
+  {
+    // Eigen::AngleAxis(t, w / t) -> Quaternion: w = cos(t/2), vec = sin(t/2) * axis
+    S sh, ch;
+    sincos_s(S(0.5) * t, sh, ch);
+    for (int k = 0; k < 3; ++k) quat[k] = sh * (w[k] / t);
+    quat[3] = ch;
+  }
+  else
+  {
+    const S t2_2 = t2 / S(4);
+    const S a = S(0.5) * (S(1) - t2_2 / S(6) + t2_2 * t2_2 / S(120));
+    for (int k = 0; k < 3; ++k) quat[k] = a * w[k];
+    quat[3] = S(1) - t2_2 / S(2) + t2_2 * t2_2 / S(24);
+  }
+}
+// quaternion::exp6 — spatial/explog-quaternion.hpp:92-136; out = (translation, quaternion)
+template<class S> inline void quatExp6(const V3<S> & v, const V3<S> & w, V3<S> & trans, S * quat)
+{
+  const S eps = eps_s<S>();
+  const S t2 = dot(w, w) + eps * eps;
+  const S t = sqrt_s(t2);
+  S st, ct;
+  sincos_s(t, st, ct);
+  const S inv_t2 = S(1) / t2;
+  const S ts_prec = taylor_precision3<S>();
+  const S alpha_wxv = (t < ts_prec) ? S(0.5) - t2 / S(24) : (S(1) - ct) * inv_t2;
+  const S alpha_w2 = (t < ts_prec) ? S(1) / S(6) - t2 / S(120) : (t - st) * inv_t2 / t;
+  const V3<S> wxv = cross(w, v);
+  trans = v + alpha_wxv * wxv + alpha_w2 * cross(w, wxv);
+  quatExp3(w, quat);
+}
+// quaternion::firstOrderNormalize — math/quaternion.hpp:90-111
+template<class S> inline void quatFirstOrderNormalize(S * q)
+{
+  const S N2 = q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3];
+  const S alpha = (S(3) - N2) / S(2);
+  for (int k = 0; k < 4; ++k) q[k] *= alpha;
+}
+
+template<class S> void integrate(const Model<S> & model, const S * q, const S * v, S * qout)
+{
+  for (int i = 1; i < model.njoints; ++i)
+  {
+    const S * qj = q + model.idx_q[i];
+    const S * vj = v + model.idx_v[i];
+    S * o = qout + model.idx_q[i];
+    const int t = model.type[i];
+    if (t <= BRBD_JOINT_PZ)
+      o[0] = qj[0] + vj[0]; // VectorSpaceOperation::integrate_impl, liegroup/vector-space.hpp:142-150
+    else if (t == BRBD_JOINT_FREEFLYER)
+    {
+      // SpecialEuclideanOperationTpl<3>::integrate_impl, liegroup/special-euclidean.hpp:660-698
+      V3<S> trans;
+      S quat1[4], res[4];
+      quatExp6(V3<S>(vj[0], vj[1], vj[2]), V3<S>(vj[3], vj[4], vj[5]), trans, quat1);
+      const V3<S> p = quatRotate(qj + 3, trans);
+      for (int k = 0; k < 3; ++k) o[k] = p[k] + qj[k];
+      quatMul(qj + 3, quat1, res);
+      const S dp = res[0] * qj[3] + res[1] * qj[4] + res[2] * qj[5] + res[3] * qj[6];
+      for (int k = 0; k < 4; ++k) res[k] = (dp < S(0)) ? -res[k] : res[k];
+      quatFirstOrderNormalize(res);
+      for (int k = 0; k < 4; ++k) o[3 + k] = res[k];
+    }
+    else if (t == BRBD_JOINT_SPHERICAL)
+    {
+      // SpecialOrthogonalOperationTpl<3>::integrate_impl, liegroup/special-orthogonal.hpp:467-481
+      S pOmega[4], res[4];
+      quatExp3(V3<S>(vj[0], vj[1], vj[2]), pOmega);
+      quatMul(qj, pOmega, res);
+      quatFirstOrderNormalize(res);
+      for (int k = 0; k < 4; ++k) o[k] = res[k];
+    }
+    else
+    {
+      // planar: SpecialEuclideanOperationTpl<2>::integrate_impl (special-euclidean.hpp:289-306) with exp (:61-90);
+      // q = (x, y, cos, sin), v = (vx, vy, omega)
+      const S c0 = qj[2], s0 = qj[3];
+      const S omega = vj[2];
+      S sv, cv;
+      sincos_s(omega, sv, cv);
+      // vcross = (-v1, v0) - (-v1 R.col(0) + v0 R.col(1)), R = [[cv, -sv], [sv, cv]]
+      S vc0 = -vj[1] - (-vj[1] * cv + vj[0] * (-sv));
+      S vc1 = vj[0] - (-vj[1] * sv + vj[0] * cv);
+      vc0 = vc0 / omega;
+      vc1 = vc1 / omega;
+      const S omega_abs = (omega < S(0)) ? -omega : omega;
+      const S t0 = (omega_abs > S(1e-14)) ? vc0 : vj[0];
+      const S t1 = (omega_abs > S(1e-14)) ? vc1 : vj[1];
+      o[0] = (c0 * t0 - s0 * t1) + qj[0]; // R0 * t + t0
+      o[1] = (s0 * t0 + c0 * t1) + qj[1];
+      o[2] = c0 * cv - s0 * sv; // R0 * R.col(0)
+      o[3] = s0 * cv + c0 * sv;
+    }
+  }
+}
+
 } // namespace rbdo

@@ -10,7 +10,8 @@ from .model import (JOINT_FREEFLYER, JOINT_PLANAR, JOINT_PX, JOINT_PY, JOINT_PZ,
                     buildSampleModelHumanoidRandom, buildSampleModelManipulator)
 from .joint_configuration import (LibcRand, batched_random_configuration, batched_random_tangent, integrate,  # noqa: F401
                                   neutral, randomConfiguration)
-from .pool import (ModelPool, abaInParallel, computeABADerivativesInParallel, computeRNEADerivativesInParallel,  # noqa: F401
-                   crbaInParallel, pin_host, rneaInParallel, unpin_host)
+from .pool import (ModelPool, abaEulerStepInParallel, abaInParallel, computeABADerivativesInParallel,  # noqa: F401
+                   computeGeneralizedGravityInParallel, computeMinverseInParallel, computeRNEADerivativesInParallel,
+                   crbaInParallel, integrateInParallel, nonLinearEffectsInParallel, pin_host, rneaInParallel, unpin_host)
 
 __version__ = "0.1.0"

@@ -24,7 +24,8 @@ SYMBOLS = [
     "brbd_pool_size", "brbd_pool_update", "brbd_pool_set_stream", "brbd_pool_synchronize",
     "brbd_pool_launch_count", "brbd_pool_last_kernel_ms", "brbd_rnea_batch", "brbd_aba_batch", "brbd_crba_batch",
     "brbd_rnea_derivatives_batch", "brbd_aba_derivatives_batch", "brbd_measure_fp64_peak",
-    "brbd_host_register", "brbd_host_unregister",
+    "brbd_host_register", "brbd_host_unregister", "brbd_nle_batch", "brbd_gravity_batch", "brbd_minverse_batch",
+    "brbd_integrate_batch", "brbd_aba_euler_step_batch",
 ]
 
 
@@ -82,6 +83,11 @@ def lib():
     L.brbd_crba_batch.argtypes = [vp, vp, i64, vp, i64, i64, ci]
     L.brbd_rnea_derivatives_batch.argtypes = [vp, vp, i64, vp, i64, vp, i64, vp, i64, vp, i64, vp, i64, vp, i64, i64, ci]
     L.brbd_aba_derivatives_batch.argtypes = [vp, vp, i64, vp, i64, vp, i64, vp, i64, vp, i64, vp, i64, vp, i64, i64, ci]
+    L.brbd_nle_batch.argtypes = [vp, vp, i64, vp, i64, vp, i64, i64, ci]
+    L.brbd_gravity_batch.argtypes = [vp, vp, i64, vp, i64, i64, ci]
+    L.brbd_minverse_batch.argtypes = [vp, vp, i64, vp, i64, i64, ci]
+    L.brbd_integrate_batch.argtypes = [vp, vp, i64, vp, i64, vp, i64, i64, ci]
+    L.brbd_aba_euler_step_batch.argtypes = [vp, vp, i64, vp, i64, vp, i64, ctypes.c_double, vp, i64, vp, i64, i64, ci]
     L.brbd_host_register.argtypes = [vp, ctypes.c_uint64]
     L.brbd_host_unregister.argtypes = [vp]
     L.brbd_measure_fp64_peak.argtypes = [vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)]

@@ -49,11 +49,11 @@ template<int G> struct CoopGemmShape
   static constexpr int RG = (G == 32) ? 8 : 4; // lane grid: RG row groups x CG column groups
   static constexpr int CG = G / RG;
   static constexpr int NB = 2 * CG;            // columns of dtau_dq (and of dtau_dv) per block
-  static constexpr int DLD = 4 * CG + 1;       // leading dimension of the D block (2 NB columns), odd
+  static constexpr int DLD = 4 * CG + 2;       // leading dimension of the D block (2 NB columns): rows 16-byte aligned
 };
 inline AbaCoopLayout aba_coop_layout(int nq, int nv, int nj, int G)
 {
-  const int dld = (G == 32 || G == 16) ? 17 : 9;
+  const int dld = (G == 32 || G == 16) ? 18 : 10;
   AbaCoopLayout L;
   L.ocb = 0;
   L.ojr = L.ocb + CB_STRIDE * nv;
@@ -493,6 +493,49 @@ BRBD_DI void coop_minv_complete(const ModelPOD<T> & m, const CoopTables & tb, T 
     const T * Pr = cb + r * CB_STRIDE;
     T Jv[6], UD[6];
     ld6(Pr + CB_J, Jv);
+    T * Mrow = Minv + r * mld;
+    if (first && last)
+    {
+      // 1-dof joint: Fcrb[i] = Fcrb[parent] + J Minv(r, c)
+      if (hp)
+      {
+        ld6(Pr + A_UD, UD);
+#pragma unroll
+        for (int b = 0; b < NCB; ++b)
+        {
+          const int c = gl + b * G;
+          if (c >= iv && c < nv)
+          {
+            if (lslot != 0xff) ld6(save[b] + 6 * lslot, Fd[b]);
+            T mv = c < sub_end ? Mrow[c] : T(0); // right of the subtree the upper triangle starts at zero (:414)
+            mv -= dot6a(UD, Fd[b]);
+            Mrow[c] = mv;
+            if (c >= own_end) Minv[c * mld + r] = mv;
+#pragma unroll
+            for (int k = 0; k < 6; ++k) Fd[b][k] += Jv[k] * mv;
+            if (sslot != 0xff) st6(save[b] + 6 * sslot, Fd[b]);
+          }
+        }
+      }
+      else
+      {
+#pragma unroll
+        for (int b = 0; b < NCB; ++b)
+        {
+          const int c = gl + b * G;
+          if (c >= iv && c < nv)
+          {
+            const T mv = c < sub_end ? Mrow[c] : T(0);
+            Mrow[c] = mv;
+            if (c >= own_end) Minv[c * mld + r] = mv;
+#pragma unroll
+            for (int k = 0; k < 6; ++k) Fd[b][k] = Jv[k] * mv;
+            if (sslot != 0xff) st6(save[b] + 6 * sslot, Fd[b]);
+          }
+        }
+      }
+      continue;
+    }
     if (hp) ld6(Pr + A_UD, UD);
 #pragma unroll
     for (int b = 0; b < NCB; ++b)
@@ -506,9 +549,9 @@ BRBD_DI void coop_minv_complete(const ModelPOD<T> & m, const CoopTables & tb, T 
 #pragma unroll
           for (int k = 0; k < 6; ++k) acc[b][k] = hp ? Fd[b][k] : T(0);
         }
-        T mv = c < sub_end ? Minv[r * mld + c] : T(0); // right of the subtree the upper triangle starts at zero (:414)
+        T mv = c < sub_end ? Mrow[c] : T(0);
         if (hp) mv -= dot6a(UD, Fd[b]);
-        Minv[r * mld + c] = mv;
+        Mrow[c] = mv;
         if (c >= own_end) Minv[c * mld + r] = mv;
 #pragma unroll
         for (int k = 0; k < 6; ++k) acc[b][k] += Jv[k] * mv;
@@ -588,7 +631,7 @@ BRBD_DI void coop_dblock_fill(const ModelPOD<T> & m, const CoopTables & tb, cons
   BRBD_SYNCWARP();
 }
 
-// out(:, block) = -Minv * Dblk; lane (rg, cg) accumulates rows rg + RG i (i < R), block columns cg + CG j (j < 4)
+// out(:, block) = -Minv * Dblk; lane (rg, cg) accumulates rows rg + RG i (i < R), block columns 4 cg + j (j < 4)
 template<class T, int G, int R>
 BRBD_DI void coop_dblock_product(int nv, const T * Minv, int mld, const T * Dblk, int c0, T * __restrict__ gq, T * __restrict__ gv, int gl,
                                  bool active)
@@ -601,14 +644,14 @@ BRBD_DI void coop_dblock_product(int nv, const T * Minv, int mld, const T * Dblk
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = T(0);
   const T * pa = Minv + rg;
-  const T * pb = Dblk + cg;
+  const T * pb = Dblk + 4 * cg;
+#pragma unroll 5
   for (int k = 0; k < nv; ++k)
   {
     T a[R], b[4];
 #pragma unroll
     for (int i = 0; i < R; ++i) a[i] = pa[S::RG * i];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) b[j] = pb[S::CG * j];
+    ld4(pb, b);
 #pragma unroll
     for (int i = 0; i < R; ++i)
 #pragma unroll
@@ -621,7 +664,7 @@ BRBD_DI void coop_dblock_product(int nv, const T * Minv, int mld, const T * Dblk
 #pragma unroll
     for (int j = 0; j < 4; ++j)
     {
-      const int dc = cg + S::CG * j;
+      const int dc = 4 * cg + j;
       const int col = c0 + (dc < S::NB ? dc : dc - S::NB);
       T * dst = (dc < S::NB ? gq : gv) + col * nv + rg;
       if (col < nv)
@@ -663,7 +706,9 @@ BRBD_DI void coop_dblock_product_dispatch(int nv, const T * Minv, int mld, const
 
 // ---- one configuration, all phases --------------------------------------------------------------------------
 // `base` = this group's region (AbaCoopLayout), q / v / tau already staged at oq / ov / ou.
-template<class T, int G>
+// MODE 0: computeABADerivatives.  MODE 1: computeMinverse (reference: algorithm/aba.hxx:613-902) — phases A1, A2, A3, A5 with
+// v = tau = 0; like the reference's data.Minv only the upper triangle is meaningful, the strictly-lower part is written as zeros.
+template<class T, int G, int MODE = 0>
 BRBD_DI void aba_derivatives_coop_config(const ModelPOD<T> & m, const CoopTables & tb, const AbaCoopLayout & L, T * base, int gl,
                                          T * __restrict__ gq, T * __restrict__ gv, T * __restrict__ gm, T * __restrict__ gddq, bool active)
 {
@@ -676,14 +721,29 @@ BRBD_DI void aba_derivatives_coop_config(const ModelPOD<T> & m, const CoopTables
   if (G == 32 && nv > G)
   {
     coop_minv_upper<T, G, (G == 32 ? 2 : 1)>(m, tb, cb, Minv, mld, gl);
-    coop_aba_forward2<T, G>(m, tb, jr, cb, su, gl);
+    if (MODE == 0) coop_aba_forward2<T, G>(m, tb, jr, cb, su, gl);
     coop_minv_complete<T, G, (G == 32 ? 2 : 1)>(m, tb, cb, Minv, mld, gl);
   }
   else
   {
     coop_minv_upper<T, G, 1>(m, tb, cb, Minv, mld, gl);
-    coop_aba_forward2<T, G>(m, tb, jr, cb, su, gl);
+    if (MODE == 0) coop_aba_forward2<T, G>(m, tb, jr, cb, su, gl);
     coop_minv_complete<T, G, 1>(m, tb, cb, Minv, mld, gl);
+  }
+  if (MODE == 1)
+  {
+    if (active)
+    {
+      int c = 0, r = gl;
+      while (r >= nv) { r -= nv; ++c; }
+      for (int e = gl; e < nv * nv; e += G)
+      {
+        gm[e] = r <= c ? Minv[c * mld + r] : T(0);
+        r += G;
+        while (r >= nv) { r -= nv; ++c; }
+      }
+    }
+    return;
   }
   coop_joint_quantities<T, G, false>(m, jr, gl, xoff, JR_OA);
   coop_subtree_sums<T, G>(m, jr, gl);
@@ -710,7 +770,7 @@ BRBD_DI void aba_derivatives_coop_config(const ModelPOD<T> & m, const CoopTables
   }
 }
 
-template<class T, int G>
+template<class T, int G, int MODE = 0>
 __global__ void __launch_bounds__(256, 1)
 aba_derivatives_coop_kernel(const ModelPOD<T> * __restrict__ gmod, const __grid_constant__ CoopTables gtb, const AbaCoopLayout L,
                             const T * __restrict__ q, int64_t ldq, const T * __restrict__ v, int64_t ldv,
@@ -741,10 +801,14 @@ aba_derivatives_coop_kernel(const ModelPOD<T> * __restrict__ gmod, const __grid_
     if (!active) cfg = B - 1; // idle groups shadow the last configuration (stores suppressed)
     const T * gq_in = q + cfg * ldq, * gv_in = v + cfg * ldv, * gt_in = tau + cfg * ldtau;
     for (int k = gl; k < nq; k += G) base[L.oq + k] = gq_in[k];
-    for (int k = gl; k < nv; k += G) { base[L.ov + k] = gv_in[k]; base[L.ou + k] = gt_in[k]; }
+    if (MODE == 0)
+      for (int k = gl; k < nv; k += G) { base[L.ov + k] = gv_in[k]; base[L.ou + k] = gt_in[k]; }
+    else
+      for (int k = gl; k < nv; k += G) { base[L.ov + k] = T(0); base[L.ou + k] = T(0); }
     BRBD_SYNCWARP();
-    aba_derivatives_coop_config<T, G>(m, tb, L, base, gl, dq + cfg * ld_dq, dv + cfg * ld_dv, dtau + cfg * ld_dtau,
-                                      ddq ? ddq + cfg * ldddq : (T *)nullptr, active);
+    aba_derivatives_coop_config<T, G, MODE>(m, tb, L, base, gl, MODE == 0 ? dq + cfg * ld_dq : (T *)nullptr,
+                                            MODE == 0 ? dv + cfg * ld_dv : (T *)nullptr, dtau + cfg * ld_dtau,
+                                            (MODE == 0 && ddq) ? ddq + cfg * ldddq : (T *)nullptr, active);
     BRBD_SYNCWARP();
   }
 }

@@ -30,6 +30,7 @@
 #include "rnea.cuh"
 #include "rnea_derivatives.cuh"
 #include "deriv_coop.cuh"
+#include "integrate.cuh"
 #include "rnea_dfs.cuh"
 #include "tree.cuh"
 
@@ -86,6 +87,11 @@ struct DeviceCtx
   // grow-only device workspace (intermediates of aba-derivatives)
   void * work = nullptr;
   size_t work_bytes = 0;
+  // second grow-only buffer: the ABA result between the two kernels of the Euler step
+  void * aux = nullptr;
+  size_t aux_bytes = 0;
+  // MAXNV zeros: the `v` / `a` operand (leading dimension 0) of nonLinearEffects / computeGeneralizedGravity
+  void * zeros = nullptr;
   cudaStream_t s() const { return use_user_stream ? user_stream : stream; }
 };
 } // namespace
@@ -118,6 +124,17 @@ brbd_status ensure_work(DeviceCtx & d, size_t bytes)
   d.work_bytes = 0;
   CUDA_TRY(cudaMalloc(&d.work, bytes));
   d.work_bytes = bytes;
+  return BRBD_OK;
+}
+
+brbd_status ensure_aux(DeviceCtx & d, size_t bytes)
+{
+  if (d.aux_bytes >= bytes) return BRBD_OK;
+  if (d.aux) CUDA_TRY(cudaFree(d.aux));
+  d.aux = nullptr;
+  d.aux_bytes = 0;
+  CUDA_TRY(cudaMalloc(&d.aux, bytes));
+  d.aux_bytes = bytes;
   return BRBD_OK;
 }
 
@@ -448,6 +465,52 @@ brbd_status launch_aba_derivs(brbd_pool * p, DeviceCtx & d, const T * q, int64_t
   return BRBD_OK;
 }
 
+// computeMinverse: the Minv phases of the warp-cooperative computeABADerivatives kernel (MODE 1)
+template<class T>
+brbd_status launch_minverse(brbd_pool * p, DeviceCtx & d, const T * q, int64_t ldq, T * Minv, int64_t ldM, int64_t B)
+{
+  const ModelPOD<double> & M = p->model.pd;
+  const int G = coop_group_size(M.nv);
+  const AbaCoopLayout L = aba_coop_layout(M.nq, M.nv, M.njoints, G);
+  const size_t static_bytes = sizeof(ModelPOD<T>) + sizeof(CoopTables) + 1024;
+  const GeometryCoop g = pick_geometry_coop(d, (size_t)L.per_group * sizeof(T), G, static_bytes, B);
+  if (p->model.coop.nbranch > A_MAXBRANCH || g.dyn_bytes + static_bytes > (size_t)d.max_smem_optin + 1024)
+    return fail(BRBD_EINVAL, "computeMinverse: model too large for the shared-memory state of one configuration");
+  brbd_status st = BRBD_OK;
+#define BRBD_LAUNCH_COOP(GG)                                                                                     \
+  {                                                                                                              \
+    st = set_smem(aba_derivatives_coop_kernel<T, GG, 1>, g.dyn_bytes);                                           \
+    if (st != BRBD_OK) return st;                                                                                \
+    aba_derivatives_coop_kernel<T, GG, 1><<<g.grid, g.warps * 32, g.dyn_bytes, d.s()>>>(                         \
+      dev_model<T>(d), p->model.coop, L, q, ldq, (const T *)nullptr, 0, (const T *)nullptr, 0, (T *)nullptr, 0, (T *)nullptr, 0, Minv, \
+      ldM, (T *)nullptr, 0, B);                                                                                  \
+  }
+  if (G == 8) BRBD_LAUNCH_COOP(8)
+  else if (G == 16) BRBD_LAUNCH_COOP(16)
+  else BRBD_LAUNCH_COOP(32)
+#undef BRBD_LAUNCH_COOP
+  p->launches += 1;
+  CUDA_TRY(cudaGetLastError());
+  return BRBD_OK;
+}
+
+// integrate / Euler step: one configuration per thread, warp tiles staged through shared memory
+template<class T, bool EULER>
+brbd_status launch_integrate(brbd_pool * p, DeviceCtx & d, const T * q, int64_t ldq, const T * v, int64_t ldv, const T * a,
+                             int64_t lda, T dt, T * qout, int64_t ldqo, T * vout, int64_t ldvo, int64_t B)
+{
+  const ModelPOD<double> & M = p->model.pd;
+  const size_t per_warp = (size_t)32 * ((M.nq | 1) + 2 * (M.nv | 1)) * sizeof(T);
+  const Geometry g = pick_geometry(d, per_warp, sizeof(ModelPOD<T>), B, 8, 16);
+  brbd_status st = set_smem(integrate_kernel<T, EULER>, g.dyn_bytes);
+  if (st != BRBD_OK) return st;
+  integrate_kernel<T, EULER><<<g.grid, g.warps_per_cta * 32, g.dyn_bytes, d.s()>>>(dev_model<T>(d), q, ldq, v, ldv, a, lda, dt, qout,
+                                                                                    ldqo, vout, ldvo, B);
+  p->launches += 1;
+  CUDA_TRY(cudaGetLastError());
+  return BRBD_OK;
+}
+
 // ------------------------------------------------------------------------------------------------
 // Generic call wrapper: argument checks, device/host pointer handling, sharding over devices.
 // ------------------------------------------------------------------------------------------------
@@ -667,6 +730,8 @@ void brbd_pool_destroy(brbd_pool * p)
     if (d.s_in) cudaStreamDestroy(d.s_in);
     if (d.s_out) cudaStreamDestroy(d.s_out);
     if (d.work) cudaFree(d.work);
+    if (d.aux) cudaFree(d.aux);
+    if (d.zeros) cudaFree(d.zeros);
     if (d.d_pd) cudaFree(d.d_pd);
     if (d.d_pf) cudaFree(d.d_pf);
     if (d.ev0) cudaEventDestroy(d.ev0);
@@ -726,6 +791,8 @@ brbd_status brbd_pool_create(const brbd_model * m, const int * device_ids, int n
       tryc(cudaEventCreate(&d.ev1), "cudaEventCreate");
       tryc(cudaMalloc(&d.d_pd, sizeof(ModelPOD<double>)), "cudaMalloc");
       tryc(cudaMalloc(&d.d_pf, sizeof(ModelPOD<float>)), "cudaMalloc");
+      tryc(cudaMalloc(&d.zeros, MAXNV * sizeof(double)), "cudaMalloc");
+      if (st == BRBD_OK) tryc(cudaMemset(d.zeros, 0, MAXNV * sizeof(double)), "cudaMemset");
     }
     if (st != BRBD_OK)
     {
@@ -844,6 +911,70 @@ brbd_status brbd_aba_derivatives_batch(brbd_pool * p, const void * q, int64_t ld
              return launch_aba_derivs<T>(p, d, (const T *)P[0], args[0].ld, (const T *)P[1], args[1].ld, (const T *)P[2],
                                          args[2].ld, (T *)P[3], args[3].ld, (T *)P[4], args[4].ld, (T *)P[5], args[5].ld,
                                          (T *)P[6], args[6].ld, B);
+           })));
+}
+
+brbd_status brbd_nle_batch(brbd_pool * p, const void * q, int64_t ldq, const void * v, int64_t ldv, void * nle, int64_t ldn,
+                           int64_t batch, int flags)
+{
+  if (!p) return fail(BRBD_EINVAL, "null pool");
+  const int nq = p->model.pd.nq, nv = p->model.pd.nv;
+  std::vector<Arg> args = {{q, nullptr, ldq, nq, false}, {v, nullptr, ldv, nv, false}, {nullptr, nle, ldn, nv, false}};
+  DISPATCH(flags, (run_call<T>(p, args, batch, flags, [&](DeviceCtx & d, std::vector<void *> & P, int64_t B) {
+             return launch_rnea<T>(p, d, (const T *)P[0], args[0].ld, (const T *)P[1], args[1].ld, (const T *)d.zeros, 0,
+                                   (T *)P[2], args[2].ld, B);
+           })));
+}
+
+brbd_status brbd_gravity_batch(brbd_pool * p, const void * q, int64_t ldq, void * g, int64_t ldg, int64_t batch, int flags)
+{
+  if (!p) return fail(BRBD_EINVAL, "null pool");
+  const int nq = p->model.pd.nq, nv = p->model.pd.nv;
+  std::vector<Arg> args = {{q, nullptr, ldq, nq, false}, {nullptr, g, ldg, nv, false}};
+  DISPATCH(flags, (run_call<T>(p, args, batch, flags, [&](DeviceCtx & d, std::vector<void *> & P, int64_t B) {
+             return launch_rnea<T>(p, d, (const T *)P[0], args[0].ld, (const T *)d.zeros, 0, (const T *)d.zeros, 0, (T *)P[1],
+                                   args[1].ld, B);
+           })));
+}
+
+brbd_status brbd_minverse_batch(brbd_pool * p, const void * q, int64_t ldq, void * Minv, int64_t ldM, int64_t batch, int flags)
+{
+  if (!p) return fail(BRBD_EINVAL, "null pool");
+  const int nq = p->model.pd.nq, nv = p->model.pd.nv;
+  std::vector<Arg> args = {{q, nullptr, ldq, nq, false}, {nullptr, Minv, ldM, (int64_t)nv * nv, false}};
+  DISPATCH(flags, (run_call<T>(p, args, batch, flags, [&](DeviceCtx & d, std::vector<void *> & P, int64_t B) {
+             return launch_minverse<T>(p, d, (const T *)P[0], args[0].ld, (T *)P[1], args[1].ld, B);
+           })));
+}
+
+brbd_status brbd_integrate_batch(brbd_pool * p, const void * q, int64_t ldq, const void * v, int64_t ldv, void * qout, int64_t ldqo,
+                                 int64_t batch, int flags)
+{
+  if (!p) return fail(BRBD_EINVAL, "null pool");
+  const int nq = p->model.pd.nq, nv = p->model.pd.nv;
+  std::vector<Arg> args = {{q, nullptr, ldq, nq, false}, {v, nullptr, ldv, nv, false}, {nullptr, qout, ldqo, nq, false}};
+  DISPATCH(flags, (run_call<T>(p, args, batch, flags, [&](DeviceCtx & d, std::vector<void *> & P, int64_t B) {
+             return launch_integrate<T, false>(p, d, (const T *)P[0], args[0].ld, (const T *)P[1], args[1].ld, (const T *)nullptr, 0,
+                                               T(1), (T *)P[2], args[2].ld, (T *)nullptr, 0, B);
+           })));
+}
+
+brbd_status brbd_aba_euler_step_batch(brbd_pool * p, const void * q, int64_t ldq, const void * v, int64_t ldv, const void * tau,
+                                      int64_t ldtau, double dt, void * q_next, int64_t ldqn, void * v_next, int64_t ldvn,
+                                      int64_t batch, int flags)
+{
+  if (!p) return fail(BRBD_EINVAL, "null pool");
+  const int nq = p->model.pd.nq, nv = p->model.pd.nv;
+  std::vector<Arg> args = {{q, nullptr, ldq, nq, false},          {v, nullptr, ldv, nv, false},         {tau, nullptr, ldtau, nv, false},
+                           {nullptr, q_next, ldqn, nq, false}, {nullptr, v_next, ldvn, nv, false}};
+  DISPATCH(flags, (run_call<T>(p, args, batch, flags, [&](DeviceCtx & d, std::vector<void *> & P, int64_t B) {
+             brbd_status st = ensure_aux(d, (size_t)B * nv * sizeof(T));
+             if (st != BRBD_OK) return st;
+             st = launch_aba<T>(p, d, (const T *)P[0], args[0].ld, (const T *)P[1], args[1].ld, (const T *)P[2], args[2].ld,
+                                (T *)d.aux, nv, B);
+             if (st != BRBD_OK) return st;
+             return launch_integrate<T, true>(p, d, (const T *)P[0], args[0].ld, (const T *)P[1], args[1].ld, (const T *)d.aux, nv,
+                                              (T)dt, (T *)P[3], args[3].ld, (T *)P[4], args[4].ld, B);
            })));
 }
 

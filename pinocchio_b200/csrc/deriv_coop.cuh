@@ -137,6 +137,13 @@ template<class T> BRBD_DI void ld6(const T * p, T * x)
   const P a = q[0], b = q[1], c = q[2];
   x[0] = a.x; x[1] = a.y; x[2] = b.x; x[3] = b.y; x[4] = c.x; x[5] = c.y;
 }
+template<class T> BRBD_DI void ld4(const T * p, T * x)
+{
+  typedef typename Pair<T>::type P;
+  const P * q = reinterpret_cast<const P *>(p);
+  const P a = q[0], b = q[1];
+  x[0] = a.x; x[1] = a.y; x[2] = b.x; x[3] = b.y;
+}
 template<class T> BRBD_DI void st6(T * p, const T * x)
 {
   typedef typename Pair<T>::type P;

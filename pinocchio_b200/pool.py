@@ -180,8 +180,8 @@ def _alloc_like(ref, rows: int, cols: int):
     return np.empty((rows, cols), dtype=ref.dtype if ref.dtype in (np.float64, np.float32) else np.float64, order="F")
 
 
-def _call(pool: ModelPool, fn_name: str, ins, outs, async_: bool = False):
-    """ins / outs: lists of (_Arg or None)."""
+def _call(pool: ModelPool, fn_name: str, ins, outs, async_: bool = False, mid=()):
+    """ins / outs: lists of (_Arg or None); `mid`: extra scalar C arguments between the inputs and the outputs."""
     args = [a for a in ins + outs if a is not None]
     B = ins[0].cols
     for a in args:
@@ -197,11 +197,15 @@ def _call(pool: ModelPool, fn_name: str, ins, outs, async_: bool = False):
     if async_:
         flags |= BRBD_ASYNC
     cargs = [pool._h_pool]
-    for a in ins + outs:
-        if a is None:
-            cargs += [ctypes.c_void_p(0), ctypes.c_int64(0)]
-        else:
-            cargs += [ctypes.c_void_p(a.ptr), ctypes.c_int64(a.ld)]
+    for group in (ins, None, outs):
+        if group is None:
+            cargs += list(mid)
+            continue
+        for a in group:
+            if a is None:
+                cargs += [ctypes.c_void_p(0), ctypes.c_int64(0)]
+            else:
+                cargs += [ctypes.c_void_p(a.ptr), ctypes.c_int64(a.ld)]
     cargs += [ctypes.c_int64(B), ctypes.c_int(flags)]
     try:
         _capi.check(getattr(_capi.lib(), fn_name)(*cargs))
@@ -289,3 +293,60 @@ def computeABADerivativesInParallel(num_threads: int, pool: ModelPool, q, v, tau
           [_describe(ddq_dq, nn, "ddq_dq", True), _describe(ddq_dv, nn, "ddq_dv", True),
            _describe(ddq_dtau, nn, "ddq_dtau", True), _describe(ddq, pool.nv, "ddq", True)], async_)
     return ddq_dq, ddq_dv, ddq_dtau, ddq
+
+
+# ---- the callers' other needs on the same sweeps; no batched version exists upstream, the names follow
+# ---- the reference's single-configuration functions ----------------------------------------------------------------
+def nonLinearEffectsInParallel(num_threads: int, pool: ModelPool, q, v, nle=None, async_: bool = False):
+    """nle[:, i] = nonLinearEffects(model, q[:, i], v[:, i]) — algorithm/rnea.hpp:105 (= rnea(q, v, 0))."""
+    _check_pool(num_threads, pool)
+    aq, av = _describe(q, pool.nq, "q"), _describe(v, pool.nv, "v")
+    if nle is None:
+        nle = _alloc_like(q, pool.nv, aq.cols)
+    _call(pool, "brbd_nle_batch", [aq, av], [_describe(nle, pool.nv, "nle", out=True)], async_)
+    return nle
+
+
+def computeGeneralizedGravityInParallel(num_threads: int, pool: ModelPool, q, g=None, async_: bool = False):
+    """g[:, i] = computeGeneralizedGravity(model, q[:, i]) — algorithm/rnea.hpp:133 (= rnea(q, 0, 0))."""
+    _check_pool(num_threads, pool)
+    aq = _describe(q, pool.nq, "q")
+    if g is None:
+        g = _alloc_like(q, pool.nv, aq.cols)
+    _call(pool, "brbd_gravity_batch", [aq], [_describe(g, pool.nv, "g", out=True)], async_)
+    return g
+
+
+def computeMinverseInParallel(num_threads: int, pool: ModelPool, q, Minv=None, async_: bool = False):
+    """Minv[:, i] = vec(computeMinverse(model, q[:, i])) — algorithm/aba.hpp:106: upper triangle of M^-1 + zeros."""
+    _check_pool(num_threads, pool)
+    aq = _describe(q, pool.nq, "q")
+    nn = pool.nv * pool.nv
+    if Minv is None:
+        Minv = _alloc_like(q, nn, aq.cols)
+    _call(pool, "brbd_minverse_batch", [aq], [_describe(Minv, nn, "Minv", out=True)], async_)
+    return Minv
+
+
+def integrateInParallel(num_threads: int, pool: ModelPool, q, v, qout=None, async_: bool = False):
+    """qout[:, i] = integrate(model, q[:, i], v[:, i]) — algorithm/joint-configuration.hpp:49-74."""
+    _check_pool(num_threads, pool)
+    aq, av = _describe(q, pool.nq, "q"), _describe(v, pool.nv, "v")
+    if qout is None:
+        qout = _alloc_like(q, pool.nq, aq.cols)
+    _call(pool, "brbd_integrate_batch", [aq, av], [_describe(qout, pool.nq, "qout", out=True)], async_)
+    return qout
+
+
+def abaEulerStepInParallel(num_threads: int, pool: ModelPool, q, v, tau, dt: float, q_next=None, v_next=None,
+                           async_: bool = False):
+    """One semi-implicit Euler step per column, on the device: a = aba(q, v, tau); v_next = v + dt a;
+    q_next = integrate(q, dt v_next) (examples/simulation-pendulum.py:153-157).  Returns (q_next, v_next)."""
+    _check_pool(num_threads, pool)
+    aq, av, at = _describe(q, pool.nq, "q"), _describe(v, pool.nv, "v"), _describe(tau, pool.nv, "tau")
+    q_next = _alloc_like(q, pool.nq, aq.cols) if q_next is None else q_next
+    v_next = _alloc_like(q, pool.nv, aq.cols) if v_next is None else v_next
+    _call(pool, "brbd_aba_euler_step_batch", [aq, av, at],
+          [_describe(q_next, pool.nq, "q_next", True), _describe(v_next, pool.nv, "v_next", True)], async_,
+          mid=(ctypes.c_double(float(dt)),))
+    return q_next, v_next

@@ -77,3 +77,15 @@ def test_emulated_aba_derivatives(emu, oracle_cls, name):
     for got, ref, what in ((ddq, rddq, "ddq"), (dt, rdt, "Minv"), (dq, rdq, "ddq_dq"), (dv, rdv, "ddq_dv")):
         assert np.isfinite(got).all(), what
         assert_close(got, ref, atol=1e-12 + 1e-10 * np.abs(ref).max(), what=what)
+
+
+@pytest.mark.parametrize("name", _models()[0])
+def test_emulated_minverse(emu, oracle_cls, name):
+    model = _get(name, _models()[1])
+    q, v, tau = random_inputs(model, 2, 17)
+    _, _, Minv, _ = _run(emu, 2, model, q, v, tau)
+    ref = oracle_cls(model).minverse(q)
+    assert_close(Minv, ref, atol=1e-12 + 1e-10 * np.abs(ref).max(), what="Minv (upper)")
+    nv = model.nv
+    for b in range(q.shape[1]):
+        assert not np.tril(Minv[:, b].reshape(nv, nv, order="F"), -1).any()

@@ -177,3 +177,80 @@ def test_error_behaviour(ctx):
     # empty batch is a no-op
     out = pb.rneaInParallel(1, pool, q[:, :0], v[:, :0], a[:, :0])
     assert out.shape == (model.nv, 0)
+
+
+# ---- the callers' other needs on the same sweeps ---------------------------------------------------
+@pytest.mark.parametrize("name", ALL_MODELS)
+def test_nle_and_gravity(ctx, name):
+    """nonLinearEffects == rnea(q, v, 0) (unittest/rnea.cpp:201-206), computeGeneralizedGravity == rnea(q, 0, 0)
+    (unittest/rnea.cpp:225-228)."""
+    import pinocchio_b200 as pb
+    model, pool, orc = ctx(name)
+    q, v, _ = random_inputs(model, 65, 31)
+    assert_close(pb.nonLinearEffectsInParallel(1, pool, q, v), orc.nle(q, v), what=f"nle {name}")
+    assert_close(pb.computeGeneralizedGravityInParallel(1, pool, q), orc.gravity(q), what=f"gravity {name}")
+
+
+@pytest.mark.parametrize("name", ALL_MODELS)
+def test_minverse(ctx, name):
+    """computeMinverse: upper triangle of M^-1 (unittest/aba.cpp:265-301), zeros below; Minv == the ddq_dtau of
+    computeABADerivatives (unittest/aba-derivatives.cpp:96-100)."""
+    import pinocchio_b200 as pb
+    model, pool, orc = ctx(name)
+    q, v, tau = random_inputs(model, 37, 33)
+    Minv = pb.computeMinverseInParallel(1, pool, q)
+    ref = orc.minverse(q)
+    assert_close(Minv, ref, atol=1e-12 + 1e-10 * np.abs(ref).max(), what=f"Minv {name}")
+    nv = model.nv
+    lower = ~np.triu(np.ones((nv, nv), dtype=bool)).reshape(-1, order="F")
+    assert not Minv[lower].any()
+    full = pb.computeABADerivativesInParallel(1, pool, q, v, tau)[2]
+    assert_close(Minv[~lower], full[~lower], atol=1e-12 + 1e-10 * np.abs(ref).max(), what=f"Minv vs ddq_dtau {name}")
+
+
+@pytest.mark.parametrize("name", ALL_MODELS)
+@pytest.mark.parametrize("B", [1, 70])
+def test_integrate(ctx, name, B):
+    import pinocchio_b200 as pb
+    model, pool, orc = ctx(name)
+    q, v, _ = random_inputs(model, B, 35)
+    assert_close(pb.integrateInParallel(1, pool, q, 0.3 * v), orc.integrate(q, 0.3 * v), what=f"integrate {name} B={B}")
+
+
+@pytest.mark.parametrize("name", ALL_MODELS)
+def test_aba_euler_step(ctx, name):
+    """a = aba(q, v, tau); v += a dt; q = integrate(q, v dt) (examples/simulation-pendulum.py:153-157), three steps on the
+    device against the same three steps with the oracle."""
+    import pinocchio_b200 as pb
+    model, pool, orc = ctx(name)
+    q, v, tau = random_inputs(model, 40, 37)
+    dt = 1e-3
+    qg, vg, qo, vo = q.copy(order="F"), v.copy(order="F"), q.copy(order="F"), v.copy(order="F")
+    for _ in range(3):
+        qg, vg = pb.abaEulerStepInParallel(1, pool, qg, vg, tau, dt)
+        a = orc.aba(qo, vo, tau)
+        vo = np.asfortranarray(vo + dt * a)
+        qo = orc.integrate(qo, dt * vo)
+    s = max(1.0, np.abs(vo).max())
+    assert_close(vg, vo, atol=1e-10 * s, what=f"euler v {name}")
+    assert_close(qg, qo, atol=1e-11, what=f"euler q {name}")
+
+
+def test_euler_step_device_resident_and_fp32(ctx):
+    """Device pointers (torch CUDA tensors) and the FP32 mode of the new entry points."""
+    import torch
+    import pinocchio_b200 as pb
+    model, pool, orc = ctx("talos_reduced_ff")
+    q, v, tau = random_inputs(model, 96, 41)
+    tq, tv, tt = (torch.from_numpy(np.ascontiguousarray(x.T)).cuda() for x in (q, v, tau))
+    qn, vn = pb.abaEulerStepInParallel(1, pool, tq, tv, tt, 2e-3)
+    a = orc.aba(q, v, tau)
+    vo = v + 2e-3 * a
+    qo = orc.integrate(q, 2e-3 * vo)
+    assert_close(vn.cpu().numpy().T, vo, atol=1e-10 * max(1.0, np.abs(vo).max()), what="euler v (device)")
+    assert_close(qn.cpu().numpy().T, qo, atol=1e-11, what="euler q (device)")
+    q32 = pb.integrateInParallel(1, pool, q.astype(np.float32), (0.3 * v).astype(np.float32))
+    assert np.abs(q32 - orc.integrate(q, 0.3 * v)).max() < 2e-6  # FP32 mode: ~10 ulp of float on O(1) coordinates
+    g32 = pb.computeGeneralizedGravityInParallel(1, pool, q.astype(np.float32))
+    gref = orc.gravity(q)
+    assert np.abs(g32 - gref).max() < 5e-5 * np.abs(gref).max()

@@ -213,3 +213,46 @@ def test_flop_counts_are_positive_and_ordered(make):
     c = {k: o.count_flops(k, q[:, 0], v[:, 0], a[:, 0]) for k in o.ALGOS}
     assert c["rnea"]["flops"] < c["aba"]["flops"] < c["rnea_derivatives"]["flops"] < c["aba_derivatives"]["flops"]
     assert c["rnea"]["sincos"] == 26
+
+
+# ---- integrate (the step after ABA) ----------------------------------------------------------
+@pytest.mark.parametrize("name", ALL)
+def test_integrate_identities(make, name):
+    """unittest/joint-configurations.cpp:46-62 (integration_test): integrate(q, 0) == q; plus exp(v) exp(-v) == 1 on every
+    Lie group, unit-norm quaternions / unit complex after the step, and agreement with the independent host-side
+    restatement pinocchio_b200.joint_configuration.integrate and with the long double instantiation."""
+    import pinocchio_b200 as pb
+    m, o = make(name)
+    q, v, _ = random_inputs(m, 8, 21)
+    assert np.array_equal(o.integrate(q, 0.0 * v), q) or np.abs(o.integrate(q, 0.0 * v) - q).max() < 2e-16
+    q1 = o.integrate(q, 0.7 * v)
+    assert np.abs(o.integrate(q1, -0.7 * v) - q).max() < 1e-14
+    assert np.abs(o.integrate(q, 0.7 * v, long_double=True) - q1).max() < 1e-14
+    for b in range(q.shape[1]):
+        assert np.abs(pb.integrate(m, q[:, b], 0.7 * v[:, b]) - q1[:, b]).max() < 1e-13
+    for j in range(1, m.njoints):
+        iq, t = m.idx_qs[j], m.joint_types[j]
+        if t == pb.JOINT_FREEFLYER:
+            assert np.abs(np.linalg.norm(q1[iq + 3:iq + 7], axis=0) - 1).max() < 1e-14
+        elif t == pb.JOINT_SPHERICAL:
+            assert np.abs(np.linalg.norm(q1[iq:iq + 4], axis=0) - 1).max() < 1e-14
+        elif t == pb.JOINT_PLANAR:
+            assert np.abs(np.linalg.norm(q1[iq + 2:iq + 4], axis=0) - 1).max() < 1e-14
+
+
+def test_integrate_known_answers(oracle_cls):
+    """Closed forms: a free-flyer at the identity moved by the twist (v, w) = ((1, 0, 0), (0, 0, th)) ends on the arc
+    (sin th / th, (1 - cos th) / th, 0) with the quaternion (0, 0, sin th/2, cos th/2) (exp6, explog-quaternion.hpp:92-136);
+    the small-angle branch (Taylor expansion below epsilon^(1/4)) agrees with the closed form to first order."""
+    import pinocchio_b200 as pb
+    from pinocchio_b200 import model as M
+    m = M.Model()
+    f = m.addJoint(0, M.JOINT_FREEFLYER, M.SE3.Identity(), "ff", np.full(7, -1.0), np.full(7, 1.0))
+    m.appendBodyToJoint(f, M._Rng(3).inertia(), M.SE3.Identity())
+    o = oracle_cls(m)
+    q0 = np.array([0, 0, 0, 0, 0, 0, 1.0]).reshape(7, 1)
+    for th in (0.9, 1e-3, 1e-7):
+        v = np.array([1.0, 0, 0, 0, 0, th]).reshape(6, 1)
+        q1 = o.integrate(q0, v)[:, 0]
+        ref = np.array([np.sin(th) / th, 2 * np.sin(th / 2) ** 2 / th, 0, 0, 0, np.sin(th / 2), np.cos(th / 2)])
+        assert np.abs(q1 - ref).max() < 1e-12, (th, q1, ref)
