@@ -213,6 +213,65 @@ inline void computeABADerivativesInParallel(size_t num_threads, DeviceModelPool 
                                           aba_partial_dtau.ld, nullptr, 0, q.cols, BRBD_PTR_HOST | BRBD_FP64));
 }
 
+// ---- the callers' other needs on the same sweeps (no batched version upstream; single-configuration semantics) ----
+// nle.col(i) = nonLinearEffects(q.col(i), v.col(i)) — algorithm/rnea.hpp:105
+inline void nonLinearEffectsInParallel(size_t num_threads, DeviceModelPool & pool, ConstMatrixView q, ConstMatrixView v, MatrixView nle)
+{
+  detail::check_pool(num_threads, pool);
+  detail::check_rows("q", q.rows, pool.nq());
+  detail::check_rows("v", v.rows, pool.nv());
+  detail::check_rows("nle", nle.rows, pool.nv());
+  detail::check_cols("v", v.cols, q.cols);
+  detail::check_cols("nle", nle.cols, q.cols);
+  check_status(brbd_nle_batch(pool.handle(), q.data, q.ld, v.data, v.ld, nle.data, nle.ld, q.cols, BRBD_PTR_HOST | BRBD_FP64));
+}
+// g.col(i) = computeGeneralizedGravity(q.col(i)) — algorithm/rnea.hpp:133
+inline void computeGeneralizedGravityInParallel(size_t num_threads, DeviceModelPool & pool, ConstMatrixView q, MatrixView g)
+{
+  detail::check_pool(num_threads, pool);
+  detail::check_rows("q", q.rows, pool.nq());
+  detail::check_rows("g", g.rows, pool.nv());
+  detail::check_cols("g", g.cols, q.cols);
+  check_status(brbd_gravity_batch(pool.handle(), q.data, q.ld, g.data, g.ld, q.cols, BRBD_PTR_HOST | BRBD_FP64));
+}
+// Minv.col(i) = vec(computeMinverse(q.col(i))): upper triangle, zeros below — algorithm/aba.hpp:106
+inline void computeMinverseInParallel(size_t num_threads, DeviceModelPool & pool, ConstMatrixView q, MatrixView Minv)
+{
+  detail::check_pool(num_threads, pool);
+  detail::check_rows("q", q.rows, pool.nq());
+  detail::check_rows("Minv", Minv.rows, (int64_t)pool.nv() * pool.nv());
+  detail::check_cols("Minv", Minv.cols, q.cols);
+  check_status(brbd_minverse_batch(pool.handle(), q.data, q.ld, Minv.data, Minv.ld, q.cols, BRBD_PTR_HOST | BRBD_FP64));
+}
+// qout.col(i) = integrate(model, q.col(i), v.col(i)) — algorithm/joint-configuration.hpp:49-74
+inline void integrateInParallel(size_t num_threads, DeviceModelPool & pool, ConstMatrixView q, ConstMatrixView v, MatrixView qout)
+{
+  detail::check_pool(num_threads, pool);
+  detail::check_rows("q", q.rows, pool.nq());
+  detail::check_rows("v", v.rows, pool.nv());
+  detail::check_rows("qout", qout.rows, pool.nq());
+  detail::check_cols("v", v.cols, q.cols);
+  detail::check_cols("qout", qout.cols, q.cols);
+  check_status(brbd_integrate_batch(pool.handle(), q.data, q.ld, v.data, v.ld, qout.data, qout.ld, q.cols, BRBD_PTR_HOST | BRBD_FP64));
+}
+// a = aba(q, v, tau); v_next = v + dt a; q_next = integrate(q, dt v_next) per column — examples/simulation-pendulum.py:153-157
+inline void abaEulerStepInParallel(size_t num_threads, DeviceModelPool & pool, ConstMatrixView q, ConstMatrixView v, ConstMatrixView tau,
+                                   double dt, MatrixView q_next, MatrixView v_next)
+{
+  detail::check_pool(num_threads, pool);
+  detail::check_rows("q", q.rows, pool.nq());
+  detail::check_rows("v", v.rows, pool.nv());
+  detail::check_rows("tau", tau.rows, pool.nv());
+  detail::check_rows("q_next", q_next.rows, pool.nq());
+  detail::check_rows("v_next", v_next.rows, pool.nv());
+  detail::check_cols("v", v.cols, q.cols);
+  detail::check_cols("tau", tau.cols, q.cols);
+  detail::check_cols("q_next", q_next.cols, q.cols);
+  detail::check_cols("v_next", v_next.cols, q.cols);
+  check_status(brbd_aba_euler_step_batch(pool.handle(), q.data, q.ld, v.data, v.ld, tau.data, tau.ld, dt, q_next.data, q_next.ld,
+                                         v_next.data, v_next.ld, q.cols, BRBD_PTR_HOST | BRBD_FP64));
+}
+
 #ifdef PINOCCHIO_B200_WITH_EIGEN
 // The reference's parameter lists (parallel/rnea.hpp:31-45, parallel/aba.hpp:32-46): outputs are passed as
 // const references and written through const_cast, exactly as the reference does (rnea.hpp:59).

@@ -14,6 +14,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -302,18 +303,34 @@ brbd_status launch_crba(brbd_pool * p, DeviceCtx & d, const T * q, int64_t ldq, 
   // preferred: oYcrb / oMi stacks in tensor memory (<= 8 warps per CTA, one CTA per SM)
   {
     const int wpv = (int)(sizeof(T) / 4);
-    CrbaTmemLayout L = crba_tmem_layout<T>(t.maxpathdof, t.maxdepth, t.nbranch, t.nv, 4);
+    CrbaTmemLayout L = crba_tmem_layout<T>(t.maxpathdof, t.maxdepth, t.nbranch, t.nv, 4, t.ffroot);
     const int cols_per_slice = L.tvals * wpv;
     const int max_warps_tmem = cols_per_slice <= 256 ? 8 : (cols_per_slice <= 512 ? 4 : 0);
     if (max_warps_tmem > 0)
     {
       Geometry2 g = pick_geometry2(d, (size_t)L.nstate * sizeof(T), (size_t)32 * L.epad * sizeof(T), B, max_warps_tmem, 1);
+      // Per-SM throughput is flat from 5 warps up (measured, profiles/r1_v5_crba_warps.txt), so what counts is the number of
+      // rounds the persistent grid needs: fewest rounds first, then the fewest warps that reach it (65536 configurations of
+      // simple_humanoid: 7 warps -> 1.98 rounds, 8 -> 1.73 rounds of which the second is 73 % full, 6 -> 2.3 i.e. 3 rounds).
+      {
+        const int64_t tiles = (B + 31) / 32;
+        int best_w = g.warps;
+        int64_t best_rounds = (tiles + (int64_t)d.sm_count * g.warps - 1) / ((int64_t)d.sm_count * g.warps);
+        for (int w = g.warps - 1; w >= 1; --w)
+        {
+          const int64_t rounds = (tiles + (int64_t)d.sm_count * w - 1) / ((int64_t)d.sm_count * w);
+          if (rounds <= best_rounds) { best_rounds = rounds; best_w = w; }
+        }
+        g.warps = best_w;
+      }
+      if (const char * e = std::getenv("BRBD_CRBA_WARPS")) // experiments: cap the warps per SM
+        g.warps = std::max(1, std::min(g.warps, std::atoi(e)));
       // the element -> configuration table of the emitter (32 * nv bytes) sits after the warp regions
       while (g.warps > 1 && (size_t)g.warps * (32 * (size_t)L.nstate * sizeof(T) + 32 * (size_t)L.epad * sizeof(T)) + 32 * (size_t)t.nv + 64 > (size_t)d.max_smem_optin) --g.warps;
       g.dyn_bytes = (size_t)g.warps * (32 * (size_t)L.nstate * sizeof(T) + 32 * (size_t)L.epad * sizeof(T)) + 32 * (size_t)t.nv;
       const int64_t ctas_needed = (B + g.warps * 32 - 1) / (g.warps * 32);
       g.grid = (int)std::max<int64_t>(1, std::min<int64_t>(ctas_needed, (int64_t)d.sm_count));
-      L = crba_tmem_layout<T>(t.maxpathdof, t.maxdepth, t.nbranch, t.nv, g.warps);
+      L = crba_tmem_layout<T>(t.maxpathdof, t.maxdepth, t.nbranch, t.nv, g.warps, t.ffroot);
 #define BRBD_LAUNCH(NT)                                                                              \
   {                                                                                                  \
     st = set_smem(crba_tmem_kernel<T, NT>, g.dyn_bytes);                                             \

@@ -136,11 +136,15 @@ struct CrbaTmemLayout
   int tY, tX, tvals; // TMEM value offsets: Y (10 x (maxdepth - 1)), oMi (12 x nbranch); values per warp slice
   int tcols;         // columns allocated by the CTA (power of two)
 };
-template<class T> inline CrbaTmemLayout crba_tmem_layout(int maxpathdof, int maxdepth, int nbranch, int nv, int warps)
+// With a free-flyer root (TreePOD::ffroot) the 6 J columns of the root are not stored: its oMi (12 values) takes their
+// place, the columns of the other path dofs move down by CRBA_FF_SAVED slots, and the six root rows of every column are
+// oMi_root.actInv(F) — the force in the root frame — instead of six 6-D dot products (J_root = oMi_root's action matrix).
+constexpr int CRBA_FF_SAVED = 24;
+template<class T> inline CrbaTmemLayout crba_tmem_layout(int maxpathdof, int maxdepth, int nbranch, int nv, int warps, int ffroot)
 {
   CrbaTmemLayout L;
   L.oJ = 0;
-  L.nstate = 6 * maxpathdof;
+  L.nstate = 6 * maxpathdof - (ffroot ? CRBA_FF_SAVED : 0);
   L.epad = nv;
   L.tY = 0;
   L.tX = 10 * (maxdepth > 1 ? maxdepth - 1 : 1);
@@ -171,6 +175,8 @@ crba_tmem_kernel(const __grid_constant__ TreePOD<T> m, const CrbaTmemLayout L, c
   // this warp's slice: lanes of its SM sub-partition, columns after those of warp - 4 (if any)
   const TmemSlots<T> tm{tbase + (((uint32_t)(warp & 3) * 32u) << 16) + (uint32_t)((warp >> 2) * L.tvals * (int)(sizeof(T) / 4))};
   const int dgc = (int)ldM - nv;
+  const bool ffroot = m.ffroot != 0;
+  const int joff = ffroot ? CRBA_FF_SAVED : 0;
   const int64_t ntiles = (B + 31) / 32;
   for (int64_t tile = (int64_t)blockIdx.x * nw + warp; tile < ntiles; tile += (int64_t)gridDim.x * nw)
   {
@@ -209,7 +215,9 @@ crba_tmem_kernel(const __grid_constant__ TreePOD<T> m, const CrbaTmemLayout L, c
           const T x[12] = {X.R.c0.x, X.R.c0.y, X.R.c0.z, X.R.c1.x, X.R.c1.y, X.R.c1.z, X.R.c2.x, X.R.c2.y, X.R.c2.z, X.p.x, X.p.y, X.p.z};
           tm.template store<12>(L.tX + 12 * r.bslot, x);
         }
-        for (int k = 0; k < r.nvj; ++k) put_motion(st, L.oJ + 6 * (r.pdof + k), act_S_col(X, r.type, k));
+        if (ffroot && i == 1) put_se3(st, L.oJ, X);
+        else
+          for (int k = 0; k < r.nvj; ++k) put_motion(st, L.oJ + 6 * (r.pdof + k) - joff, act_S_col(X, r.type, k));
         Yown = act(X, tree_inertia(m, i));
         if (r.nchild > 0)
         {
@@ -226,10 +234,22 @@ crba_tmem_kernel(const __grid_constant__ TreePOD<T> m, const CrbaTmemLayout L, c
         for (int k = 0; k < r.nvj; ++k)
         {
           const int col = r.idx_v + k;
-          const Force<T> F = Y * get_motion<T>(st, L.oJ + 6 * (r.pdof + k));
+          Force<T> F;
+          int t0 = 0;
+          if (ffroot)
+          {
+            const SE3<T> Xr = get_se3<T>(st, L.oJ);
+            F = Y * (j == 1 ? act_S_col(Xr, J_FF, k) : get_motion<T>(st, L.oJ + 6 * (r.pdof + k) - joff));
+            // rows of the free-flyer root: J_root^T F = oMi_root.actInv(F)  (S = identity, joint-free-flyer.hpp:47-57)
+            const Vec3<T> fl = tmul(Xr.R, F.lin), fa = tmul(Xr.R, F.ang - cross(Xr.p, F.lin));
+            myrow[0] = fl.x; myrow[1] = fl.y; myrow[2] = fl.z; myrow[3] = fa.x; myrow[4] = fa.y; myrow[5] = fa.z;
+            t0 = 6;
+          }
+          else
+            F = Y * get_motion<T>(st, L.oJ + 6 * (r.pdof + k));
 #pragma unroll 4
-          for (int t = 0; t < npath; ++t)
-            myrow[m.path_row[j][t]] = dot6(get_motion<T>(st, L.oJ + 6 * t), F);
+          for (int t = t0; t < npath; ++t)
+            myrow[m.path_row[j][t]] = dot6(get_motion<T>(st, L.oJ + 6 * t - joff), F);
           myrow[col] += m.armature[col];
           __syncwarp();
           {

@@ -43,7 +43,7 @@ template<class T> struct TreePOD
   int maxpathdof; // max over joints of pdof + nvj
   int nbranch;    // number of branch slots (max number of branching joints on one root path)
   int pslots;     // persistent-store slots per configuration (ABA)
-  int pad_;
+  int ffroot;     // 1: joint 1 is a free-flyer and the only root joint (every root path starts with its 6 dofs)
   JointRec j[MAXJ];
   unsigned long long anc_mask[MAXNV]; // bit r set: row r belongs to an ancestor-or-self of the joint owning this column
   unsigned char path_row[MAXJ][MAXPATH]; // path_row[j][t]: tangent row of path dof t on the root path of joint j
@@ -82,6 +82,9 @@ template<class T> inline void build_tree(const ModelPOD<double> & M, TreePOD<T> 
     if (nchild[i] >= 2 && bdepth[i] + 1 > P.nbranch) P.nbranch = bdepth[i] + 1;
   }
   P.pslots = poff;
+  P.ffroot = (M.njoints > 1 && M.type[1] == J_FF && M.parent[1] == 0) ? 1 : 0;
+  for (int i = 2; i < M.njoints; ++i)
+    if (M.parent[i] == 0) P.ffroot = 0;
   for (int i = 1; i < M.njoints; ++i)
   {
     unsigned long long mask = 0;

@@ -14,7 +14,7 @@ from oracle import Oracle, build_oracle
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--models", default="manipulator,humanoid_random,simple_humanoid_ff,talos_reduced_ff")
-ap.add_argument("--algos", default="rnea,aba,crba,rnea_derivatives,aba_derivatives")
+ap.add_argument("--algos", default="rnea,aba,crba,rnea_derivatives,aba_derivatives,nle,gravity,minverse,integrate,euler_step")
 ap.add_argument("--batch", type=int, default=65536)
 ap.add_argument("--reps", type=int, default=5)
 ap.add_argument("--dtype", default="f64")
@@ -37,7 +37,8 @@ for name in args.models.split(","):
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
     outs = {"vec": torch.empty((B, nv), dtype=dt, device="cuda"),
             "m1": torch.empty((B, nv * nv), dtype=dt, device="cuda"), "m2": torch.empty((B, nv * nv), dtype=dt, device="cuda"),
-            "m3": torch.empty((B, nv * nv), dtype=dt, device="cuda")}
+            "m3": torch.empty((B, nv * nv), dtype=dt, device="cuda"), "vec2": torch.empty((B, nv), dtype=dt, device="cuda"),
+            "cfg": torch.empty((B, nq), dtype=dt, device="cuda")}
     calls = {
         "rnea": (lambda: pb.rneaInParallel(1, pool, tq, tv, ta, outs["vec"], async_=True), es * (nq + 3 * nv), "rnea"),
         "aba": (lambda: pb.abaInParallel(1, pool, tq, tv, ta, outs["vec"], async_=True), es * (nq + 3 * nv), "aba"),
@@ -46,10 +47,17 @@ for name in args.models.split(","):
                              es * (nq + 2 * nv + 3 * nv * nv), "rnea_derivatives"),
         "aba_derivatives": (lambda: pb.computeABADerivativesInParallel(1, pool, tq, tv, ta, outs["m1"], outs["m2"], outs["m3"], async_=True),
                             es * (nq + 2 * nv + 3 * nv * nv), "aba_derivatives"),
+        # the callers' other needs; no operation count in the oracle -> HBM figures only
+        "nle": (lambda: pb.nonLinearEffectsInParallel(1, pool, tq, tv, outs["vec"], async_=True), es * (nq + 2 * nv), None),
+        "gravity": (lambda: pb.computeGeneralizedGravityInParallel(1, pool, tq, outs["vec"], async_=True), es * (nq + nv), None),
+        "minverse": (lambda: pb.computeMinverseInParallel(1, pool, tq, outs["m1"], async_=True), es * (nq + nv * nv), None),
+        "integrate": (lambda: pb.integrateInParallel(1, pool, tq, tv, outs["cfg"], async_=True), es * (2 * nq + nv), None),
+        "euler_step": (lambda: pb.abaEulerStepInParallel(1, pool, tq, tv, ta, 1e-3, outs["cfg"], outs["vec2"], async_=True),
+                       es * (2 * nq + 3 * nv), "aba"),
     }
     for algo in args.algos.split(","):
         fn, bytes_per, oname = calls[algo]
-        flops = orc.count_flops(oname, q[:, 0], v[:, 0], a[:, 0])["flops"]
+        flops = orc.count_flops(oname, q[:, 0], v[:, 0], a[:, 0])["flops"] if oname else 0
         for _ in range(3):
             fn()
         torch.cuda.synchronize()
