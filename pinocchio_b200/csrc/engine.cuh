@@ -201,22 +201,43 @@ template<class T> BRBD_DI Motion<T> act_S_col(const SE3<T> & X, int type, int k)
 template<class T>
 BRBD_DI void tile_load(T * s, int pad, const T * g, int64_t ld, int rows, int ncols, int lane)
 {
+  // loads are issued in batches of 8 per lane before the first shared-memory store, so that their latencies overlap
+  constexpr int U = 8;
   if (ld == rows)
   {
     const int total = rows * ncols;
     int c = 0, r = lane;
     while (r >= rows) { r -= rows; ++c; }
-    for (int k = lane; k < total; k += 32)
+    for (int k0 = lane; k0 < total; k0 += 32 * U)
     {
-      s[c * pad + r] = g[k];
-      r += 32;
-      while (r >= rows) { r -= rows; ++c; }
+      T tmp[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+      {
+        const int k = k0 + 32 * u;
+        tmp[u] = k < total ? g[k] : T(0);
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+      {
+        if (k0 + 32 * u < total) s[c * pad + r] = tmp[u];
+        r += 32;
+        while (r >= rows) { r -= rows; ++c; }
+      }
     }
   }
   else
   {
-    for (int c = 0; c < ncols; ++c)
-      for (int r = lane; r < rows; r += 32) s[c * pad + r] = g[(int64_t)c * ld + r];
+    for (int c0 = 0; c0 < ncols; c0 += U)
+      for (int r = lane; r < rows; r += 32)
+      {
+        T tmp[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) tmp[u] = c0 + u < ncols ? g[(int64_t)(c0 + u) * ld + r] : T(0);
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+          if (c0 + u < ncols) s[(c0 + u) * pad + r] = tmp[u];
+      }
   }
 }
 template<class T>
