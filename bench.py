@@ -101,6 +101,15 @@ def algorithmic_numbers(model, orc):
     }
 
 
+def host_threads():
+    """Every hardware thread this process may run on.  Not omp_get_max_threads(): torchrun exports OMP_NUM_THREADS=1 to
+    its workers, which would time the CPU arm on one core."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
 def cpu_sample(orc, model, nthreads, target_s=12.0):
     """ABA + CRBA with the OpenMP oracle on a bounded sample of the workload; returns (evals/s, sample size)."""
     from conftest import random_inputs
@@ -129,7 +138,7 @@ def run_reference(args):
     build_oracle()
     model = load_model(MODEL)
     orc = Oracle(model)
-    nthreads = Oracle.max_threads()
+    nthreads = host_threads()
     from conftest import random_inputs
     n = 4096
     q, v, tau = random_inputs(model, n, 5)
@@ -326,7 +335,7 @@ def main():
         "fp64_peak_measured_TFLOPs": fp64_peak / 1e12,
     }
     if world == 1 and not args.no_cpu:
-        nthreads = Oracle.max_threads()
+        nthreads = host_threads()
         cpu_v, n2, dt = cpu_sample(orc, model, nthreads)
         line["cpu_baseline"] = {"value": cpu_v, "unit": "evals/s", "cores": nthreads, "kind": "port",
                                 "sample": f"{n2} configurations through ABA(WORLD) + CRBA(WORLD) in {dt:.1f} s with the OpenMP "
