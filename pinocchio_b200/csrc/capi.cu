@@ -216,6 +216,21 @@ Geometry2 pick_geometry2(const DeviceCtx & d, size_t state_bytes, size_t warp_by
   return g;
 }
 
+// Warps per SM of a persistent one-CTA-per-SM kernel whose per-SM throughput does not grow with occupancy any more: fewest
+// rounds of the grid over the batch first, then the fewest warps that reach that number of rounds.
+inline int pick_warps_by_rounds(const DeviceCtx & d, int64_t B, int wmax)
+{
+  const int64_t tiles = (B + 31) / 32;
+  int best_w = wmax;
+  int64_t best_rounds = (tiles + (int64_t)d.sm_count * wmax - 1) / ((int64_t)d.sm_count * wmax);
+  for (int w = wmax - 1; w >= 1; --w)
+  {
+    const int64_t rounds = (tiles + (int64_t)d.sm_count * w - 1) / ((int64_t)d.sm_count * w);
+    if (rounds <= best_rounds) { best_rounds = rounds; best_w = w; }
+  }
+  return best_w;
+}
+
 // kernels are instantiated for 1..4 warps per CTA (NT = threads per CTA is a template parameter)
 #define BRBD_SWITCH_WARPS(w)              \
   switch (w)                              \
@@ -232,15 +247,32 @@ brbd_status launch_rnea(brbd_pool * p, DeviceCtx & d, const T * q, int64_t ldq, 
 {
   const TreePOD<T> & t = tree_of<T>(p);
   const RneaLayout L = rnea_layout(t.maxdepth, t.nbranch);
-  const Geometry2 g = pick_geometry2(d, (size_t)L.nstate * sizeof(T), 0, B, 4, 4);
+  // one CTA per SM, up to 8 warps, chosen by the number of rounds (as CRBA)
+  const size_t per_warp = (size_t)32 * L.nstate * sizeof(T);
+  int warps = (int)std::max<size_t>(1, std::min<size_t>(8, (size_t)d.max_smem_optin / per_warp));
+  warps = pick_warps_by_rounds(d, B, warps);
+  if (const char * e = std::getenv("BRBD_RNEA_WARPS")) warps = std::max(1, std::min(warps, std::atoi(e)));
+  const size_t dyn_bytes = (size_t)warps * per_warp;
+  const int64_t ctas_needed = (B + warps * 32 - 1) / (warps * 32);
+  const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(ctas_needed, (int64_t)d.sm_count));
   brbd_status st = BRBD_OK;
 #define BRBD_LAUNCH(NT)                                                                              \
   {                                                                                                  \
-    st = set_smem(rnea_dfs_kernel<T, NT>, g.dyn_bytes);                                              \
+    st = set_smem(rnea_dfs_kernel<T, NT>, dyn_bytes);                                                \
     if (st != BRBD_OK) return st;                                                                    \
-    rnea_dfs_kernel<T, NT><<<g.grid, NT, g.dyn_bytes, d.s()>>>(t, L, q, ldq, v, ldv, a, lda, tau, ldtau, B); \
+    rnea_dfs_kernel<T, NT><<<grid, NT, dyn_bytes, d.s()>>>(t, L, q, ldq, v, ldv, a, lda, tau, ldtau, B); \
   }
-  BRBD_SWITCH_WARPS(g.warps)
+  switch (warps)
+  {
+  case 1: BRBD_LAUNCH(32) break;
+  case 2: BRBD_LAUNCH(64) break;
+  case 3: BRBD_LAUNCH(96) break;
+  case 4: BRBD_LAUNCH(128) break;
+  case 5: BRBD_LAUNCH(160) break;
+  case 6: BRBD_LAUNCH(192) break;
+  case 7: BRBD_LAUNCH(224) break;
+  default: BRBD_LAUNCH(256) break;
+  }
 #undef BRBD_LAUNCH
   p->launches += 1;
   CUDA_TRY(cudaGetLastError());
@@ -312,17 +344,7 @@ brbd_status launch_crba(brbd_pool * p, DeviceCtx & d, const T * q, int64_t ldq, 
       // Per-SM throughput is flat from 5 warps up (measured, profiles/r1_v5_crba_warps.txt), so what counts is the number of
       // rounds the persistent grid needs: fewest rounds first, then the fewest warps that reach it (65536 configurations of
       // simple_humanoid: 7 warps -> 1.98 rounds, 8 -> 1.73 rounds of which the second is 73 % full, 6 -> 2.3 i.e. 3 rounds).
-      {
-        const int64_t tiles = (B + 31) / 32;
-        int best_w = g.warps;
-        int64_t best_rounds = (tiles + (int64_t)d.sm_count * g.warps - 1) / ((int64_t)d.sm_count * g.warps);
-        for (int w = g.warps - 1; w >= 1; --w)
-        {
-          const int64_t rounds = (tiles + (int64_t)d.sm_count * w - 1) / ((int64_t)d.sm_count * w);
-          if (rounds <= best_rounds) { best_rounds = rounds; best_w = w; }
-        }
-        g.warps = best_w;
-      }
+      g.warps = pick_warps_by_rounds(d, B, g.warps);
       if (const char * e = std::getenv("BRBD_CRBA_WARPS")) // experiments: cap the warps per SM
         g.warps = std::max(1, std::min(g.warps, std::atoi(e)));
       // the element -> configuration table of the emitter (32 * nv bytes) sits after the warp regions

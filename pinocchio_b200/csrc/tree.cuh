@@ -177,14 +177,14 @@ template<class T> BRBD_DI Inertia<T> tree_inertia(const TreePOD<T> & m, int i)
 // liMi = jointPlacements[i] * M_J(q) with the structural zeros of M_J dropped (same arithmetic as
 // engine.cuh joint_liMi; reference rnea.hxx:61, aba.hxx:117, crba.hxx:47 + the joints' calc()).
 // qj points at this configuration's q segment in GLOBAL memory.
-template<class T> BRBD_DI SE3<T> tree_liMi(const TreePOD<T> & m, int i, int type, const T * __restrict__ qj, T q0)
+// liMi of joint i from (s, c): revolute (s, c) = sincos(q); prismatic s = q; multi-dof joints read q from global memory
+// (s = first coordinate).  Kernels that need liMi again in their backward sweep keep (s, c) instead of the 12 values.
+template<class T> BRBD_DI SE3<T> tree_liMi_sc(const TreePOD<T> & m, int i, int type, const T * __restrict__ qj, T s, T c)
 {
   const SE3<T> P = tree_placement(m, i);
   SE3<T> X;
   if (type <= J_RZ)
   {
-    T s, c;
-    sincos_t(q0, &s, &c);
     X.p = P.p;
     if (type == J_RX) { X.R.c0 = P.R.c0; X.R.c1 = c * P.R.c1 + s * P.R.c2; X.R.c2 = c * P.R.c2 - s * P.R.c1; }
     else if (type == J_RY) { X.R.c1 = P.R.c1; X.R.c2 = c * P.R.c2 + s * P.R.c0; X.R.c0 = c * P.R.c0 - s * P.R.c2; }
@@ -193,29 +193,41 @@ template<class T> BRBD_DI SE3<T> tree_liMi(const TreePOD<T> & m, int i, int type
   else if (type <= J_PZ)
   {
     X.R = P.R;
-    X.p = P.p + q0 * P.R.col(type - J_PX);
+    X.p = P.p + s * P.R.col(type - J_PX);
   }
   else if (type == J_FF)
   {
     SE3<T> MJ;
     MJ.R = quat_to_mat(__ldg(qj + 3), __ldg(qj + 4), __ldg(qj + 5), __ldg(qj + 6));
-    MJ.p = Vec3<T>(q0, __ldg(qj + 1), __ldg(qj + 2));
+    MJ.p = Vec3<T>(s, __ldg(qj + 1), __ldg(qj + 2));
     X = P * MJ;
   }
   else if (type == J_SPH)
   {
-    X.R = P.R * quat_to_mat(q0, __ldg(qj + 1), __ldg(qj + 2), __ldg(qj + 3));
+    X.R = P.R * quat_to_mat(s, __ldg(qj + 1), __ldg(qj + 2), __ldg(qj + 3));
     X.p = P.p;
   }
   else
   { // planar: q = (x, y, cos, sin)
-    const T c = __ldg(qj + 2), s = __ldg(qj + 3);
-    X.R.c0 = c * P.R.c0 + s * P.R.c1;
-    X.R.c1 = c * P.R.c1 - s * P.R.c0;
+    const T cc = __ldg(qj + 2), ss = __ldg(qj + 3);
+    X.R.c0 = cc * P.R.c0 + ss * P.R.c1;
+    X.R.c1 = cc * P.R.c1 - ss * P.R.c0;
     X.R.c2 = P.R.c2;
-    X.p = P.p + q0 * P.R.c0 + __ldg(qj + 1) * P.R.c1;
+    X.p = P.p + s * P.R.c0 + __ldg(qj + 1) * P.R.c1;
   }
   return X;
+}
+// (s, c) of joint i for tree_liMi_sc
+template<class T> BRBD_DI void tree_sc(int type, T q0, T * s, T * c)
+{
+  if (type <= J_RZ) sincos_t(q0, s, c);
+  else { *s = q0; *c = T(0); }
+}
+template<class T> BRBD_DI SE3<T> tree_liMi(const TreePOD<T> & m, int i, int type, const T * __restrict__ qj, T q0)
+{
+  T s, c;
+  tree_sc(type, q0, &s, &c);
+  return tree_liMi_sc(m, i, type, qj, s, c);
 }
 template<class T> BRBD_DI SE3<T> tree_liMi(const TreePOD<T> & m, int i, int type, const T * __restrict__ qj)
 {
