@@ -708,6 +708,7 @@ BRBD_DI void coop_dblock_product_dispatch(int nv, const T * Minv, int mld, const
 // `base` = this group's region (AbaCoopLayout), q / v / tau already staged at oq / ov / ou.
 // MODE 0: computeABADerivatives.  MODE 1: computeMinverse (reference: algorithm/aba.hxx:613-902) — phases A1, A2, A3, A5 with
 // v = tau = 0; like the reference's data.Minv only the upper triangle is meaningful, the strictly-lower part is written as zeros.
+// MODE 2: ABA alone (phases A1, A2, A4) — the small-batch path of abaInParallel, see rnea_coop_kernel in deriv_coop.cuh.
 template<class T, int G, int MODE = 0>
 BRBD_DI void aba_derivatives_coop_config(const ModelPOD<T> & m, const CoopTables & tb, const AbaCoopLayout & L, T * base, int gl,
                                          T * __restrict__ gq, T * __restrict__ gv, T * __restrict__ gm, T * __restrict__ gddq, bool active)
@@ -718,6 +719,13 @@ BRBD_DI void aba_derivatives_coop_config(const ModelPOD<T> & m, const CoopTables
   int oa_unused = JR_OA;
   const int xoff = coop_forward<T, G, false>(m, tb, sq, sv, (const T *)nullptr, jr, cb, gl, &oa_unused);
   coop_aba_backward<T, G>(m, tb, jr, cb, su, base + L.osc, gl, xoff);
+  if (MODE == 2)
+  {
+    coop_aba_forward2<T, G>(m, tb, jr, cb, su, gl);
+    if (active)
+      for (int k = gl; k < nv; k += G) gddq[k] = su[k];
+    return;
+  }
   if (G == 32 && nv > G)
   {
     coop_minv_upper<T, G, (G == 32 ? 2 : 1)>(m, tb, cb, Minv, mld, gl);
@@ -781,12 +789,7 @@ aba_derivatives_coop_kernel(const ModelPOD<T> * __restrict__ gmod, const __grid_
   __shared__ CoopTables tb;
   extern __shared__ __align__(16) unsigned char dyn_smem[];
   copy_model_to_smem(&m, gmod);
-  {
-    const int n = (int)(sizeof(CoopTables) / 4);
-    const int * s = reinterpret_cast<const int *>(&gtb);
-    int * d = reinterpret_cast<int *>(&tb);
-    for (int k = threadIdx.x; k < n; k += blockDim.x) d[k] = s[k];
-  }
+  copy_words_to_smem(reinterpret_cast<int *>(&tb), reinterpret_cast<const int *>(&gtb), (int)(sizeof(CoopTables) / 4));
   __syncthreads();
   constexpr int GPW = 32 / G; // configurations per warp
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
@@ -801,14 +804,14 @@ aba_derivatives_coop_kernel(const ModelPOD<T> * __restrict__ gmod, const __grid_
     if (!active) cfg = B - 1; // idle groups shadow the last configuration (stores suppressed)
     const T * gq_in = q + cfg * ldq, * gv_in = v + cfg * ldv, * gt_in = tau + cfg * ldtau;
     for (int k = gl; k < nq; k += G) base[L.oq + k] = gq_in[k];
-    if (MODE == 0)
+    if (MODE != 1)
       for (int k = gl; k < nv; k += G) { base[L.ov + k] = gv_in[k]; base[L.ou + k] = gt_in[k]; }
     else
       for (int k = gl; k < nv; k += G) { base[L.ov + k] = T(0); base[L.ou + k] = T(0); }
     BRBD_SYNCWARP();
     aba_derivatives_coop_config<T, G, MODE>(m, tb, L, base, gl, MODE == 0 ? dq + cfg * ld_dq : (T *)nullptr,
-                                            MODE == 0 ? dv + cfg * ld_dv : (T *)nullptr, dtau + cfg * ld_dtau,
-                                            (MODE == 0 && ddq) ? ddq + cfg * ldddq : (T *)nullptr, active);
+                                            MODE == 0 ? dv + cfg * ld_dv : (T *)nullptr, MODE == 2 ? (T *)nullptr : dtau + cfg * ld_dtau,
+                                            (MODE != 1 && ddq) ? ddq + cfg * ldddq : (T *)nullptr, active);
     BRBD_SYNCWARP();
   }
 }

@@ -16,6 +16,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -177,9 +179,23 @@ Geometry pick_geometry(const DeviceCtx & d, size_t per_warp, size_t static_bytes
   return best;
 }
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize is raised only when a launch needs more than what was set before for that
+// kernel on that device (the call costs microseconds, which is what a small batch is made of)
 template<class K> brbd_status set_smem(K kernel, size_t dyn_bytes)
 {
+  static std::mutex mu;
+  static std::map<std::pair<int, const void *>, size_t> done;
+  int dev = 0;
+  CUDA_TRY(cudaGetDevice(&dev));
+  const std::pair<int, const void *> key(dev, reinterpret_cast<const void *>(kernel));
+  {
+    std::lock_guard<std::mutex> lock(mu);
+    auto it = done.find(key);
+    if (it != done.end() && it->second >= dyn_bytes) return BRBD_OK;
+  }
   CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_bytes));
+  std::lock_guard<std::mutex> lock(mu);
+  done[key] = dyn_bytes;
   return BRBD_OK;
 }
 
@@ -241,11 +257,70 @@ inline int pick_warps_by_rounds(const DeviceCtx & d, int64_t B, int wmax)
   default: BRBD_LAUNCH(128) break;        \
   }
 
+// Launch geometry of the warp-cooperative kernels: G lanes per configuration, `per_group` elements of shared
+// memory per configuration, one CTA per SM with as many warps as fit (<= 8), persistent grid.
+struct GeometryCoop
+{
+  int warps, grid;
+  size_t dyn_bytes;
+};
+inline int coop_group_size(int nv) { return nv <= 8 ? 8 : (nv <= 16 ? 16 : 32); }
+GeometryCoop pick_geometry_coop(const DeviceCtx & d, size_t group_bytes, int G, size_t static_bytes, int64_t batch)
+{
+  const size_t per_warp = group_bytes * (size_t)(32 / G);
+  const size_t cap = (size_t)d.max_smem_optin - static_bytes;
+  GeometryCoop g;
+  g.warps = (int)std::max<size_t>(1, std::min<size_t>(8, cap / per_warp));
+  const int64_t per_cta = (int64_t)g.warps * (32 / G);
+  g.grid = (int)std::max<int64_t>(1, std::min<int64_t>((batch + per_cta - 1) / per_cta, (int64_t)d.sm_count));
+  // small batches: spread the configurations over all SMs instead of filling a few CTAs
+  while (g.warps > 1 && (int64_t)(g.warps - 1) * (32 / G) * d.sm_count >= batch) --g.warps;
+  g.dyn_bytes = (size_t)g.warps * per_warp;
+  const int64_t per_cta2 = (int64_t)g.warps * (32 / G);
+  g.grid = (int)std::max<int64_t>(1, std::min<int64_t>((batch + per_cta2 - 1) / per_cta2, (int64_t)d.sm_count));
+  return g;
+}
+// Below this many configurations per device the one-configuration-per-thread kernels cannot fill the GPU and their latency
+// (one thread walking the whole tree) dominates: rneaInParallel / abaInParallel switch to the cooperative kernels
+// (G lanes per configuration).  Measured crossover: profiles/r1_v5_small_batch.txt.
+inline int64_t coop_max_batch(bool aba, int nv)
+{
+  if (const char * e = std::getenv("BRBD_COOP_MAX_BATCH")) return std::atoll(e);
+  if (nv <= 8) return 4096; // 4 configurations per warp
+  return aba ? 2048 : 4096;
+}
+
 template<class T>
 brbd_status launch_rnea(brbd_pool * p, DeviceCtx & d, const T * q, int64_t ldq, const T * v, int64_t ldv, const T * a,
                         int64_t lda, T * tau, int64_t ldtau, int64_t B)
 {
   const TreePOD<T> & t = tree_of<T>(p);
+  if (B <= coop_max_batch(false, p->model.pd.nv))
+  {
+    const ModelPOD<double> & M = p->model.pd;
+    const CoopLayout L = coop_layout(M.nq, M.nv, M.njoints);
+    const int G = coop_group_size(M.nv);
+    const size_t static_bytes = sizeof(ModelPOD<T>) + sizeof(CoopTables) + 1024;
+    const GeometryCoop g = pick_geometry_coop(d, (size_t)L.per_group * sizeof(T), G, static_bytes, B);
+    if (g.dyn_bytes + static_bytes <= (size_t)d.max_smem_optin + 1024)
+    {
+      brbd_status st = BRBD_OK;
+#define BRBD_LAUNCH_COOP(GG)                                                                                     \
+  {                                                                                                              \
+    st = set_smem(rnea_coop_kernel<T, GG>, g.dyn_bytes);                                                         \
+    if (st != BRBD_OK) return st;                                                                                \
+    rnea_coop_kernel<T, GG><<<g.grid, g.warps * 32, g.dyn_bytes, d.s()>>>(dev_model<T>(d), p->model.coop, L, q, ldq, v, ldv, a, lda, \
+                                                                            tau, ldtau, B);                      \
+  }
+      if (G == 8) BRBD_LAUNCH_COOP(8)
+      else if (G == 16) BRBD_LAUNCH_COOP(16)
+      else BRBD_LAUNCH_COOP(32)
+#undef BRBD_LAUNCH_COOP
+      p->launches += 1;
+      CUDA_TRY(cudaGetLastError());
+      return BRBD_OK;
+    }
+  }
   const RneaLayout L = rnea_layout(t.maxdepth, t.nbranch);
   // one CTA per SM, up to 8 warps, chosen by the number of rounds (as CRBA)
   const size_t per_warp = (size_t)32 * L.nstate * sizeof(T);
@@ -285,6 +360,31 @@ brbd_status launch_aba(brbd_pool * p, DeviceCtx & d, const T * q, int64_t ldq, c
 {
   const TreePOD<T> & t = tree_of<T>(p);
   brbd_status st = BRBD_OK;
+  if (B <= coop_max_batch(true, p->model.pd.nv) && p->model.coop.nbranch <= A_MAXBRANCH)
+  {
+    const ModelPOD<double> & M = p->model.pd;
+    const int G = coop_group_size(M.nv);
+    const AbaCoopLayout L = aba_coop_layout(M.nq, M.nv, M.njoints, G);
+    const size_t static_bytes = sizeof(ModelPOD<T>) + sizeof(CoopTables) + 1024;
+    const GeometryCoop g = pick_geometry_coop(d, (size_t)L.per_group * sizeof(T), G, static_bytes, B);
+    if (g.dyn_bytes + static_bytes <= (size_t)d.max_smem_optin + 1024)
+    {
+#define BRBD_LAUNCH_COOP(GG)                                                                                     \
+  {                                                                                                              \
+    st = set_smem(aba_derivatives_coop_kernel<T, GG, 2>, g.dyn_bytes);                                           \
+    if (st != BRBD_OK) return st;                                                                                \
+    aba_derivatives_coop_kernel<T, GG, 2><<<g.grid, g.warps * 32, g.dyn_bytes, d.s()>>>(                         \
+      dev_model<T>(d), p->model.coop, L, q, ldq, v, ldv, tau, ldtau, (T *)nullptr, 0, (T *)nullptr, 0, (T *)nullptr, 0, a, lda, B); \
+  }
+      if (G == 8) BRBD_LAUNCH_COOP(8)
+      else if (G == 16) BRBD_LAUNCH_COOP(16)
+      else BRBD_LAUNCH_COOP(32)
+#undef BRBD_LAUNCH_COOP
+      p->launches += 1;
+      CUDA_TRY(cudaGetLastError());
+      return BRBD_OK;
+    }
+  }
   // preferred: per-depth (Y, f, a_bias) in tensor memory, J of the root path + branch slots in shared memory
   {
     AbaTmemLayout L = aba_tmem_layout<T>(t.maxpathdof, t.maxdepth, t.nbranch, 4);
@@ -390,26 +490,6 @@ brbd_status launch_crba(brbd_pool * p, DeviceCtx & d, const T * q, int64_t ldq, 
   p->launches += 1;
   CUDA_TRY(cudaGetLastError());
   return BRBD_OK;
-}
-
-// Launch geometry of the warp-cooperative kernels: G lanes per configuration, `per_group` elements of shared
-// memory per configuration, one CTA per SM with as many warps as fit (<= 8), persistent grid.
-struct GeometryCoop
-{
-  int warps, grid;
-  size_t dyn_bytes;
-};
-inline int coop_group_size(int nv) { return nv <= 8 ? 8 : (nv <= 16 ? 16 : 32); }
-GeometryCoop pick_geometry_coop(const DeviceCtx & d, size_t group_bytes, int G, size_t static_bytes, int64_t batch)
-{
-  const size_t per_warp = group_bytes * (size_t)(32 / G);
-  const size_t cap = (size_t)d.max_smem_optin - static_bytes;
-  GeometryCoop g;
-  g.warps = (int)std::max<size_t>(1, std::min<size_t>(8, cap / per_warp));
-  g.dyn_bytes = (size_t)g.warps * per_warp;
-  const int64_t per_cta = (int64_t)g.warps * (32 / G);
-  g.grid = (int)std::max<int64_t>(1, std::min<int64_t>((batch + per_cta - 1) / per_cta, (int64_t)d.sm_count));
-  return g;
 }
 
 template<class T>

@@ -333,16 +333,16 @@ BRBD_DI void coop_joint_quantities(const ModelPOD<T> & m, T * jr, int gl, int xo
 // Joints are numbered depth-first, so walking i = nj-1 .. 1 and adding record i into record parent(i) completes
 // every subtree sum; a lane owns NC components for the whole walk (no cross-lane dependency, no barrier), and the
 // running sum of a chain (parent(i) == i - 1) stays in registers.
-template<class T, int G>
+template<class T, int G, int FIRST = 0, int COUNT = JR_NSUM>
 BRBD_DI void coop_subtree_sums(const ModelPOD<T> & m, T * jr, int gl)
 {
-  constexpr int NC = (JR_NSUM + G - 1) / G;
+  constexpr int NC = (COUNT + G - 1) / G;
   const int nj = m.njoints;
   T carry[NC];
   bool on[NC];
 #pragma unroll
-  for (int t = 0; t < NC; ++t) { on[t] = gl + t * G < JR_NSUM; carry[t] = T(0); }
-  T * col = jr + gl;
+  for (int t = 0; t < NC; ++t) { on[t] = gl + t * G < COUNT; carry[t] = T(0); }
+  T * col = jr + FIRST + gl;
   int carry_idx = -1;
   for (int i = nj - 1; i > 0; --i)
   {
@@ -517,12 +517,7 @@ rnea_derivatives_coop_kernel(const ModelPOD<T> * __restrict__ gm, const __grid_c
   __shared__ CoopTables tb;
   extern __shared__ __align__(16) unsigned char dyn_smem[];
   copy_model_to_smem(&m, gm);
-  {
-    const int n = (int)(sizeof(CoopTables) / 4);
-    const int * s = reinterpret_cast<const int *>(&gtb);
-    int * d = reinterpret_cast<int *>(&tb);
-    for (int k = threadIdx.x; k < n; k += blockDim.x) d[k] = s[k];
-  }
+  copy_words_to_smem(reinterpret_cast<int *>(&tb), reinterpret_cast<const int *>(&gtb), (int)(sizeof(CoopTables) / 4));
   __syncthreads();
   constexpr int GPW = 32 / G; // configurations per warp
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
@@ -548,6 +543,76 @@ rnea_derivatives_coop_kernel(const ModelPOD<T> * __restrict__ gm, const __grid_c
     coop_entries<T, G, true>(m, tb, cb, dq + cfg * ld_dq, dv + cfg * ld_dv, da + cfg * ld_da, gl, active);
     if (tau && active)
       for (int k = gl; k < nv; k += G) tau[cfg * ldtau + k] = sa[k];
+    BRBD_SYNCWARP();
+  }
+}
+
+// ---- small batches: RNEA, G lanes per configuration ------------------------------------------------------------------
+// One configuration per thread needs >= 33 000 configurations to fill a B200 and its latency is that of one thread walking
+// the whole tree (~90 us for a humanoid).  Below that, the batch is given to the cooperative phases above: forward kinematics
+// by pointer jumping, f_i = Y_i a_i + v_i x* (Y_i v_i) per joint (rnea.hxx:71-73 in the world frame), subtree sums of f
+// (the `f[parent] += liMi.act(f)` of rnea.hxx:105-106), tau = J^T f + armature o a (rnea.hxx:103, :158).
+template<class T, int G>
+BRBD_DI void rnea_coop_config(const ModelPOD<T> & m, const CoopTables & tb, const CoopLayout & L, T * base, int gl)
+{
+  T * sq = base + L.oq, * sv = base + L.ov, * sa = base + L.oa, * jr = base + L.ojr, * cb = base + L.ocb;
+  int oa_off = JR_OA;
+  const int xoff = coop_forward<T, G, true>(m, tb, sq, sv, sa, jr, cb, gl, &oa_off);
+  const int nj = m.njoints, nv = m.nv;
+  for (int i = 1 + gl; i < nj; i += G)
+  {
+    T * r = jr + i * JR_STRIDE;
+    const SE3<T> X = load_se3(r + xoff);
+    const Motion<T> ov = load_motion(r + JR_OV);
+    Motion<T> oa = load_motion(r + oa_off);
+    oa.lin -= Vec3<T>(m.gravity[0], m.gravity[1], m.gravity[2]); // a_gf[0] = -gravity (rnea.hxx:138)
+    const Inertia<T> Y = act(X, model_inertia(m, i));
+    Force<T> of = Y * oa;
+    of += fcross(ov, Y * ov);
+    store6(r + JR_OF, of);
+  }
+  BRBD_SYNCWARP();
+  coop_subtree_sums<T, G, JR_OF, 6>(m, jr, gl);
+  for (int c = gl; c < nv; c += G)
+  {
+    T Jv[6];
+    ld6(cb + c * CB_STRIDE + CB_J, Jv);
+    const T * f = jr + m.dof_joint[c] * JR_STRIDE + JR_OF;
+    sa[c] = Jv[0] * f[0] + Jv[1] * f[1] + Jv[2] * f[2] + Jv[3] * f[3] + Jv[4] * f[4] + Jv[5] * f[5] + m.armature[c] * sa[c];
+  }
+  BRBD_SYNCWARP();
+}
+
+template<class T, int G>
+__global__ void __launch_bounds__(256, 1)
+rnea_coop_kernel(const ModelPOD<T> * __restrict__ gm, const __grid_constant__ CoopTables gtb, const CoopLayout L,
+                 const T * __restrict__ q, int64_t ldq, const T * __restrict__ v, int64_t ldv, const T * __restrict__ a, int64_t lda,
+                 T * __restrict__ tau, int64_t ldtau, int64_t B)
+{
+  __shared__ ModelPOD<T> m;
+  __shared__ CoopTables tb;
+  extern __shared__ __align__(16) unsigned char dyn_smem[];
+  copy_model_to_smem(&m, gm);
+  copy_words_to_smem(reinterpret_cast<int *>(&tb), reinterpret_cast<const int *>(&gtb), (int)(sizeof(CoopTables) / 4));
+  __syncthreads();
+  constexpr int GPW = 32 / G;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const int gl = lane % G, grp = lane / G;
+  T * base = reinterpret_cast<T *>(dyn_smem) + (size_t)(warp * GPW + grp) * L.per_group;
+  const int nq = m.nq, nv = m.nv;
+  const int64_t ntiles = (B + GPW - 1) / GPW;
+  for (int64_t tile = (int64_t)blockIdx.x * nw + warp; tile < ntiles; tile += (int64_t)gridDim.x * nw)
+  {
+    int64_t cfg = tile * GPW + grp;
+    const bool active = cfg < B;
+    if (!active) cfg = B - 1;
+    const T * gq_in = q + cfg * ldq, * gv_in = v + cfg * ldv, * ga_in = a + cfg * lda;
+    for (int k = gl; k < nq; k += G) base[L.oq + k] = gq_in[k];
+    for (int k = gl; k < nv; k += G) { base[L.ov + k] = gv_in[k]; base[L.oa + k] = ga_in[k]; }
+    BRBD_SYNCWARP();
+    rnea_coop_config<T, G>(m, tb, L, base, gl);
+    if (active)
+      for (int k = gl; k < nv; k += G) tau[cfg * ldtau + k] = base[L.oa + k];
     BRBD_SYNCWARP();
   }
 }

@@ -37,12 +37,32 @@ template<class T> struct ModelPOD
   T gravity[3];
 };
 
+// global -> shared copy of a POD by the whole CTA; loads are issued 8 at a time per thread so that their latencies overlap
+// (a small-batch launch runs one warp per CTA: a plain loop would serialise ~100 round trips to L2)
+BRBD_DI void copy_words_to_smem(int * d, const int * s, int n)
+{
+  constexpr int U = 8;
+  const int nt = blockDim.x;
+  for (int k0 = threadIdx.x; k0 < n; k0 += nt * U)
+  {
+    int tmp[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+    {
+      const int k = k0 + u * nt;
+      tmp[u] = k < n ? s[k] : 0;
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+    {
+      const int k = k0 + u * nt;
+      if (k < n) d[k] = tmp[u];
+    }
+  }
+}
 template<class T> BRBD_DI void copy_model_to_smem(ModelPOD<T> * dst, const ModelPOD<T> * src)
 {
-  const int n = (int)(sizeof(ModelPOD<T>) / 4);
-  const int * s = reinterpret_cast<const int *>(src);
-  int * d = reinterpret_cast<int *>(dst);
-  for (int k = threadIdx.x; k < n; k += blockDim.x) d[k] = s[k];
+  copy_words_to_smem(reinterpret_cast<int *>(dst), reinterpret_cast<const int *>(src), (int)(sizeof(ModelPOD<T>) / 4));
 }
 
 template<class T> BRBD_DI SE3<T> model_placement(const ModelPOD<T> & m, int i)

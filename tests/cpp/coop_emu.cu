@@ -75,8 +75,8 @@ void emu_aba_derivs(const ModelPOD<double> & m, const CoopTables & tb, const dou
     for (int k = 0; k < m.nq; ++k) base[L.oq + k] = q[cfg * m.nq + k];
     for (int k = 0; k < m.nv; ++k)
     {
-      base[L.ov + k] = MODE == 0 ? v[cfg * m.nv + k] : 0.0;
-      base[L.ou + k] = MODE == 0 ? tau[cfg * m.nv + k] : 0.0;
+      base[L.ov + k] = MODE != 1 ? v[cfg * m.nv + k] : 0.0;
+      base[L.ou + k] = MODE != 1 ? tau[cfg * m.nv + k] : 0.0;
     }
     run_lanes(G, [&](int gl) {
       aba_derivatives_coop_config<double, G, MODE>(m, tb, L, base, gl, dq + cfg * nn, dv + cfg * nn, dtau + cfg * nn, ddq + cfg * m.nv,
@@ -111,6 +111,20 @@ void emu_rnea_derivs(const ModelPOD<double> & m, const CoopTables & tb, const do
     free(base);
   }
 }
+template<int G>
+void emu_rnea(const ModelPOD<double> & m, const CoopTables & tb, const double * q, const double * v, const double * a, double * tau, int64_t B)
+{
+  const CoopLayout L = coop_layout(m.nq, m.nv, m.njoints);
+  for (int64_t cfg = 0; cfg < B; ++cfg)
+  {
+    double * base = alloc_region((size_t)L.per_group);
+    for (int k = 0; k < m.nq; ++k) base[L.oq + k] = q[cfg * m.nq + k];
+    for (int k = 0; k < m.nv; ++k) { base[L.ov + k] = v[cfg * m.nv + k]; base[L.oa + k] = a[cfg * m.nv + k]; }
+    run_lanes(G, [&](int gl) { rnea_coop_config<double, G>(m, tb, L, base, gl); });
+    for (int k = 0; k < m.nv; ++k) tau[cfg * m.nv + k] = base[L.oa + k];
+    free(base);
+  }
+}
 } // namespace
 
 extern "C" {
@@ -119,7 +133,9 @@ const char * emu_last_error(void) { return g_err.c_str(); }
 
 // algo: 0 = computeRNEADerivatives (third input = a; outputs dtau_dq, dtau_dv, dtau_da, tau),
 //       1 = computeABADerivatives  (third input = tau; outputs ddq_dq, ddq_dv, ddq_dtau, ddq),
-//       2 = computeMinverse        (only q is read; output o3 = upper triangle of Minv + zeros).
+//       2 = computeMinverse        (only q is read; output o3 = upper triangle of Minv + zeros),
+//       3 = rnea, small-batch path (third input = a; output ovec = tau),
+//       4 = aba, small-batch path  (third input = tau; output ovec = ddq).
 // Dense column-major blocks, one configuration per column (ld == rows).  G = 0 picks the group size the engine uses.
 int emu_derivatives(int algo, const brbd_flat_model * f, const double * q, const double * v, const double * x, double * o1, double * o2,
                     double * o3, double * ovec, int64_t B, int G)
@@ -130,7 +146,7 @@ int emu_derivatives(int algo, const brbd_flat_model * f, const double * q, const
   if (st != BRBD_OK) return (int)st;
   build_coop_tables(m, tb);
   if (G == 0) G = m.nv <= 8 ? 8 : (m.nv <= 16 ? 16 : 32);
-  if (algo >= 1 && tb.nbranch > A_MAXBRANCH)
+  if ((algo == 1 || algo == 2 || algo == 4) && tb.nbranch > A_MAXBRANCH)
   {
     g_err = "more branching joints than save slots";
     return -1;
@@ -139,7 +155,9 @@ int emu_derivatives(int algo, const brbd_flat_model * f, const double * q, const
   {                                                                                \
     if (algo == 0) emu_rnea_derivs<GG>(m, tb, q, v, x, o1, o2, o3, ovec, B);       \
     else if (algo == 1) emu_aba_derivs<GG, 0>(m, tb, q, v, x, o1, o2, o3, ovec, B); \
-    else emu_aba_derivs<GG, 1>(m, tb, q, v, x, o1, o2, o3, ovec, B);               \
+    else if (algo == 2) emu_aba_derivs<GG, 1>(m, tb, q, v, x, o1, o2, o3, ovec, B); \
+    else if (algo == 3) emu_rnea<GG>(m, tb, q, v, x, ovec, B);                     \
+    else emu_aba_derivs<GG, 2>(m, tb, q, v, x, o1, o2, o3, ovec, B);               \
   }
   if (G == 8) EMU_RUN(8)
   else if (G == 16) EMU_RUN(16)

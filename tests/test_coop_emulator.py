@@ -89,3 +89,18 @@ def test_emulated_minverse(emu, oracle_cls, name):
     nv = model.nv
     for b in range(q.shape[1]):
         assert not np.tril(Minv[:, b].reshape(nv, nv, order="F"), -1).any()
+
+
+@pytest.mark.parametrize("name", _models()[0])
+def test_emulated_small_batch_rnea_and_aba(emu, oracle_cls, name):
+    """The small-batch (cooperative) kernels of rneaInParallel / abaInParallel; aba(rnea(a)) == a closes the loop
+    (unittest/aba.cpp:143-154)."""
+    model = _get(name, _models()[1])
+    orc = oracle_cls(model)
+    q, v, a = random_inputs(model, 3, 19)
+    tau = _run(emu, 3, model, q, v, a)[3]
+    assert_close(tau, orc.rnea(q, v, a), atol=1e-12 * max(1.0, np.abs(tau).max()), what="rnea (coop)")
+    ddq = _run(emu, 4, model, q, v, tau)[3]
+    ref = orc.aba(q, v, tau)
+    assert_close(ddq, ref, atol=1e-12 + 1e-10 * np.abs(ref).max(), what="aba (coop)")
+    assert_close(ddq, a, atol=1e-12 + 1e-9 * np.abs(a).max(), what="aba(rnea(a)) == a")

@@ -254,3 +254,21 @@ def test_euler_step_device_resident_and_fp32(ctx):
     g32 = pb.computeGeneralizedGravityInParallel(1, pool, q.astype(np.float32))
     gref = orc.gravity(q)
     assert np.abs(g32 - gref).max() < 5e-5 * np.abs(gref).max()
+
+
+@pytest.mark.parametrize("name", ALL_MODELS)
+@pytest.mark.parametrize("path", ["thread", "coop"])
+def test_rnea_aba_both_paths(ctx, name, path, monkeypatch):
+    """rneaInParallel / abaInParallel have two device paths — one configuration per thread (large batches) and G lanes per
+    configuration (small batches, chosen by the batch size); BRBD_COOP_MAX_BATCH forces either. Both must match the oracle,
+    and each other to rounding."""
+    import pinocchio_b200 as pb
+    model, pool, orc = ctx(name)
+    monkeypatch.setenv("BRBD_COOP_MAX_BATCH", "0" if path == "thread" else "1000000")
+    for B in (1, 33, 130):
+        q, v, a = random_inputs(model, B, 51)
+        tau = pb.rneaInParallel(1, pool, q, v, a)
+        assert_close(tau, orc.rnea(q, v, a), atol=1e-12 * max(1.0, np.abs(tau).max()), what=f"rnea[{path}] {name} B={B}")
+        ddq = pb.abaInParallel(1, pool, q, v, tau)
+        ref = orc.aba(q, v, tau)
+        assert_close(ddq, ref, atol=1e-12 + 1e-10 * np.abs(ref).max(), what=f"aba[{path}] {name} B={B}")
