@@ -332,7 +332,8 @@ BRBD_DI void coop_joint_quantities(const ModelPOD<T> & m, T * jr, int gl, int xo
 // ---- phase 3: subtree sums, lanes = components ------------------------------------------------------------
 // Joints are numbered depth-first, so walking i = nj-1 .. 1 and adding record i into record parent(i) completes
 // every subtree sum; a lane owns NC components for the whole walk (no cross-lane dependency, no barrier), and the
-// running sum of a chain (parent(i) == i - 1) stays in registers.
+// running sum of a chain (parent(i) == i - 1) stays in registers.  (Tried: per-branching-joint accumulators with the own
+// values loaded four joints ahead — more instructions, no shorter: 4.2 % -> 5.6 % of computeABADerivatives.)
 template<class T, int G, int FIRST = 0, int COUNT = JR_NSUM>
 BRBD_DI void coop_subtree_sums(const ModelPOD<T> & m, T * jr, int gl)
 {
@@ -423,9 +424,11 @@ BRBD_DI void coop_columns(const ModelPOD<T> & m, const T * jr, T * cb, T * tau_i
 //                                    J_r . dFdv_c (:450-451),  J_r . dFda_c (:420-421, + armature on the diagonal)
 //   r in the strict subtree:         dFda_r . dAdq_c + dYtJ_r . dVdq_c (:433-435),  dFda_r . dAdv_c + dYtJ_r . J_c (:446-448)
 //   otherwise 0.
+// any_up / any_low: whether ANY row of the caller's row block is an ancestor row / a subtree row of column c (the same for all
+// lanes of the warp: every group of the warp evaluates the same model) — a part no row needs is skipped altogether.
 template<class T, bool WITH_DA>
 BRBD_DI void coop_entry(const ModelPOD<T> & m, const CoopTables & tb, const T * cb, const T * Jr, const T * Fd, const T * Yd, int r, int c,
-                        T & vq, T & vv, T & va)
+                        T & vq, T & vv, T & va, bool any_up = true, bool any_low = true)
 {
   const unsigned info = tb.colinfo[c];
   const int ivc = info & 0xff, own_end = (info >> 8) & 0xff, sub_end = info >> 16;
@@ -434,22 +437,43 @@ BRBD_DI void coop_entry(const ModelPOD<T> & m, const CoopTables & tb, const T * 
   const bool low = r >= own_end && r < sub_end;
   const T * P = cb + c * CB_STRIDE;
   T x[6], y[6];
-  ld6(P + (own ? CB_DFDQ : CB_DFDQP), x);
-  const T Aq = dot6a(Jr, x);
-  ld6(P + CB_DADQ, x); ld6(P + CB_DVDQ, y);
-  const T Bq = dot6a(Fd, x) + dot6a(Yd, y);
-  ld6(P + CB_DFDV, x);
-  const T Av = dot6a(Jr, x);
-  ld6(P + CB_DADV, x); ld6(P + CB_J, y);
-  const T Bv = dot6a(Fd, x) + dot6a(Yd, y);
+  T Aq = T(0), Av = T(0), Bq = T(0), Bv = T(0), Aa = T(0);
+  if (any_up)
+  {
+    ld6(P + (own ? CB_DFDQ : CB_DFDQP), x);
+    Aq = dot6a(Jr, x);
+    ld6(P + CB_DFDV, x);
+    Av = dot6a(Jr, x);
+    if (WITH_DA)
+    {
+      ld6(P + CB_DFDA, x);
+      Aa = dot6a(Jr, x);
+    }
+  }
+  if (any_low)
+  {
+    ld6(P + CB_DADQ, x); ld6(P + CB_DVDQ, y);
+    Bq = dot6a(Fd, x) + dot6a(Yd, y);
+    ld6(P + CB_DADV, x); ld6(P + CB_J, y);
+    Bv = dot6a(Fd, x) + dot6a(Yd, y);
+  }
   vq = up ? Aq : (low ? Bq : T(0));
   vv = up ? Av : (low ? Bv : T(0));
   if (WITH_DA)
   {
-    ld6(P + CB_DFDA, x);
-    va = up ? dot6a(Jr, x) : T(0);
+    va = up ? Aa : T(0);
     if (r == c) va += m.armature[c];
   }
+}
+// row-block flags of column c for rows [rb, rb + R)
+BRBD_DI void coop_block_flags(const CoopTables & tb, int c, int rb, int R, bool & any_up, bool & any_low)
+{
+  const unsigned info = tb.colinfo[c];
+  const int own_end = (info >> 8) & 0xff, sub_end = info >> 16;
+  const unsigned long long blk = (R >= 64 ? ~0ull : ((1ull << R) - 1ull)) << rb;
+  any_up = (tb.anc_mask[c] & blk) != 0ull;
+  const int lo = own_end > rb ? own_end : rb, hi = sub_end < rb + R ? sub_end : rb + R;
+  any_low = lo < hi;
 }
 
 template<class T, int G, bool WITH_DA>
@@ -526,14 +550,36 @@ rnea_derivatives_coop_kernel(const ModelPOD<T> * __restrict__ gm, const __grid_c
   T * sq = base + L.oq, * sv = base + L.ov, * sa = base + L.oa, * jr = base + L.ojr, * cb = base + L.ocb;
   const int nq = m.nq, nv = m.nv;
   const int64_t ntiles = (B + GPW - 1) / GPW;
-  for (int64_t tile = (int64_t)blockIdx.x * nw + warp; tile < ntiles; tile += (int64_t)gridDim.x * nw)
+  // the inputs of the next configuration are fetched into registers while the current one is evaluated (nq <= 2 G)
+  T rq[2], rv[2], ra[2];
+  auto fetch = [&](int64_t tile) {
+    int64_t c = tile * GPW + grp;
+    if (c >= B) c = B - 1;
+    const T * gq_in = q + c * ldq, * gv_in = v + c * ldv, * ga_in = a + c * lda;
+#pragma unroll
+    for (int t = 0; t < 2; ++t)
+    {
+      const int k = gl + t * G;
+      rq[t] = k < nq ? gq_in[k] : T(0);
+      rv[t] = k < nv ? gv_in[k] : T(0);
+      ra[t] = k < nv ? ga_in[k] : T(0);
+    }
+  };
+  const int64_t tile0 = (int64_t)blockIdx.x * nw + warp, tstep = (int64_t)gridDim.x * nw;
+  if (tile0 < ntiles) fetch(tile0);
+  for (int64_t tile = tile0; tile < ntiles; tile += tstep)
   {
     int64_t cfg = tile * GPW + grp;
     const bool active = cfg < B;
     if (!active) cfg = B - 1; // idle groups shadow the last configuration (stores suppressed)
-    const T * gq_in = q + cfg * ldq, * gv_in = v + cfg * ldv, * ga_in = a + cfg * lda;
-    for (int k = gl; k < nq; k += G) sq[k] = gq_in[k];
-    for (int k = gl; k < nv; k += G) { sv[k] = gv_in[k]; sa[k] = ga_in[k]; }
+#pragma unroll
+    for (int t = 0; t < 2; ++t)
+    {
+      const int k = gl + t * G;
+      if (k < nq) sq[k] = rq[t];
+      if (k < nv) { sv[k] = rv[t]; sa[k] = ra[t]; }
+    }
+    if (tile + tstep < ntiles) fetch(tile + tstep);
     BRBD_SYNCWARP();
     int oa_off = JR_OA;
     const int xoff = coop_forward<T, G, true>(m, tb, sq, sv, sa, jr, cb, gl, &oa_off);

@@ -50,7 +50,32 @@ int main()
     try { pb::rneaInParallel(1, pool, {q.data(), nq - 1, B, nq}, {v.data(), nv, B, nv}, {a.data(), nv, B, nv}, {tau.data(), nv, B, nv}); }
     catch (const std::invalid_argument &) { threw = true; }
     if (!threw) { std::printf("FAIL wrong-size argument did not throw std::invalid_argument\n"); return 1; }
-    std::printf("OK max|aba(rnea(a)) - a| = %.3e over %d configurations\n", err, B);
+    // the rest of the shim: nle + M a == tau (unittest/rnea.cpp:195-206), Minv M == 1 on the diagonal, integrate(q, 0) == q
+    std::vector<double> nle(nv * B), M(nv * nv * B), Minv(nv * nv * B), zero(nv * B, 0.0), q2(nq * B), qn(nq * B), vn(nv * B);
+    pb::nonLinearEffectsInParallel(1, pool, {q.data(), nq, B, nq}, {v.data(), nv, B, nv}, {nle.data(), nv, B, nv});
+    pb::crbaInParallel(1, pool, {q.data(), nq, B, nq}, {M.data(), nv * nv, B, nv * nv});
+    pb::computeMinverseInParallel(1, pool, {q.data(), nq, B, nq}, {Minv.data(), nv * nv, B, nv * nv});
+    pb::integrateInParallel(1, pool, {q.data(), nq, B, nq}, {zero.data(), nv, B, nv}, {q2.data(), nq, B, nq});
+    pb::abaEulerStepInParallel(1, pool, {q.data(), nq, B, nq}, {v.data(), nv, B, nv}, {tau.data(), nv, B, nv}, 1e-3, {qn.data(), nq, B, nq},
+                               {vn.data(), nv, B, nv});
+    double err2 = 0, err3 = 0, err4 = 0;
+    for (int b = 0; b < B; ++b)
+    {
+      const double * Mb = M.data() + (size_t)b * nv * nv, * Ib = Minv.data() + (size_t)b * nv * nv;
+      auto sym = [&](const double * A, int r, int c) { return r <= c ? A[c * nv + r] : A[r * nv + c]; }; // upper triangles
+      for (int r = 0; r < nv; ++r)
+      {
+        double t = nle[b * nv + r], d = 0;
+        for (int c = 0; c < nv; ++c) { t += sym(Mb, r, c) * a[b * nv + c]; d += sym(Ib, r, c) * sym(Mb, c, r); }
+        err2 = std::fmax(err2, std::fabs(t - tau[b * nv + r]));
+        err3 = std::fmax(err3, std::fabs(d - 1.0));
+      }
+      for (int k = 0; k < nv; ++k) err4 = std::fmax(err4, std::fabs(vn[b * nv + k] - (v[b * nv + k] + 1e-3 * a[b * nv + k])));
+    }
+    for (int k = 0; k < nq * B; ++k) err4 = std::fmax(err4, std::fabs(q2[k] - q[k]));
+    if (!(err2 < 1e-9 && err3 < 1e-9 && err4 < 1e-9)) { std::printf("FAIL nle/crba/Minv/integrate/euler identities: %.3e %.3e %.3e\n", err2, err3, err4); return 1; }
+    std::printf("OK max|aba(rnea(a)) - a| = %.3e over %d configurations; M a + nle - tau %.1e, diag(Minv M) - 1 %.1e, integrate/euler %.1e\n", err,
+                B, err2, err3, err4);
     return 0;
   }
   catch (const std::runtime_error & e)

@@ -177,6 +177,16 @@ def test_error_behaviour(ctx):
     # empty batch is a no-op
     out = pb.rneaInParallel(1, pool, q[:, :0], v[:, :0], a[:, :0])
     assert out.shape == (model.nv, 0)
+    # the other entry points check sizes the same way
+    with pytest.raises(ValueError):
+        pb.nonLinearEffectsInParallel(1, pool, q, v[:-1])
+    with pytest.raises(ValueError):
+        pb.computeMinverseInParallel(1, pool, q, Minv=np.zeros((model.nv * model.nv - 1, 4), order="F"))
+    with pytest.raises(ValueError):
+        pb.integrateInParallel(1, pool, q, v, qout=np.zeros((model.nq, 3), order="F"))
+    with pytest.raises(ValueError):
+        pb.abaEulerStepInParallel(1, pool, q, v[:, :2], a, 1e-3)
+    assert pb.computeGeneralizedGravityInParallel(1, pool, q[:, :0]).shape == (model.nv, 0)
 
 
 # ---- the callers' other needs on the same sweeps ---------------------------------------------------
