@@ -26,6 +26,7 @@
 #include "aba_derivatives.cuh"
 #include "aba_deriv_coop.cuh"
 #include "aba_dfs.cuh"
+#include "aba_rr.cuh"
 #include "crba.cuh"
 #include "crba_dfs.cuh"
 #include "engine.cuh"
@@ -385,7 +386,50 @@ brbd_status launch_aba(brbd_pool * p, DeviceCtx & d, const T * q, int64_t ldq, c
       return BRBD_OK;
     }
   }
-  // preferred: per-depth (Y, f, a_bias) in tensor memory, J of the root path + branch slots in shared memory
+  // preferred (v4): the backward sweep recomputes the per-depth quantities; (sin, cos, v) per depth and the branch slots in
+  // tensor memory, only the pass-3 record ring in shared memory -> up to 8 warps per SM
+  if (!std::getenv("BRBD_ABA_V3"))
+  {
+    const int wpv = (int)(sizeof(T) / 4);
+    AbaRRLayout L = aba_rr_layout<T>(t.maxdepth, t.nbranch, 4);
+    const int cols_per_slice = L.tvals * wpv;
+    const int max_warps_tmem = cols_per_slice <= 256 ? 8 : (cols_per_slice <= 512 ? 4 : 0);
+    if (max_warps_tmem > 0)
+    {
+      const size_t per_warp = (size_t)32 * L.nstate * sizeof(T);
+      int warps = (int)std::max<size_t>(1, std::min<size_t>((size_t)max_warps_tmem, (size_t)d.max_smem_optin / per_warp));
+      warps = pick_warps_by_rounds(d, B, warps);
+      if (const char * e = std::getenv("BRBD_ABA_WARPS")) warps = std::max(1, std::min(warps, std::atoi(e)));
+      const size_t dyn_bytes = (size_t)warps * per_warp;
+      const int64_t ctas_needed = (B + warps * 32 - 1) / (warps * 32);
+      const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(ctas_needed, (int64_t)d.sm_count));
+      L = aba_rr_layout<T>(t.maxdepth, t.nbranch, warps);
+      st = ensure_work(d, (size_t)grid * warps * 32 * (size_t)t.pslots * sizeof(T));
+      if (st != BRBD_OK) return st;
+#define BRBD_LAUNCH(NT)                                                                              \
+  {                                                                                                  \
+    st = set_smem(aba_rr_kernel<T, NT>, dyn_bytes);                                                  \
+    if (st != BRBD_OK) return st;                                                                    \
+    aba_rr_kernel<T, NT><<<grid, NT, dyn_bytes, d.s()>>>(t, L, q, ldq, v, ldv, tau, ldtau, a, lda, (T *)d.work, B); \
+  }
+      switch (warps)
+      {
+      case 1: BRBD_LAUNCH(32) break;
+      case 2: BRBD_LAUNCH(64) break;
+      case 3: BRBD_LAUNCH(96) break;
+      case 4: BRBD_LAUNCH(128) break;
+      case 5: BRBD_LAUNCH(160) break;
+      case 6: BRBD_LAUNCH(192) break;
+      case 7: BRBD_LAUNCH(224) break;
+      default: BRBD_LAUNCH(256) break;
+      }
+#undef BRBD_LAUNCH
+      p->launches += 1;
+      CUDA_TRY(cudaGetLastError());
+      return BRBD_OK;
+    }
+  }
+  // v3: per-depth (Y, f, a_bias) in tensor memory, J of the root path + branch slots in shared memory
   {
     AbaTmemLayout L = aba_tmem_layout<T>(t.maxpathdof, t.maxdepth, t.nbranch, 4);
     if (L.tvals * (int)(sizeof(T) / 4) <= 512)
