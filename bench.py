@@ -31,10 +31,10 @@ MODEL = "simple_humanoid_ff"
 BATCH = 65536
 L2_BYTES = 126 * 1024 * 1024
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures
-# (profiles/r1_v3_step_ncu_full.csv: crba_tmem_kernel<double,192> 37.9 MB read + 593.9 MB written, aba_tmem_kernel<double,128>
-# 367.3 MB read + 434.9 MB written — the ABA figure is 11x its 74 MB of algorithmic bytes: the pass-3 record store
-# does not stay L2-resident next to the 642 MB CRBA output); bytes per launch of 65536 configurations
-NCU_TRAFFIC = {"crba": 631.85e6, "aba": 802.21e6}
+# (profiles/r1_v6_step_ncu_full.csv: crba_tmem_kernel<double,224> 43.7 MB read + 597.4 MB written; aba_rr_kernel<double,224>
+# 385.4 MB read + 449.1 MB written — the ABA figure is 11x its 74 MB of algorithmic bytes: the per-thread pass-3 record
+# store, 186 MB for a resident wave, does not stay L2-resident); bytes per launch of 65536 configurations
+NCU_TRAFFIC = {"crba": 641.1e6, "aba": 834.5e6}
 
 
 def load_model(name):
@@ -309,7 +309,7 @@ def main():
     # `bound` is "hbm" | "tensor") describes; ABA is bound by the FP64 pipe (AI 24 flop/B, no tensor cores on this
     # path) and is reported against the measured DFMA peak under `fp64_roofline`.  `share_of_step` says how the
     # step's time splits, so the dominant kernel can be read off either way.
-    kname = {"aba": "aba_tmem_kernel<double>", "crba": "crba_tmem_kernel<double>"}
+    kname = {"aba": "aba_rr_kernel<double>", "crba": "crba_tmem_kernel<double>"}
     roofline = {"bound": "hbm", "kernel": kname["crba"], "achieved": kern["crba"]["achieved_GBs"], "peak": hbm_peak,
                 "unit": "GB/s", "frac": kern["crba"]["hbm_frac"], "traffic": NCU_TRAFFIC.get("crba"), "peak_source": peak_src,
                 "share_of_step": crba_ms / (aba_ms + crba_ms)}
