@@ -20,9 +20,15 @@
 namespace brbd
 {
 
+#ifndef BRBD_ABA_RR_RING
+#define BRBD_ABA_RR_RING 2
+#endif
+constexpr int ABA_RR_RING = BRBD_ABA_RR_RING; // pass-3 records in flight per thread (power of two)
 struct AbaRRLayout
 {
-  int oR, oG, oP, nstate; // shared memory: pass-3 record ring (20 x ABA_RING), oa_gf of open branching joints (6 each), prefetch (4)
+  int oR, oP, nstate;     // shared memory: pass-3 record ring (20 x ABA_RR_RING), prefetch (4).  Kept small on purpose: the kernel
+                          // runs at 255 registers with ~70 local-memory spill accesses per joint, and what shared memory
+                          // does not take is L1 for them (ring of 4 -> 2: 0.367 -> 0.294 ms)
   int tS, tB, tvals;      // TMEM values: per depth (s, c, v) (3), per branch slot oMi 12 | ov 6 | Ia acc 21 | f acc 6 (45)
   int tcols;
 };
@@ -31,8 +37,7 @@ template<class T> inline AbaRRLayout aba_rr_layout(int maxdepth, int nbranch, in
   AbaRRLayout L;
   const int nb = nbranch > 0 ? nbranch : 1;
   L.oR = 0;
-  L.oG = 20 * ABA_RING;
-  L.oP = L.oG + 6 * nb;
+  L.oP = 20 * ABA_RR_RING;
   L.nstate = L.oP + 4;
   L.tS = 0;
   L.tB = 3 * maxdepth;
@@ -394,7 +399,7 @@ aba_rr_kernel(const __grid_constant__ TreePOD<T> m, const AbaRRLayout L, const T
     {
       Motion<T> ag = mzero<T>();
 #pragma unroll
-      for (int d = 0; d < ABA_RING; ++d)
+      for (int d = 0; d < ABA_RR_RING; ++d)
       {
         const int i = 1 + d;
         if (i < nj && m.j[i].nvj == 1)
@@ -407,9 +412,9 @@ aba_rr_kernel(const __grid_constant__ TreePOD<T> m, const AbaRRLayout L, const T
       }
       for (int i = 1; i < nj; ++i)
       {
-        async_wait_group<ABA_RING - 1>();
+        async_wait_group<ABA_RR_RING - 1>();
         const JointRec r = m.j[i];
-        const int ro = L.oR + 20 * ((i - 1) & (ABA_RING - 1));
+        const int ro = L.oR + 20 * ((i - 1) & (ABA_RR_RING - 1));
         Motion<T> agp;
         if (r.parent == 0)
         {
@@ -417,7 +422,13 @@ aba_rr_kernel(const __grid_constant__ TreePOD<T> m, const AbaRRLayout L, const T
           agp.lin = Vec3<T>(-m.gravity[0], -m.gravity[1], -m.gravity[2]); // data.oa_gf[0] = -gravity (aba.hxx:260)
         }
         else if (r.parent != i - 1)
-          agp = get_motion<T>(st, L.oG + 6 * m.j[r.parent].bslot);
+        {
+          T g6[6];
+          tmem_wait_st();
+          tm.template load<6>(L.tB + ABA_BR * m.j[r.parent].bslot + 12, g6);
+          agp.lin = Vec3<T>(g6[0], g6[1], g6[2]);
+          agp.ang = Vec3<T>(g6[3], g6[4], g6[5]);
+        }
         else
           agp = ag;
         if (r.nvj == 1)
@@ -438,9 +449,13 @@ aba_rr_kernel(const __grid_constant__ TreePOD<T> m, const AbaRRLayout L, const T
           ag = aba_forward2_multidof<T, NT, 6>(r, P, agp, out);
         else
           ag = aba_forward2_multidof<T, NT, 3>(r, P, agp, out);
-        if (r.bslot >= 0) put_motion(st, L.oG + 6 * r.bslot, ag);
+        if (r.bslot >= 0)
+        { // oa_gf of an open branching joint: in its TMEM slot, where ov sat during passes 1 and 2
+          const T g6[6] = {ag.lin.x, ag.lin.y, ag.lin.z, ag.ang.x, ag.ang.y, ag.ang.z};
+          tm.template store<6>(L.tB + ABA_BR * r.bslot + 12, g6);
+        }
         {
-          const int in = i + ABA_RING; // refill the slot just consumed
+          const int in = i + ABA_RR_RING; // refill the slot just consumed
           if (in < nj && m.j[in].nvj == 1)
           {
             const int pn = m.j[in].poff;
