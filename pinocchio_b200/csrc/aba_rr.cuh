@@ -23,12 +23,12 @@ namespace brbd
 #ifndef BRBD_ABA_RR_RING
 #define BRBD_ABA_RR_RING 2
 #endif
-constexpr int ABA_RR_RING = BRBD_ABA_RR_RING; // pass-3 records in flight per thread (power of two)
+constexpr int ABA_RR_RING = BRBD_ABA_RR_RING; // pass-3 records in flight per thread
 struct AbaRRLayout
 {
   int oR, oP, nstate;     // shared memory: pass-3 record ring (20 x ABA_RR_RING), prefetch (4).  Kept small on purpose: the kernel
                           // runs at 255 registers with ~70 local-memory spill accesses per joint, and what shared memory
-                          // does not take is L1 for them (ring of 4 -> 2: 0.367 -> 0.294 ms)
+                          // does not take is L1 for them (ring of 4 -> 2: 0.367 -> 0.294 ms; 3: 0.304 ms)
   int tS, tB, tvals;      // TMEM values: per depth (s, c, v) (3), per branch slot oMi 12 | ov 6 | Ia acc 21 | f acc 6 (45)
   int tcols;
 };
@@ -398,6 +398,7 @@ aba_rr_kernel(const __grid_constant__ TreePOD<T> m, const AbaRRLayout L, const T
     // ---- pass 3 (aba.hxx:206-226), as aba_tmem_kernel: records stream back through a per-thread cp.async ring ----------
     {
       Motion<T> ag = mzero<T>();
+      int rslot = 0;
 #pragma unroll
       for (int d = 0; d < ABA_RR_RING; ++d)
       {
@@ -414,7 +415,8 @@ aba_rr_kernel(const __grid_constant__ TreePOD<T> m, const AbaRRLayout L, const T
       {
         async_wait_group<ABA_RR_RING - 1>();
         const JointRec r = m.j[i];
-        const int ro = L.oR + 20 * ((i - 1) & (ABA_RR_RING - 1));
+        const int ro = L.oR + 20 * rslot;
+        rslot = rslot + 1 == ABA_RR_RING ? 0 : rslot + 1;
         Motion<T> agp;
         if (r.parent == 0)
         {
