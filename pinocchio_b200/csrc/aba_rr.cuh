@@ -24,9 +24,11 @@ namespace brbd
 #define BRBD_ABA_RR_RING 2
 #endif
 constexpr int ABA_RR_RING = BRBD_ABA_RR_RING; // pass-3 records in flight per thread
+static_assert(20 * ABA_RR_RING >= 27, "the hand-over slots alias the record ring");
 struct AbaRRLayout
 {
-  int oR, oP, nstate;     // shared memory: pass-3 record ring (20 x ABA_RR_RING), prefetch (4).  Kept small on purpose: the kernel
+  int oR, oP, oA, nstate; // oA: hand-over of an only child's (oYaba 21 | of 6) to its parent's step, aliases the ring (idle in passes 1-2)
+                          // shared memory: pass-3 record ring (20 x ABA_RR_RING), prefetch (4).  Kept small on purpose: the kernel
                           // runs at 255 registers with ~70 local-memory spill accesses per joint, and what shared memory
                           // does not take is L1 for them (ring of 4 -> 2: 0.367 -> 0.294 ms; 3: 0.304 ms)
   int tS, tB, tvals;      // TMEM values: per depth (s, c, v) (3), per branch slot oMi 12 | ov 6 | Ia acc 21 | f acc 6 (45)
@@ -38,6 +40,7 @@ template<class T> inline AbaRRLayout aba_rr_layout(int maxdepth, int nbranch, in
   const int nb = nbranch > 0 ? nbranch : 1;
   L.oR = 0;
   L.oP = 20 * ABA_RR_RING;
+  L.oA = L.oR;
   L.nstate = L.oP + 4;
   L.tS = 0;
   L.tB = 3 * maxdepth;
@@ -55,18 +58,21 @@ template<class T> BRBD_DI Mat3<T> mul_bt(const Mat3<T> & A, const Mat3<T> & B) /
   return r;
 }
 
-// multi-dof backward step with the J columns rebuilt from oMi (see aba_backward_multidof in aba_dfs.cuh)
+// multi-dof backward step with the J columns rebuilt from oMi (see aba_backward_multidof in aba_dfs.cuh).  Out of line: it runs
+// once or twice per configuration and would otherwise dominate the register budget of the 1-dof path.  (oYaba, of) come in and
+// the contribution to the parent goes out through the 27 hand-over slots st[oA ..]: by-value structs travel through the stack.
 template<class T, int NT, int NVJ>
-__device__ __noinline__ AbaContribution<T> aba_rr_backward_multidof(const TreePOD<T> & m, const JointRec r, const SE3<T> X, const PStore<T, NT> P,
-                                                                    const T * __restrict__ tc, const bool live, const AbaContribution<T> in,
-                                                                    const Motion<T> abm)
+__device__ __noinline__ void aba_rr_backward_multidof(const TreePOD<T> & m, const JointRec r, const SE3<T> X, const Slots<T, NT> st, const int oA,
+                                                      const PStore<T, NT> P, const T * __restrict__ tc, const bool live, const Motion<T> abm)
 {
-  AbaContribution<T> io = in;
-  T (&A)[21] = io.A;
-  T (&fa)[6] = io.fa;
+  T A[21], fa[6];
+#pragma unroll
+  for (int k = 0; k < 21; ++k) A[k] = st[oA + k];
+#pragma unroll
+  for (int k = 0; k < 6; ++k) fa[k] = st[oA + 21 + k];
   Force<T> fi;
-  fi.lin = Vec3<T>(in.fa[0], in.fa[1], in.fa[2]);
-  fi.ang = Vec3<T>(in.fa[3], in.fa[4], in.fa[5]);
+  fi.lin = Vec3<T>(fa[0], fa[1], fa[2]);
+  fi.ang = Vec3<T>(fa[3], fa[4], fa[5]);
   const int po = r.poff, iv = r.idx_v;
   T Jm[NVJ][6], U[6][NVJ], StU[NVJ][NVJ], Di[NVJ][NVJ], UD[6][NVJ], uj[NVJ];
 #pragma unroll
@@ -142,8 +148,11 @@ __device__ __noinline__ AbaContribution<T> aba_rr_backward_multidof(const TreePO
       for (int k = 1; k < NVJ; ++k) acc += UD[rr][k] * uj[k];
       fa[rr] += Iab[rr] + acc;
     }
+#pragma unroll
+    for (int k = 0; k < 21; ++k) st[oA + k] = A[k];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) st[oA + 21 + k] = fa[k];
   }
-  return io;
 }
 
 template<class T, int NT>
@@ -174,12 +183,8 @@ aba_rr_kernel(const __grid_constant__ TreePOD<T> m, const AbaRRLayout L, const T
     T * __restrict__ out = live ? ddq + cfg * ldddq : nullptr;
     SE3<T> X;
     Motion<T> ov = mzero<T>();
-    // (oYaba, of) of the joint in its backward step; what the step leaves in (A, fA) is the contribution to the parent,
-    // which an only child hands over in these very registers
-    T A[21];
-    Force<T> fA = fzero<T>();
-#pragma unroll
-    for (int k = 0; k < 21; ++k) A[k] = T(0);
+    // (oYaba, of) of a joint only live in registers inside its backward step; what the step leaves for the parent goes through
+    // the branching joint's TMEM accumulator or, for an only child, through 27 shared-memory slots
     async_fetch(&st[L.oP], qc + m.j[1].idx_q);
     async_fetch(&st[L.oP + 1], vc + m.j[1].idx_v);
     for (int i = 1; i < nj; ++i)
@@ -247,6 +252,7 @@ aba_rr_kernel(const __grid_constant__ TreePOD<T> m, const AbaRRLayout L, const T
         const T tau0 = st[L.oP + 2 + tslot];
         tslot ^= 1;
         if (r.parent != stop) async_fetch(&st[L.oP + 2 + tslot], tc + m.j[r.parent].idx_v);
+        T A[21];
         T sj = si, cj = ci, vj = vi;
         if (j != i)
         {
@@ -272,25 +278,32 @@ aba_rr_kernel(const __grid_constant__ TreePOD<T> m, const AbaRRLayout L, const T
             ovp = ov - X.act(tree_joint_velocity(r.type, vc + iv));
           abm = mcross(ovp, ov);
         }
-        if (j == i) inertia_to_sym6(Y, A);
-        else
+        inertia_to_sym6(Y, A);
+        if (j != i)
         {
-          T own[21];
-          inertia_to_sym6(Y, own);
           if (r.bslot >= 0)
-          {
-            T acc[27];
-            tm.template load<27>(L.tB + ABA_BR * r.bslot + 18, acc);
+          { // the children's contributions sit in the accumulator; added in chunks (register pressure)
+            const int b = L.tB + ABA_BR * r.bslot + 18;
 #pragma unroll
-            for (int k = 0; k < 21; ++k) A[k] = own[k] + acc[k];
-            fi.lin += Vec3<T>(acc[21], acc[22], acc[23]);
-            fi.ang += Vec3<T>(acc[24], acc[25], acc[26]);
+            for (int ch = 0; ch < 3; ++ch)
+            {
+              T acc[9];
+              tm.template load<9>(b + 9 * ch, acc);
+#pragma unroll
+              for (int k = 0; k < 9; ++k)
+                if (9 * ch + k < 21) A[9 * ch + k] += acc[k];
+              if (ch == 2)
+              {
+                fi.lin += Vec3<T>(acc[3], acc[4], acc[5]);
+                fi.ang += Vec3<T>(acc[6], acc[7], acc[8]);
+              }
+            }
           }
           else
-          { // only child: its contribution is what the previous step left in (A, fA)
+          { // only child: its contribution is what the previous step left in the hand-over slots
 #pragma unroll
-            for (int k = 0; k < 21; ++k) A[k] += own[k];
-            fi += fA;
+            for (int k = 0; k < 21; ++k) A[k] += st[L.oA + k];
+            fi += get_force<T>(st, L.oA + 21);
           }
         }
         T fa[6];
@@ -333,16 +346,18 @@ aba_rr_kernel(const __grid_constant__ TreePOD<T> m, const AbaRRLayout L, const T
         }
         else
         {
-          AbaContribution<T> io;
 #pragma unroll
-          for (int k = 0; k < 21; ++k) io.A[k] = A[k];
-          f2a(fi, io.fa);
-          if (nvj == 6) io = aba_rr_backward_multidof<T, NT, 6>(m, r, X, P, tc, live, io, abm);
-          else io = aba_rr_backward_multidof<T, NT, 3>(m, r, X, P, tc, live, io, abm);
+          for (int k = 0; k < 21; ++k) st[L.oA + k] = A[k];
+          put_force(st, L.oA + 21, fi);
+          if (nvj == 6) aba_rr_backward_multidof<T, NT, 6>(m, r, X, st, L.oA, P, tc, live, abm);
+          else aba_rr_backward_multidof<T, NT, 3>(m, r, X, st, L.oA, P, tc, live, abm);
+          if (r.parent > 0)
+          {
 #pragma unroll
-          for (int k = 0; k < 21; ++k) A[k] = io.A[k];
+            for (int k = 0; k < 21; ++k) A[k] = st[L.oA + k];
 #pragma unroll
-          for (int k = 0; k < 6; ++k) fa[k] = io.fa[k];
+            for (int k = 0; k < 6; ++k) fa[k] = st[L.oA + 21 + k];
+          }
         }
         if (r.parent > 0)
         {
@@ -350,29 +365,35 @@ aba_rr_kernel(const __grid_constant__ TreePOD<T> m, const AbaRRLayout L, const T
           if (rp.bslot >= 0)
           {
             const int b = L.tB + ABA_BR * rp.bslot + 18;
-            T acc[27];
             if (j == r.parent + 1)
             { // first child opens the accumulator
-#pragma unroll
-              for (int k = 0; k < 21; ++k) acc[k] = A[k];
-#pragma unroll
-              for (int k = 0; k < 6; ++k) acc[21 + k] = fa[k];
+              tm.template store<21>(b, A);
+              tm.template store<6>(b + 21, fa);
             }
             else
             {
               tmem_wait_st();
-              tm.template load<27>(b, acc);
 #pragma unroll
-              for (int k = 0; k < 21; ++k) acc[k] += A[k];
+              for (int ch = 0; ch < 3; ++ch)
+              {
+                T acc[9];
+                tm.template load<9>(b + 9 * ch, acc);
 #pragma unroll
-              for (int k = 0; k < 6; ++k) acc[21 + k] += fa[k];
+                for (int k = 0; k < 9; ++k)
+                {
+                  const int e = 9 * ch + k;
+                  acc[k] += e < 21 ? A[e] : fa[e - 21];
+                }
+                tm.template store<9>(b + 9 * ch, acc);
+              }
             }
-            tm.template store<27>(b, acc);
           }
           else
           {
-            fA.lin = Vec3<T>(fa[0], fa[1], fa[2]);
-            fA.ang = Vec3<T>(fa[3], fa[4], fa[5]);
+#pragma unroll
+            for (int k = 0; k < 21; ++k) st[L.oA + k] = A[k];
+#pragma unroll
+            for (int k = 0; k < 6; ++k) st[L.oA + 21 + k] = fa[k];
           }
           if (r.parent != stop)
           { // the unwind goes on with the parent: oMi_parent = oMi_j liMi_j^-1, ov_parent = ov_j - J_j v_j
