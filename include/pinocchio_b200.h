@@ -46,6 +46,8 @@ typedef enum brbd_joint_type {
   BRBD_JOINT_FREEFLYER = 6,                                  /* joint-free-flyer.hpp (nq 7, nv 6) */
   BRBD_JOINT_SPHERICAL = 7,                                  /* joint-spherical.hpp  (nq 4, nv 3) */
   BRBD_JOINT_PLANAR = 8,                                     /* joint-planar.hpp     (nq 4, nv 3) */
+  BRBD_JOINT_REVOLUTE_UNALIGNED = 9,                         /* joint-revolute-unaligned.hpp: axis in brbd_flat_model::axis */
+  BRBD_JOINT_PRISMATIC_UNALIGNED = 10,                       /* joint-prismatic-unaligned.hpp */
   BRBD_JOINT_UNIVERSE = -1                                   /* slot 0 only */
 } brbd_joint_type;
 
@@ -66,6 +68,8 @@ typedef struct brbd_flat_model {
                                  (xx,xy,yy,xz,yz,zz) — spatial/symmetric3.hpp:46-51      */
   const double * armature;    /* [nv]                                                     */
   double gravity[3];          /* linear part of model.gravity (default 0,0,-9.81)         */
+  const double * axis;        /* [njoints*3] unit axis of the *_UNALIGNED joints, joint frame (other
+                                 entries ignored); may be NULL when the model has none   */
 } brbd_flat_model;
 
 typedef struct brbd_model brbd_model; /* validated host copy + derived topology tables */

@@ -22,6 +22,7 @@ class _FlatModel(ctypes.Structure):
         ("idx_q", ctypes.POINTER(ctypes.c_int32)), ("idx_v", ctypes.POINTER(ctypes.c_int32)),
         ("placement", ctypes.POINTER(ctypes.c_double)), ("inertia", ctypes.POINTER(ctypes.c_double)),
         ("armature", ctypes.POINTER(ctypes.c_double)), ("gravity", ctypes.c_double * 3),
+        ("axis", ctypes.POINTER(ctypes.c_double)),
     ]
 
 
@@ -76,6 +77,12 @@ class Oracle:
         dp = lambda k: f[k].ctypes.data_as(ctypes.POINTER(ctypes.c_double))
         fm.parents, fm.joint_type, fm.idx_q, fm.idx_v = ip("parents"), ip("joint_type"), ip("idx_q"), ip("idx_v")
         fm.placement, fm.inertia, fm.armature = dp("placement"), dp("inertia"), dp("armature")
+        if "axis" not in f:
+            f = dict(f)
+            f["axis"] = np.zeros(3 * self.njoints)
+            self._keep = f
+        f["axis"] = np.ascontiguousarray(f["axis"], dtype=np.float64)
+        fm.axis = dp("axis")
         for k in range(3):
             fm.gravity[k] = float(f["gravity"][k])
         self._h = ctypes.c_void_p(_lib().oracle_model_create(ctypes.byref(fm)))

@@ -445,8 +445,9 @@ template<class S> inline Force<S> mul6(const Mat6<S> & A, const Motion<S> & v)
 // ---------------------------------------------------------------------------------------------
 // Model (constants in Scalar) and Data (workspaces): multibody/model.hpp:97-205, data.hxx:30-315
 // ---------------------------------------------------------------------------------------------
-inline int joint_nq(int t) { return t <= BRBD_JOINT_PZ ? 1 : (t == BRBD_JOINT_FREEFLYER ? 7 : 4); }
-inline int joint_nv(int t) { return t <= BRBD_JOINT_PZ ? 1 : (t == BRBD_JOINT_FREEFLYER ? 6 : 3); }
+inline bool joint_unaligned(int t) { return t == BRBD_JOINT_REVOLUTE_UNALIGNED || t == BRBD_JOINT_PRISMATIC_UNALIGNED; }
+inline int joint_nq(int t) { return (t <= BRBD_JOINT_PZ || joint_unaligned(t)) ? 1 : (t == BRBD_JOINT_FREEFLYER ? 7 : 4); }
+inline int joint_nv(int t) { return (t <= BRBD_JOINT_PZ || joint_unaligned(t)) ? 1 : (t == BRBD_JOINT_FREEFLYER ? 6 : 3); }
 
 template<class S> struct Model
 {
@@ -455,6 +456,7 @@ template<class S> struct Model
   std::vector<SE3<S>> jointPlacements;
   std::vector<Inertia<S>> inertias;
   std::vector<S> armature;
+  std::vector<V3<S>> axis; // unit axis of the unaligned joints (joint-revolute-unaligned.hpp, joint-prismatic-unaligned.hpp)
   Motion<S> gravity; // model.gravity, linear = (0,0,-9.81) by default (model.hxx:40)
 
   explicit Model(const brbd_flat_model & f)
@@ -467,9 +469,11 @@ template<class S> struct Model
     nvs.resize(njoints);
     jointPlacements.resize(njoints);
     inertias.resize(njoints);
+    axis.resize(njoints);
     for (int i = 0; i < njoints; ++i)
     {
       nvs[i] = (i == 0) ? 0 : joint_nv(type[i]);
+      if (f.axis) axis[i] = V3<S>(S(f.axis[3 * i]), S(f.axis[3 * i + 1]), S(f.axis[3 * i + 2]));
       const double * P = f.placement + 12 * i;
       for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) jointPlacements[i].R(r, c) = S(P[3 * r + c]);
       for (int k = 0; k < 3; ++k) jointPlacements[i].p[k] = S(P[9 + k]);
@@ -606,6 +610,34 @@ inline void jointCalc(const Model<S> & model, int i, const S * q, const S * vq, 
     jd.M.p[axis] = qj[0];
     jd.Sm[LINEAR + axis][0] = S(1);
     if (vj) jd.v.lin[axis] = vj[0];
+  }
+  else if (t == BRBD_JOINT_REVOLUTE_UNALIGNED)
+  {
+    // JointModelRevoluteUnalignedTpl::calc, joint-revolute-unaligned.hpp:668-672: toRotationMatrix(axis, cos, sin) of
+    // math/rotation.hpp:26-55 (Eigen's AngleAxis formula); S = (0, axis), v = axis qdot (:84-103)
+    const V3<S> & ax = model.axis[i];
+    S sa, ca;
+    sincos_s(qj[0], sa, ca);
+    const V3<S> sin_axis = sa * ax, cos1_axis = (S(1) - ca) * ax;
+    jd.M = SE3<S>::Identity();
+    S tmp = cos1_axis[0] * ax[1];
+    jd.M.R(0, 1) = tmp - sin_axis[2]; jd.M.R(1, 0) = tmp + sin_axis[2];
+    tmp = cos1_axis[0] * ax[2];
+    jd.M.R(0, 2) = tmp + sin_axis[1]; jd.M.R(2, 0) = tmp - sin_axis[1];
+    tmp = cos1_axis[1] * ax[2];
+    jd.M.R(1, 2) = tmp - sin_axis[0]; jd.M.R(2, 1) = tmp + sin_axis[0];
+    for (int k = 0; k < 3; ++k) jd.M.R(k, k) = cos1_axis[k] * ax[k] + ca;
+    for (int k = 0; k < 3; ++k) jd.Sm[ANGULAR + k][0] = ax[k];
+    if (vj) jd.v.ang = vj[0] * ax;
+  }
+  else if (t == BRBD_JOINT_PRISMATIC_UNALIGNED)
+  {
+    // JointModelPrismaticUnalignedTpl::calc, joint-prismatic-unaligned.hpp: translation = axis q; S = (axis, 0)
+    const V3<S> & ax = model.axis[i];
+    jd.M = SE3<S>::Identity();
+    jd.M.p = qj[0] * ax;
+    for (int k = 0; k < 3; ++k) jd.Sm[LINEAR + k][0] = ax[k];
+    if (vj) jd.v.lin = vj[0] * ax;
   }
   else
   if (t == BRBD_JOINT_FREEFLYER)
@@ -1336,7 +1368,7 @@ template<class S> void integrate(const Model<S> & model, const S * q, const S * 
     const S * vj = v + model.idx_v[i];
     S * o = qout + model.idx_q[i];
     const int t = model.type[i];
-    if (t <= BRBD_JOINT_PZ)
+    if (t <= BRBD_JOINT_PZ || joint_unaligned(t))
       o[0] = qj[0] + vj[0]; // VectorSpaceOperation::integrate_impl, liegroup/vector-space.hpp:142-150
     else if (t == BRBD_JOINT_FREEFLYER)
     {

@@ -5,8 +5,8 @@ RNEA / ABA / CRBA / computeRNEADerivatives / computeABADerivatives over batches 
 configurations.  The compute path is hand-written sm_100a CUDA behind a C ABI
 (include/pinocchio_b200.h); this package is the host-side mirror of the reference interface.
 """
-from .model import (JOINT_FREEFLYER, JOINT_PLANAR, JOINT_PX, JOINT_PY, JOINT_PZ, JOINT_RX, JOINT_RY, JOINT_RZ,  # noqa: F401
-                    JOINT_SPHERICAL, SE3, Inertia, Model, buildModelFromUrdf, buildSampleModelHumanoid,
+from .model import (JOINT_FREEFLYER, JOINT_PLANAR, JOINT_PRISMATIC_UNALIGNED, JOINT_PX, JOINT_PY, JOINT_PZ,  # noqa: F401
+                    JOINT_REVOLUTE_UNALIGNED, JOINT_RX, JOINT_RY, JOINT_RZ, JOINT_SPHERICAL, SE3, Inertia, Model, buildModelFromUrdf, buildSampleModelHumanoid,
                     buildSampleModelHumanoidRandom, buildSampleModelManipulator)
 from .joint_configuration import (LibcRand, batched_random_configuration, batched_random_tangent, integrate,  # noqa: F401
                                   neutral, randomConfiguration)

@@ -37,6 +37,7 @@ class FlatModel(ctypes.Structure):
         ("idx_q", ctypes.POINTER(ctypes.c_int32)), ("idx_v", ctypes.POINTER(ctypes.c_int32)),
         ("placement", ctypes.POINTER(ctypes.c_double)), ("inertia", ctypes.POINTER(ctypes.c_double)),
         ("armature", ctypes.POINTER(ctypes.c_double)), ("gravity", ctypes.c_double * 3),
+        ("axis", ctypes.POINTER(ctypes.c_double)),
     ]
 
 
@@ -108,6 +109,7 @@ def make_flat(flat: dict):
         keep[k] = keep[k].astype(np.int32)
     for k in ("placement", "inertia", "armature"):
         keep[k] = keep[k].astype(np.float64)
+    keep["axis"] = np.ascontiguousarray(flat["axis"], dtype=np.float64) if "axis" in flat else np.zeros(3 * int(flat["njoints"]))
     if keep["armature"].size == 0:
         keep["armature"] = np.zeros(1)
     fm = FlatModel()
@@ -115,7 +117,7 @@ def make_flat(flat: dict):
     ip = lambda k: keep[k].ctypes.data_as(ctypes.POINTER(ctypes.c_int32))
     dp = lambda k: keep[k].ctypes.data_as(ctypes.POINTER(ctypes.c_double))
     fm.parents, fm.joint_type, fm.idx_q, fm.idx_v = ip("parents"), ip("joint_type"), ip("idx_q"), ip("idx_v")
-    fm.placement, fm.inertia, fm.armature = dp("placement"), dp("inertia"), dp("armature")
+    fm.placement, fm.inertia, fm.armature, fm.axis = dp("placement"), dp("inertia"), dp("armature"), dp("axis")
     for k in range(3):
         fm.gravity[k] = float(flat["gravity"][k])
     return fm, keep

@@ -24,7 +24,7 @@ from typing import Optional
 
 import numpy as np
 
-from .model import (JOINT_FREEFLYER, JOINT_PLANAR, JOINT_PZ, JOINT_SPHERICAL, Model)
+from .model import (JOINT_FREEFLYER, JOINT_PLANAR, JOINT_PZ, JOINT_REVOLUTE_UNALIGNED, JOINT_SPHERICAL, Model)
 
 RAND_MAX = 2147483647
 
@@ -71,7 +71,7 @@ def randomConfiguration(model: Model, lo=None, hi=None, rng: Optional[LibcRand] 
 
     for j in range(1, model.njoints):
         t, iq = model.joint_types[j], model.idx_qs[j]
-        if t <= JOINT_PZ:
+        if t <= JOINT_PZ or t >= JOINT_REVOLUTE_UNALIGNED:
             vec(iq, 1)
         elif t == JOINT_FREEFLYER:
             vec(iq, 3)
@@ -96,7 +96,7 @@ def batched_random_configuration(model: Model, batch: int, seed: int, lo: float 
     q = np.empty((batch, model.nq), dtype=np.float64)
     for j in range(1, model.njoints):
         t, iq = model.joint_types[j], model.idx_qs[j]
-        if t <= JOINT_PZ:
+        if t <= JOINT_PZ or t >= JOINT_REVOLUTE_UNALIGNED:
             q[:, iq] = g.uniform(lo, hi, batch)
         elif t == JOINT_FREEFLYER:
             q[:, iq:iq + 3] = g.uniform(lo, hi, (batch, 3))
@@ -192,7 +192,7 @@ def integrate(model: Model, q: np.ndarray, v: np.ndarray) -> np.ndarray:
     out = np.array(q, dtype=np.float64, copy=True)
     for j in range(1, model.njoints):
         t, iq, iv = model.joint_types[j], model.idx_qs[j], model.idx_vs[j]
-        if t <= JOINT_PZ:
+        if t <= JOINT_PZ or t >= JOINT_REVOLUTE_UNALIGNED:
             out[iq] = q[iq] + v[iv]
         elif t == JOINT_FREEFLYER:  # special-euclidean.hpp:660-698
             quat = q[iq + 3:iq + 7]

@@ -28,6 +28,7 @@ import numpy as np
 JOINT_RX, JOINT_RY, JOINT_RZ = 0, 1, 2
 JOINT_PX, JOINT_PY, JOINT_PZ = 3, 4, 5
 JOINT_FREEFLYER, JOINT_SPHERICAL, JOINT_PLANAR = 6, 7, 8
+JOINT_REVOLUTE_UNALIGNED, JOINT_PRISMATIC_UNALIGNED = 9, 10  # axis given per joint (joint-{revolute,prismatic}-unaligned.hpp)
 JOINT_UNIVERSE = -1
 
 _JOINT_NAMES = {
@@ -35,15 +36,16 @@ _JOINT_NAMES = {
     JOINT_PX: "JointModelPX", JOINT_PY: "JointModelPY", JOINT_PZ: "JointModelPZ",
     JOINT_FREEFLYER: "JointModelFreeFlyer", JOINT_SPHERICAL: "JointModelSpherical",
     JOINT_PLANAR: "JointModelPlanar", JOINT_UNIVERSE: "universe",
+    JOINT_REVOLUTE_UNALIGNED: "JointModelRevoluteUnaligned", JOINT_PRISMATIC_UNALIGNED: "JointModelPrismaticUnaligned",
 }
 
 
 def joint_nq(t: int) -> int:
-    return 1 if 0 <= t <= JOINT_PZ else (7 if t == JOINT_FREEFLYER else 4)
+    return 1 if (0 <= t <= JOINT_PZ or t >= JOINT_REVOLUTE_UNALIGNED) else (7 if t == JOINT_FREEFLYER else 4)
 
 
 def joint_nv(t: int) -> int:
-    return 1 if 0 <= t <= JOINT_PZ else (6 if t == JOINT_FREEFLYER else 3)
+    return 1 if (0 <= t <= JOINT_PZ or t >= JOINT_REVOLUTE_UNALIGNED) else (6 if t == JOINT_FREEFLYER else 3)
 
 
 # --------------------------------------------------------------------------------------------
@@ -213,6 +215,7 @@ class Model:
         self.nqs: List[int] = [0]
         self.nvs: List[int] = [0]
         self.jointPlacements: List[SE3] = [SE3.Identity()]
+        self.axes: List[np.ndarray] = [np.zeros(3)]  # unit axis of the unaligned joints, zeros elsewhere
         self.inertias: List[Inertia] = [Inertia.Zero()]
         self.armature = np.zeros(0)
         self.lowerPositionLimit = np.zeros(0)
@@ -222,7 +225,7 @@ class Model:
 
     # -- model.hxx:61-170 ---------------------------------------------------------------
     def addJoint(self, parent: int, joint_type: int, placement: SE3, name: str,
-                 min_config=None, max_config=None) -> int:
+                 min_config=None, max_config=None, axis=None) -> int:
         if not (0 <= parent < self.njoints):
             raise ValueError("The index of the parent joint is not valid.")
         if joint_type not in _JOINT_NAMES or joint_type == JOINT_UNIVERSE:
@@ -238,6 +241,13 @@ class Model:
         self.nqs.append(nqj)
         self.nvs.append(nvj)
         self.jointPlacements.append(placement.copy())
+        if joint_type >= JOINT_REVOLUTE_UNALIGNED:
+            ax = np.asarray(axis, dtype=np.float64)
+            if ax.shape != (3,) or not np.linalg.norm(ax) > 0:
+                raise ValueError("an unaligned joint needs a non-zero axis")
+            self.axes.append(ax / np.linalg.norm(ax))  # the reference normalises too (joint-revolute-unaligned.hpp:611-615)
+        else:
+            self.axes.append(np.zeros(3))
         self.inertias.append(Inertia.Zero())
         self.nq += nqj
         self.nv += nvj
@@ -341,6 +351,7 @@ class Model:
             "inertia": np.ascontiguousarray(inertia),
             "armature": np.ascontiguousarray(self.armature, dtype=np.float64),
             "gravity": np.array(self.gravity, dtype=np.float64),
+            "axis": np.ascontiguousarray(np.array(self.axes, dtype=np.float64).reshape(-1)),
         }
 
     # -- (de)serialisation of the flattened model: fixtures that travel to the GPU box ---------
@@ -356,6 +367,7 @@ class Model:
         d["inertia"] = [[repr(float(x)) for x in row] for row in f["inertia"]]
         d["armature"] = [repr(float(x)) for x in f["armature"]]
         d["gravity"] = [repr(float(x)) for x in f["gravity"]]
+        d["axis"] = [repr(float(x)) for x in f["axis"]]
         return json.dumps(d, indent=1)
 
     @staticmethod
@@ -368,11 +380,12 @@ class Model:
         inertia = np.array([[float(x) for x in row] for row in d["inertia"]])
         lo = np.array([float(x) for x in d["lowerPositionLimit"]])
         hi = np.array([float(x) for x in d["upperPositionLimit"]])
+        axes = np.array([float(x) for x in d["axis"]]).reshape(-1, 3) if "axis" in d else np.zeros((n, 3))
         for i in range(1, n):
             t = d["joint_type"][i]
             iq = d["idx_q"][i]
             jid = m.addJoint(d["parents"][i], t, SE3(placement[i, :9].reshape(3, 3), placement[i, 9:]),
-                             d["names"][i], lo[iq:iq + joint_nq(t)], hi[iq:iq + joint_nq(t)])
+                             d["names"][i], lo[iq:iq + joint_nq(t)], hi[iq:iq + joint_nq(t)], axis=axes[i])
             m.inertias[jid] = Inertia(inertia[i, 0], inertia[i, 1:4], inertia[i, 4:])
         m.inertias[0] = Inertia(inertia[0, 0], inertia[0, 1:4], inertia[0, 4:])
         m.armature = np.array([float(x) for x in d["armature"]])
@@ -591,7 +604,8 @@ def buildModelFromUrdf(path_or_xml: str, root_joint: Optional[int] = None,
     Child links are visited in urdfdom's order (children attached while iterating the
     name-sorted joint map) and depth-first (src/parsers/urdf/model.cpp:67-294); fixed joints
     merge their body into the parent joint; axis-aligned revolute / continuous / prismatic axes
-    map to RX/RY/RZ / PX/PY/PZ; anything else raises (unaligned joints are "next").
+    map to RX/RY/RZ / PX/PY/PZ, any other axis to RevoluteUnaligned / PrismaticUnaligned (which the engine re-frames
+    into RZ / PZ at brbd_model_create, model_build.hpp).
     ``continuous`` joints would be RUB* (nq=2) in the reference and are rejected here.
     """
     text = path_or_xml
@@ -645,12 +659,14 @@ def buildModelFromUrdf(path_or_xml: str, root_joint: Optional[int] = None,
                 body_frame[child] = model.addBodyFrame(child, frame.parentJoint, M, fid)
             elif jtype in ("revolute", "prismatic"):
                 k = _axis_tag(axis)
-                if k is None:
-                    raise ValueError(f"joint {jname}: unaligned axis {axis} is not supported")
-                tag = (JOINT_RX if jtype == "revolute" else JOINT_PX) + k
+                if k is None:  # CartesianAxis AXIS_UNALIGNED: Joint*Unaligned(axis.normalized()) — parsers/urdf/model.hxx:437-480
+                    tag = JOINT_REVOLUTE_UNALIGNED if jtype == "revolute" else JOINT_PRISMATIC_UNALIGNED
+                else:
+                    tag = (JOINT_RX if jtype == "revolute" else JOINT_PX) + k
                 lo = [float(lim.get("lower", "0"))] if lim is not None else None
                 hi = [float(lim.get("upper", "0"))] if lim is not None else None
-                jid = model.addJoint(frame.parentJoint, tag, frame.placement * placement, jname, lo, hi)
+                jid = model.addJoint(frame.parentJoint, tag, frame.placement * placement, jname, lo, hi,
+                                     axis=axis if k is None else None)
                 jf = model.addJointFrame(jid, parent_fid)
                 body_frame[child] = _urdf_append_body(model, jf, Y, SE3.Identity(), child)
             elif jtype in ("floating", "planar"):

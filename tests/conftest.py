@@ -60,6 +60,26 @@ def make_extra_models():
     m2.appendBodyToJoint(t, rng.inertia())
     m2.armature = np.abs(rng.sym(m2.nv)) * 0.05
     out["double_ff"] = m2
+    # joints about arbitrary axes (JointModelRevoluteUnaligned / PrismaticUnaligned): a chain with a branch, children
+    # of every kind below an unaligned joint, axes including -z (the half-turn case of the re-framing) and +z
+    m3 = M.Model()
+    m3.name = "unaligned"
+
+    def addu(jt, parent, name, axis=None):
+        nqj = M.joint_nq(jt)
+        idx = m3.addJoint(parent, jt, rng.se3(), name, np.full(nqj, -1.0), np.full(nqj, 1.0), axis=axis)
+        m3.appendBodyToJoint(idx, rng.inertia(), M.SE3.Identity())
+        return idx
+    u1 = addu(M.JOINT_REVOLUTE_UNALIGNED, 0, "ru1", [0.3, -0.5, 0.8])
+    u2 = addu(M.JOINT_PRISMATIC_UNALIGNED, u1, "pu1", [-0.7, 0.2, 0.1])
+    u3 = addu(M.JOINT_REVOLUTE_UNALIGNED, u2, "ru2", [0.0, 0.0, -2.0])
+    addu(M.JOINT_RY, u3, "ry_tip")
+    s3 = addu(M.JOINT_SPHERICAL, u1, "sph")
+    u4 = addu(M.JOINT_REVOLUTE_UNALIGNED, s3, "ru3", [1.0, 1.0, 1.0])
+    addu(M.JOINT_PRISMATIC_UNALIGNED, u4, "pu2", [0.0, 0.0, 1.0])
+    addu(M.JOINT_REVOLUTE_UNALIGNED, u4, "ru4", [0.0, 1e-9, 1.0])
+    m3.armature = np.abs(rng.sym(m3.nv)) * 0.05
+    out["unaligned"] = m3
     return out
 
 

@@ -32,6 +32,7 @@ int main()
   flat.parents = parents.data(); flat.joint_type = types.data(); flat.idx_q = idx.data(); flat.idx_v = idx.data();
   flat.placement = placement.data(); flat.inertia = inertia.data(); flat.armature = armature.data();
   flat.gravity[0] = 0; flat.gravity[1] = 0; flat.gravity[2] = -9.81;
+  flat.axis = nullptr;               // no joint about an arbitrary axis in this model
 
   try
   {

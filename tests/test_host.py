@@ -112,8 +112,10 @@ def test_urdf_rules_on_inline_model():
     assert abs(m.inertias[2].mass - 1.5) < 1e-15  # l1 + tool merged
     assert np.allclose(m.inertias[2].lever, (1.0 * np.array([0.1, 0, 0]) + 0.5 * np.array([0, 0, 0.7])) / 1.5)
     assert np.allclose(m.jointPlacements[2].R, [[0, -1, 0], [1, 0, 0], [0, 0, 1]], atol=1e-15)
-    with pytest.raises(ValueError):
-        M.buildModelFromUrdf(urdf.replace('axis xyz="0 0 1"', 'axis xyz="0 0.6 0.8"'), M.JOINT_FREEFLYER)
+    # any other axis -> JointModelRevoluteUnaligned(axis.normalized()) (parsers/urdf/model.hxx:437-480)
+    mu = M.buildModelFromUrdf(urdf.replace('axis xyz="0 0 1"', 'axis xyz="0 0.3 0.4"'), M.JOINT_FREEFLYER)
+    assert mu.joint_types[1:] == [M.JOINT_FREEFLYER, M.JOINT_PY, M.JOINT_REVOLUTE_UNALIGNED]
+    assert np.allclose(mu.axes[3], [0, 0.6, 0.8], atol=1e-15) and (mu.nq, mu.nv) == (9, 8)
 
 
 def test_inertia_algebra_against_dense_matrices():

@@ -9,7 +9,7 @@ import pytest
 
 from conftest import MODEL_NAMES, load_model, make_extra_models, random_inputs
 
-ALL = MODEL_NAMES + ["mixed", "double_ff"]
+ALL = MODEL_NAMES + ["mixed", "double_ff", "unaligned"]
 EXTRA = make_extra_models()
 
 
@@ -256,3 +256,34 @@ def test_integrate_known_answers(oracle_cls):
         q1 = o.integrate(q0, v)[:, 0]
         ref = np.array([np.sin(th) / th, 2 * np.sin(th / 2) ** 2 / th, 0, 0, 0, np.sin(th / 2), np.cos(th / 2)])
         assert np.abs(q1 - ref).max() < 1e-12, (th, q1, ref)
+
+
+def test_unaligned_joints_reduce_to_the_aligned_ones(oracle_cls):
+    """unittest/joint-revolute.cpp / joint-prismatic.cpp "vsRX / vsPX" pattern: JointModelRevoluteUnaligned(e_k) gives the
+    results of JointModelR{X,Y,Z}, PrismaticUnaligned(e_k) those of P{X,Y,Z} — pins the oracle's unaligned branch against
+    its axis-aligned one (joint-revolute-unaligned.hpp:668-672 vs joint-revolute.hpp:791-820)."""
+    from pinocchio_b200 import model as M
+
+    def chain(unaligned):
+        rng = M._Rng(21)
+        m = M.Model()
+        parent = 0
+        for k in range(6):
+            ax = np.eye(3)[k % 3]
+            rev = k < 3
+            if unaligned:
+                jt = M.JOINT_REVOLUTE_UNALIGNED if rev else M.JOINT_PRISMATIC_UNALIGNED
+                parent = m.addJoint(parent, jt, rng.se3(), f"j{k}", [-1.0], [1.0], axis=ax)
+            else:
+                parent = m.addJoint(parent, (M.JOINT_RX if rev else M.JOINT_PX) + k % 3, rng.se3(), f"j{k}", [-1.0], [1.0])
+            m.appendBodyToJoint(parent, rng.inertia(), M.SE3.Identity())
+        return m
+    ma, mu = chain(False), chain(True)
+    oa, ou = oracle_cls(ma), oracle_cls(mu)
+    q, v, a = random_inputs(ma, 5, 3)
+    tau = oa.rnea(q, v, a)
+    assert np.allclose(ou.rnea(q, v, a), tau, rtol=0, atol=1e-13 * np.abs(tau).max())
+    assert np.allclose(ou.aba(q, v, tau), oa.aba(q, v, tau), rtol=0, atol=1e-11 * np.abs(a).max())
+    assert np.allclose(ou.crba(q, world=True), oa.crba(q, world=True), rtol=0, atol=1e-13 * np.abs(tau).max())
+    for x, y in zip(ou.rnea_derivatives(q, v, a), oa.rnea_derivatives(q, v, a)):
+        assert np.allclose(x, y, rtol=0, atol=1e-12 * max(1.0, np.abs(y).max()))
