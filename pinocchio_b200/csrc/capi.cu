@@ -470,6 +470,37 @@ brbd_status launch_aba(brbd_pool * p, DeviceCtx & d, const T * q, int64_t ldq, c
   return BRBD_OK;
 }
 
+// ---- TMA tensor maps over the caller's (nv*nv x B, leading dimension ldM) matrix block: see crba_tma_kernel ----------
+typedef CUresult (*brbd_encode_tiled_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                         const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                         CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static brbd_encode_tiled_fn encode_tiled_fn()
+{
+  static brbd_encode_tiled_fn fn = [] {
+    void * p = nullptr;
+    cudaDriverEntryPointQueryResult qr;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qr) != cudaSuccess || qr != cudaDriverEntryPointSuccess)
+      p = nullptr;
+    return (brbd_encode_tiled_fn)p;
+  }();
+  return fn;
+}
+template<class T>
+bool crba_tma_setup(T * Mout, int64_t ldM, int64_t B, int nv, CrbaTmaGeom & G, CUtensorMap & map0)
+{
+  const brbd_encode_tiled_fn enc = encode_tiled_fn();
+  constexpr int E = (int)sizeof(T), K = 16 / E;
+  if (!enc || (reinterpret_cast<uintptr_t>(Mout) & 15) || (nv % K) || (ldM % K) || nv > 256 || ldM < (int64_t)nv * nv) return false;
+  G.bx = nv;
+  const cuuint64_t gd[2] = {(cuuint64_t)ldM, (cuuint64_t)B};
+  const cuuint64_t gs[1] = {(cuuint64_t)ldM * (cuuint64_t)E};
+  const cuuint32_t bd[2] = {(cuuint32_t)nv, 32};
+  const cuuint32_t es[2] = {1, 1};
+  return enc(&map0, E == 8 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void *)Mout, gd, gs, bd, es,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 template<class T>
 brbd_status launch_crba(brbd_pool * p, DeviceCtx & d, const T * q, int64_t ldq, T * Mout, int64_t ldM, int64_t B)
 {
@@ -484,6 +515,15 @@ brbd_status launch_crba(brbd_pool * p, DeviceCtx & d, const T * q, int64_t ldq, 
     const int max_warps_tmem = cols_per_slice <= 256 ? 8 : (cols_per_slice <= 512 ? 4 : 0);
     if (max_warps_tmem > 0)
     {
+      // default: column blocks leave through TMA tensor stores (crba_tma_kernel) where the caller's layout allows a tensor
+      // map (see crba_dfs.cuh); BRBD_CRBA_V=tmem keeps the LSU emitter
+      const char * ver = std::getenv("BRBD_CRBA_V");
+      CrbaTmaGeom G{0};
+      CUtensorMap map0;
+      const bool tma = !(ver && std::strcmp(ver, "tmem") == 0) && crba_tma_setup<T>(Mout, ldM, B, t.nv, G, map0);
+      if (tma) L.epad = G.bx;
+      const int epad = L.epad;
+      const size_t tab_bytes = tma ? 0 : 128 * (size_t)t.nv;
       Geometry2 g = pick_geometry2(d, (size_t)L.nstate * sizeof(T), (size_t)32 * L.epad * sizeof(T), B, max_warps_tmem, 1);
       // Per-SM throughput is flat from 5 warps up (measured, profiles/r1_v5_crba_warps.txt), so what counts is the number of
       // rounds the persistent grid needs: fewest rounds first, then the fewest warps that reach it (65536 configurations of
@@ -491,17 +531,27 @@ brbd_status launch_crba(brbd_pool * p, DeviceCtx & d, const T * q, int64_t ldq, 
       g.warps = pick_warps_by_rounds(d, B, g.warps);
       if (const char * e = std::getenv("BRBD_CRBA_WARPS")) // experiments: cap the warps per SM
         g.warps = std::max(1, std::min(g.warps, std::atoi(e)));
-      // the element -> configuration table of the emitter (32 * nv bytes) sits after the warp regions
-      while (g.warps > 1 && (size_t)g.warps * (32 * (size_t)L.nstate * sizeof(T) + 32 * (size_t)L.epad * sizeof(T)) + 32 * (size_t)t.nv + 64 > (size_t)d.max_smem_optin) --g.warps;
-      g.dyn_bytes = (size_t)g.warps * (32 * (size_t)L.nstate * sizeof(T) + 32 * (size_t)L.epad * sizeof(T)) + 32 * (size_t)t.nv;
+      // the element -> global offset table of the emitter (32 * nv ints) sits after the warp regions
+      while (g.warps > 1 && (size_t)g.warps * (32 * (size_t)L.nstate * sizeof(T) + 32 * (size_t)L.epad * sizeof(T)) + tab_bytes + 64 > (size_t)d.max_smem_optin) --g.warps;
+      g.dyn_bytes = (size_t)g.warps * (32 * (size_t)L.nstate * sizeof(T) + 32 * (size_t)L.epad * sizeof(T)) + tab_bytes;
       const int64_t ctas_needed = (B + g.warps * 32 - 1) / (g.warps * 32);
       g.grid = (int)std::max<int64_t>(1, std::min<int64_t>(ctas_needed, (int64_t)d.sm_count));
       L = crba_tmem_layout<T>(t.maxpathdof, t.maxdepth, t.nbranch, t.nv, g.warps, t.ffroot);
+      L.epad = epad;
 #define BRBD_LAUNCH(NT)                                                                              \
   {                                                                                                  \
-    st = set_smem(crba_tmem_kernel<T, NT>, g.dyn_bytes);                                             \
-    if (st != BRBD_OK) return st;                                                                    \
-    crba_tmem_kernel<T, NT><<<g.grid, NT, g.dyn_bytes, d.s()>>>(t, L, q, ldq, Mout, ldM, B);         \
+    if (tma)                                                                                         \
+    {                                                                                                \
+      st = set_smem(crba_tma_kernel<T, NT>, g.dyn_bytes);                                            \
+      if (st != BRBD_OK) return st;                                                                  \
+      crba_tma_kernel<T, NT><<<g.grid, NT, g.dyn_bytes, d.s()>>>(t, L, map0, q, ldq, B);                  \
+    }                                                                                                \
+    else                                                                                             \
+    {                                                                                                \
+      st = set_smem(crba_tmem_kernel<T, NT>, g.dyn_bytes);                                           \
+      if (st != BRBD_OK) return st;                                                                  \
+      crba_tmem_kernel<T, NT><<<g.grid, NT, g.dyn_bytes, d.s()>>>(t, L, q, ldq, Mout, ldM, B);       \
+    }                                                                                                \
   }
       switch (g.warps)
       {
@@ -522,7 +572,7 @@ brbd_status launch_crba(brbd_pool * p, DeviceCtx & d, const T * q, int64_t ldq, 
   }
   // fallback for very deep trees: all state in shared memory
   const CrbaLayout L = crba_layout(t.maxpathdof, t.maxdepth, t.nbranch, t.nv);
-  const Geometry2 g = pick_geometry2(d, (size_t)L.nstate * sizeof(T), (size_t)32 * L.epad * sizeof(T) + 32 * t.nv, B, 4, 2);
+  const Geometry2 g = pick_geometry2(d, (size_t)L.nstate * sizeof(T), (size_t)32 * L.epad * sizeof(T) + 128 * t.nv, B, 4, 2);
 #define BRBD_LAUNCH(NT)                                                                              \
   {                                                                                                  \
     st = set_smem(crba_dfs_kernel<T, NT>, g.dyn_bytes);                                              \

@@ -14,6 +14,8 @@
 // are written as zeros (crba.hpp:15-22; a fresh Data holds zeros there, data.hxx:43).
 #pragma once
 
+#include <cuda.h> // CUtensorMap (type only; the encoder is fetched through cudaGetDriverEntryPoint, capi.cu)
+
 #include "tmem.cuh"
 #include "tree.cuh"
 
@@ -48,15 +50,15 @@ crba_dfs_kernel(const __grid_constant__ TreePOD<T> m, const CrbaLayout L, const 
   const Slots<T, NT> st{sm + tid};
   T * em = sm + (size_t)L.nstate * NT + (size_t)warp * 32 * L.epad; // [32][nv], row = configuration of the tile
   T * myrow = em + lane * L.epad;
-  // ctab[t * 32 + lane] = configuration (row of em) of element e = lane + 32 t of a column block
-  unsigned char * ctab = reinterpret_cast<unsigned char *>(sm + (size_t)L.nstate * NT + (size_t)nw * 32 * L.epad);
+  // gofs[e] = global offset of element e of a (32 configurations x nv) column block: e + (e / nv) * (ldM - nv)
+  int * gofs = reinterpret_cast<int *>(sm + (size_t)L.nstate * NT + (size_t)nw * 32 * L.epad);
   const int nj = m.njoints, nv = m.nv;
-  for (int e = tid; e < 32 * nv; e += NT) ctab[e] = (unsigned char)(e / nv);
+  const int dgc = (int)ldM - nv;
+  for (int e = tid; e < 32 * nv; e += NT) gofs[e] = e + (e / nv) * dgc;
   // The emitter rows hold zeros outside the entries of the column being assembled: a joint zeroes its own
   // rows once its columns are flushed (it is never again an ancestor of a column of this tile).
   for (int k = lane; k < 32 * L.epad; k += 32) em[k] = T(0);
   __syncthreads();
-  const int dgc = (int)ldM - nv; // global offset of element e of a column block: e + c * (ldM - nv)
   const int64_t ntiles = (B + 31) / 32;
   for (int64_t tile = (int64_t)blockIdx.x * nw + warp; tile < ntiles; tile += (int64_t)gridDim.x * nw)
   {
@@ -104,7 +106,7 @@ crba_dfs_kernel(const __grid_constant__ TreePOD<T> m, const CrbaLayout L, const 
           {
             T * __restrict__ g = gtile + (int64_t)col * nv;
 #pragma unroll 5
-            for (int e = lane; e < total; e += 32) g[e + (int)ctab[e] * dgc] = em[e];
+            for (int e = lane; e < total; e += 32) g[gofs[e]] = em[e];
           }
           __syncwarp();
         }
@@ -140,6 +142,7 @@ struct CrbaTmemLayout
 // place, the columns of the other path dofs move down by CRBA_FF_SAVED slots, and the six root rows of every column are
 // oMi_root.actInv(F) — the force in the root frame — instead of six 6-D dot products (J_root = oMi_root's action matrix).
 constexpr int CRBA_FF_SAVED = 24;
+constexpr int CRBA_PF = 4; // L2 prefetch distance of q, in joints 
 template<class T> inline CrbaTmemLayout crba_tmem_layout(int maxpathdof, int maxdepth, int nbranch, int nv, int warps, int ffroot)
 {
   CrbaTmemLayout L;
@@ -167,14 +170,14 @@ crba_tmem_kernel(const __grid_constant__ TreePOD<T> m, const CrbaTmemLayout L, c
   const Slots<T, NT> st{sm + tid};
   T * em = sm + (size_t)L.nstate * NT + (size_t)warp * 32 * L.epad;
   T * myrow = em + lane * L.epad;
-  unsigned char * ctab = reinterpret_cast<unsigned char *>(sm + (size_t)L.nstate * NT + (size_t)nw * 32 * L.epad);
+  int * gofs = reinterpret_cast<int *>(sm + (size_t)L.nstate * NT + (size_t)nw * 32 * L.epad);
   const int nj = m.njoints, nv = m.nv;
-  for (int e = tid; e < 32 * nv; e += NT) ctab[e] = (unsigned char)(e / nv);
+  const int dgc = (int)ldM - nv;
+  for (int e = tid; e < 32 * nv; e += NT) gofs[e] = e + (e / nv) * dgc;
   for (int k = lane; k < 32 * L.epad; k += 32) em[k] = T(0);
   const uint32_t tbase = tmem_alloc_cta(L.tcols, &tmem_base_slot); // includes __syncthreads()
   // this warp's slice: lanes of its SM sub-partition, columns after those of warp - 4 (if any)
   const TmemSlots<T> tm{tbase + (((uint32_t)(warp & 3) * 32u) << 16) + (uint32_t)((warp >> 2) * L.tvals * (int)(sizeof(T) / 4))};
-  const int dgc = (int)ldM - nv;
   const bool ffroot = m.ffroot != 0;
   const int joff = ffroot ? CRBA_FF_SAVED : 0;
   const int64_t ntiles = (B + 31) / 32;
@@ -189,12 +192,22 @@ crba_tmem_kernel(const __grid_constant__ TreePOD<T> m, const CrbaTmemLayout L, c
     SE3<T> X;
     Inertia<T> Yown;
     T qnext = __ldg(qc + m.j[1].idx_q); // first coordinate of the next joint, fetched one joint ahead
+    // ... and its cache line is asked into L2 CRBA_PF joints ahead (running into the next tile of this warp): under the
+    // kernel's write stream a DRAM read takes longer than one joint step
+    const int64_t tnext = tile + (int64_t)gridDim.x * nw;
+    const int64_t cnext = tnext * 32 + lane;
+    const T * __restrict__ qn = tnext < ntiles ? q + (cnext < B ? cnext : B - 1) * ldq : qc;
     for (int i = 1; i < nj; ++i)
     {
       {
         const JointRec r = m.j[i];
         const T q0 = qnext;
         if (i + 1 < nj) qnext = __ldg(qc + m.j[i + 1].idx_q);
+        {
+          const int ip = i + CRBA_PF;
+          const T * pa = ip < nj ? qc + m.j[ip].idx_q : qn + m.j[ip - nj + 1 < nj ? ip - nj + 1 : nj - 1].idx_q;
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(pa));
+        }
         const SE3<T> Xl = tree_liMi(m, i, r.type, qc + r.idx_q, q0);
         if (r.parent > 0)
         {
@@ -255,7 +268,7 @@ crba_tmem_kernel(const __grid_constant__ TreePOD<T> m, const CrbaTmemLayout L, c
           {
             T * __restrict__ g = gtile + (int64_t)col * nv;
 #pragma unroll 5
-            for (int e = lane; e < total; e += 32) g[e + (int)ctab[e] * dgc] = em[e];
+            for (int e = lane; e < total; e += 32) g[gofs[e]] = em[e];
           }
           __syncwarp();
         }
@@ -283,6 +296,185 @@ crba_tmem_kernel(const __grid_constant__ TreePOD<T> m, const CrbaTmemLayout L, c
     }
     __syncwarp();
   }
+  tmem_wait_st();
+  tmem_free_cta(tbase, L.tcols);
+}
+
+// ------------------------------------------------------------------------------------------------------
+// crba_tma_kernel: crba_tmem_kernel with the column blocks leaving the SM through TMA tensor stores.
+//
+// Measured on the kernel above (65 536 x simple_humanoid, scripts/gpu_x.sh): 0.245 ms, of which
+// 0.11 ms are the column flush; the LSU stores do not overlap with the other warps' arithmetic whatever the unrolling, the
+// address table, the store width or the phase of the warps, and one cp.async.bulk per lane and column (256..304 bytes
+// each) is bound by the copy engine's issue rate.  Here the warp's (32 configurations x nv) column block is ONE (or two)
+// cp.async.bulk.tensor.2d stores issued by one lane: asynchronous, a few KB per instruction.
+//
+// The caller's matrix is seen as a 2-D tensor, inner dimension = one configuration's nv x nv matrix (col-major, so column
+// `col` is the inner range [col nv, col nv + nv)), outer dimension = configurations with stride ldM.  A tensor store needs
+// 16-byte aligned box starts, a box whose inner extent is a multiple of 16 bytes and 16-byte strides, i.e. (FP64) even nv
+// and even ldM — talos (nv 38), humanoid_random (32), humanoid (34); measured: box starts at odd elements raise "illegal
+// instruction" (scripts/tma_probe.py), so odd nv (simple_humanoid, 35: every other column segment starts 8 bytes off a
+// 16-byte boundary) stays on crba_tmem_kernel.
+// The emitter tile is rewritten only after cp.async.bulk.wait_group.read, lazily — just before the next column is
+// assembled — so the wait hides behind the forward step / the Y J product in between.
+// ------------------------------------------------------------------------------------------------------
+struct CrbaTmaGeom
+{
+  int bx; // box inner extent = emitter row length (elements) = nv
+};
+BRBD_DI void tma_store_2d(const void * tmap, const void * ssrc, int x, int y)
+{
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(tmap),
+               "r"((uint32_t)__cvta_generic_to_shared(ssrc)), "r"(x), "r"(y)
+               : "memory");
+}
+BRBD_DI void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+BRBD_DI void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+BRBD_DI void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+BRBD_DI void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+template<class T, int NT>
+__global__ void __launch_bounds__(NT, 1)
+crba_tma_kernel(const __grid_constant__ TreePOD<T> m, const CrbaTmemLayout L, const __grid_constant__ CUtensorMap map0,
+                const T * __restrict__ q, int64_t ldq, int64_t B)
+{
+  extern __shared__ __align__(128) unsigned char dyn_smem128[];
+  __shared__ uint32_t tmem_base_slot;
+  T * sm = reinterpret_cast<T *>(dyn_smem128);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  constexpr int nw = NT / 32;
+  // [tiles of the warps (128-byte aligned, TMA source) | J slots]
+  T * em = sm + (size_t)warp * 32 * L.epad;
+  const Slots<T, NT> st{sm + (size_t)nw * 32 * L.epad + tid};
+  T * row = em + lane * L.epad;
+  const int nj = m.njoints, nv = m.nv;
+  for (int k = 0; k < L.epad; ++k) row[k] = T(0);
+  const uint32_t tbase = tmem_alloc_cta(L.tcols, &tmem_base_slot); // includes __syncthreads()
+  const TmemSlots<T> tm{tbase + (((uint32_t)(warp & 3) * 32u) << 16) + (uint32_t)((warp >> 2) * L.tvals * (int)(sizeof(T) / 4))};
+  const bool ffroot = m.ffroot != 0;
+  const int joff = ffroot ? CRBA_FF_SAVED : 0;
+  const int64_t ntiles = (B + 31) / 32;
+  int pj = 0; // joint of the column in flight (0: none)
+  for (int64_t tile = (int64_t)blockIdx.x * nw + warp; tile < ntiles; tile += (int64_t)gridDim.x * nw)
+  {
+    const int64_t c0 = tile * 32;
+    const bool live = c0 + lane < B;
+    const int64_t cfg = live ? c0 + lane : B - 1; // idle lanes shadow the last configuration
+    const T * __restrict__ qc = q + cfg * ldq;
+    SE3<T> X;
+    Inertia<T> Yown;
+    T qnext = __ldg(qc + m.j[1].idx_q);
+    const int64_t tnext = tile + (int64_t)gridDim.x * nw;
+    const int64_t cnext = tnext * 32 + lane;
+    const T * __restrict__ qn = tnext < ntiles ? q + (cnext < B ? cnext : B - 1) * ldq : qc;
+    for (int i = 1; i < nj; ++i)
+    {
+      {
+        const JointRec r = m.j[i];
+        const T q0 = qnext;
+        if (i + 1 < nj) qnext = __ldg(qc + m.j[i + 1].idx_q);
+        {
+          const int ip = i + CRBA_PF;
+          const T * pa = ip < nj ? qc + m.j[ip].idx_q : qn + m.j[ip - nj + 1 < nj ? ip - nj + 1 : nj - 1].idx_q;
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(pa));
+        }
+        const SE3<T> Xl = tree_liMi(m, i, r.type, qc + r.idx_q, q0);
+        if (r.parent > 0)
+        {
+          if (r.parent != i - 1)
+          {
+            T x[12];
+            tmem_wait_st();
+            tm.template load<12>(L.tX + 12 * m.j[r.parent].bslot, x);
+            X.R.c0 = Vec3<T>(x[0], x[1], x[2]); X.R.c1 = Vec3<T>(x[3], x[4], x[5]); X.R.c2 = Vec3<T>(x[6], x[7], x[8]);
+            X.p = Vec3<T>(x[9], x[10], x[11]);
+          }
+          X = X * Xl;
+        }
+        else
+          X = Xl;
+        if (r.bslot >= 0)
+        {
+          const T x[12] = {X.R.c0.x, X.R.c0.y, X.R.c0.z, X.R.c1.x, X.R.c1.y, X.R.c1.z, X.R.c2.x, X.R.c2.y, X.R.c2.z, X.p.x, X.p.y, X.p.z};
+          tm.template store<12>(L.tX + 12 * r.bslot, x);
+        }
+        if (ffroot && i == 1) put_se3(st, L.oJ, X);
+        else
+          for (int k = 0; k < r.nvj; ++k) put_motion(st, L.oJ + 6 * (r.pdof + k) - joff, act_S_col(X, r.type, k));
+        Yown = act(X, tree_inertia(m, i));
+        if (r.nchild > 0)
+        {
+          const T y[10] = {Yown.m, Yown.c.x, Yown.c.y, Yown.c.z, Yown.I.xx, Yown.I.xy, Yown.I.yy, Yown.I.xz, Yown.I.yz, Yown.I.zz};
+          tm.template store<10>(L.tY + 10 * (r.depth - 1), y);
+        }
+      }
+      const int stop = m.j[i].stop;
+      Inertia<T> Y = Yown;
+      for (int j = i; j != stop; j = m.j[j].parent)
+      {
+        const JointRec r = m.j[j];
+        const int npath = r.pdof + r.nvj;
+        for (int k = 0; k < r.nvj; ++k)
+        {
+          const int col = r.idx_v + k;
+          Force<T> F;
+          SE3<T> Xr;
+          if (ffroot)
+          {
+            Xr = get_se3<T>(st, L.oJ);
+            F = Y * (j == 1 ? act_S_col(Xr, J_FF, k) : get_motion<T>(st, L.oJ + 6 * (r.pdof + k) - joff));
+          }
+          else
+            F = Y * get_motion<T>(st, L.oJ + 6 * (r.pdof + k));
+          if (pj)
+          { // the tile is free again once the engine has read the previous column block out of it
+            if (lane == 0) bulk_wait_read();
+            __syncwarp();
+            if (pj != j) // the rows of a finished joint are never again on the path of a column of this tile
+              for (int kk = 0; kk < m.j[pj].nvj; ++kk) row[m.j[pj].idx_v + kk] = T(0);
+          }
+          int t0 = 0;
+          if (ffroot)
+          {
+            // rows of the free-flyer root: J_root^T F = oMi_root.actInv(F)  (S = identity, joint-free-flyer.hpp:47-57)
+            const Vec3<T> fl = tmul(Xr.R, F.lin), fa = tmul(Xr.R, F.ang - cross(Xr.p, F.lin));
+            row[0] = fl.x; row[1] = fl.y; row[2] = fl.z; row[3] = fa.x; row[4] = fa.y; row[5] = fa.z;
+            t0 = 6;
+          }
+#pragma unroll 4
+          for (int t = t0; t < npath; ++t)
+            row[m.path_row[j][t]] = dot6(get_motion<T>(st, L.oJ + 6 * t - joff), F);
+          row[col] += m.armature[col];
+          fence_async_smem();
+          __syncwarp();
+          if (lane == 0)
+          {
+            tma_store_2d(&map0, em, col * nv, (int)c0); // rows past the batch are clipped by the tensor map
+            bulk_commit();
+          }
+          pj = j;
+        }
+        if (r.parent > 0)
+        {
+          T y[10];
+          tmem_wait_st();
+          tm.template load<10>(L.tY + 10 * (r.depth - 2), y);
+          Inertia<T> Yp;
+          Yp.m = y[0]; Yp.c = Vec3<T>(y[1], y[2], y[3]);
+          Yp.I.xx = y[4]; Yp.I.xy = y[5]; Yp.I.yy = y[6]; Yp.I.xz = y[7]; Yp.I.yz = y[8]; Yp.I.zz = y[9];
+          Yp += Y;
+          Y = Yp;
+          if (r.parent == stop)
+          {
+            const T z[10] = {Yp.m, Yp.c.x, Yp.c.y, Yp.c.z, Yp.I.xx, Yp.I.xy, Yp.I.yy, Yp.I.xz, Yp.I.yz, Yp.I.zz};
+            tm.template store<10>(L.tY + 10 * (r.depth - 2), z);
+          }
+        }
+      }
+    }
+  }
+  if (lane == 0) bulk_wait_all();
+  __syncwarp();
   tmem_wait_st();
   tmem_free_cta(tbase, L.tcols);
 }

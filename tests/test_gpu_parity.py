@@ -282,3 +282,24 @@ def test_rnea_aba_both_paths(ctx, name, path, monkeypatch):
         ddq = pb.abaInParallel(1, pool, q, v, tau)
         ref = orc.aba(q, v, tau)
         assert_close(ddq, ref, atol=1e-12 + 1e-10 * np.abs(ref).max(), what=f"aba[{path}] {name} B={B}")
+
+
+@pytest.mark.parametrize("name,pad", [("humanoid", 0), ("humanoid", 1), ("humanoid", 2), ("talos_reduced_ff", 6),
+                                      ("simple_humanoid_ff", 0), ("simple_humanoid_ff", 1), ("humanoid_random", 0)])
+@pytest.mark.parametrize("B", [1, 31, 77])
+def test_crba_device_layouts(ctx, name, pad, B):
+    """CRBA into device matrices with a padded leading dimension: even nv and even ld leave through TMA tensor stores
+    (crba_tma_kernel), anything else through the LSU emitter (crba_tmem_kernel); the padding is never written and a partial
+    last tile is clipped."""
+    import torch
+    import pinocchio_b200 as pb
+    model, pool, orc = ctx(name)
+    nn = model.nv * model.nv
+    q, _, _ = random_inputs(model, B, 71)
+    tq = torch.from_numpy(np.ascontiguousarray(q.T)).cuda()
+    big = torch.full((B + 1, nn + pad), -7.0, dtype=torch.float64, device="cuda")
+    pb.crbaInParallel(1, pool, tq, big[:B, :nn])
+    torch.cuda.synchronize()
+    got = big.cpu().numpy()
+    assert_close(got[:B, :nn].T, orc.crba(q, world=True), atol=1e-11, what=f"crba {name} ld={nn + pad}")
+    assert (got[:B, nn:] == -7.0).all() and (got[B] == -7.0).all(), "wrote outside the caller's block"
