@@ -486,19 +486,35 @@ static brbd_encode_tiled_fn encode_tiled_fn()
   return fn;
 }
 template<class T>
-bool crba_tma_setup(T * Mout, int64_t ldM, int64_t B, int nv, CrbaTmaGeom & G, CUtensorMap & map0)
+bool crba_tma_setup(T * Mout, int64_t ldM, int64_t B, int nv, CrbaTmaGeom & G, CUtensorMap & map0, CUtensorMap & map1)
 {
   const brbd_encode_tiled_fn enc = encode_tiled_fn();
   constexpr int E = (int)sizeof(T), K = 16 / E;
-  if (!enc || (reinterpret_cast<uintptr_t>(Mout) & 15) || (nv % K) || (ldM % K) || nv > 256 || ldM < (int64_t)nv * nv) return false;
-  G.bx = nv;
-  const cuuint64_t gd[2] = {(cuuint64_t)ldM, (cuuint64_t)B};
-  const cuuint64_t gs[1] = {(cuuint64_t)ldM * (cuuint64_t)E};
-  const cuuint32_t bd[2] = {(cuuint32_t)nv, 32};
+  if (!enc || (reinterpret_cast<uintptr_t>(Mout) & 15) || nv > 255 || ldM < (int64_t)nv * nv) return false;
+  const bool even = (nv % K) == 0 && (ldM % K) == 0;
+  const bool odd = E == 8 && (nv & 1) && nv >= 3;
+  if (!even && !odd) return false;
+  G.odd = even ? 0 : 1;
+  G.pairs = (!even && (ldM & 1)) ? 1 : 0;
+  G.bx = even ? nv : nv + 1;
+  const CUtensorMapDataType dt = E == 8 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
   const cuuint32_t es[2] = {1, 1};
-  return enc(&map0, E == 8 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void *)Mout, gd, gs, bd, es,
-             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
-             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+  auto make = [&](CUtensorMap & mp, T * base, cuuint64_t inner, cuuint64_t outer, cuuint64_t stride_elems, cuuint32_t rows) {
+    const cuuint64_t gd[2] = {inner, outer > 0 ? outer : 1};
+    const cuuint64_t gs[1] = {stride_elems * (cuuint64_t)E};
+    const cuuint32_t bd[2] = {(cuuint32_t)G.bx, rows};
+    return enc(&mp, dt, 2, (void *)base, gd, gs, bd, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+               CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+  };
+  if (!G.pairs)
+  {
+    if (!make(map0, Mout, (cuuint64_t)ldM, (cuuint64_t)B, (cuuint64_t)ldM, 32)) return false;
+    map1 = map0;
+    return true;
+  }
+  if (!make(map0, Mout, (cuuint64_t)ldM, (cuuint64_t)((B + 1) / 2), (cuuint64_t)(2 * ldM), 16)) return false;
+  if (B < 2) { map1 = map0; return true; } // the kernel issues no odd-half store for a single configuration
+  return make(map1, Mout + (ldM - 1), (cuuint64_t)(ldM + 1), (cuuint64_t)(B / 2), (cuuint64_t)(2 * ldM), 16);
 }
 
 template<class T>
@@ -518,9 +534,9 @@ brbd_status launch_crba(brbd_pool * p, DeviceCtx & d, const T * q, int64_t ldq, 
       // default: column blocks leave through TMA tensor stores (crba_tma_kernel) where the caller's layout allows a tensor
       // map (see crba_dfs.cuh); BRBD_CRBA_V=tmem keeps the LSU emitter
       const char * ver = std::getenv("BRBD_CRBA_V");
-      CrbaTmaGeom G{0};
-      CUtensorMap map0;
-      const bool tma = !(ver && std::strcmp(ver, "tmem") == 0) && crba_tma_setup<T>(Mout, ldM, B, t.nv, G, map0);
+      CrbaTmaGeom G{0, 0, 0};
+      CUtensorMap map0, map1;
+      const bool tma = !(ver && std::strcmp(ver, "tmem") == 0) && crba_tma_setup<T>(Mout, ldM, B, t.nv, G, map0, map1);
       if (tma) L.epad = G.bx;
       const int epad = L.epad;
       const size_t tab_bytes = tma ? 0 : 128 * (size_t)t.nv;
@@ -540,11 +556,17 @@ brbd_status launch_crba(brbd_pool * p, DeviceCtx & d, const T * q, int64_t ldq, 
       L.epad = epad;
 #define BRBD_LAUNCH(NT)                                                                              \
   {                                                                                                  \
-    if (tma)                                                                                         \
+    if (tma && G.odd)                                                                                \
     {                                                                                                \
-      st = set_smem(crba_tma_kernel<T, NT>, g.dyn_bytes);                                            \
+      st = set_smem(crba_tma_kernel<T, NT, true>, g.dyn_bytes);                                      \
       if (st != BRBD_OK) return st;                                                                  \
-      crba_tma_kernel<T, NT><<<g.grid, NT, g.dyn_bytes, d.s()>>>(t, L, map0, q, ldq, B);                  \
+      crba_tma_kernel<T, NT, true><<<g.grid, NT, g.dyn_bytes, d.s()>>>(t, L, G, map0, map1, q, ldq, Mout, ldM, B); \
+    }                                                                                                \
+    else if (tma)                                                                                    \
+    {                                                                                                \
+      st = set_smem(crba_tma_kernel<T, NT, false>, g.dyn_bytes);                                     \
+      if (st != BRBD_OK) return st;                                                                  \
+      crba_tma_kernel<T, NT, false><<<g.grid, NT, g.dyn_bytes, d.s()>>>(t, L, G, map0, map1, q, ldq, Mout, ldM, B); \
     }                                                                                                \
     else                                                                                             \
     {                                                                                                \

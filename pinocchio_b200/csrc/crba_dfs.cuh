@@ -311,16 +311,27 @@ crba_tmem_kernel(const __grid_constant__ TreePOD<T> m, const CrbaTmemLayout L, c
 //
 // The caller's matrix is seen as a 2-D tensor, inner dimension = one configuration's nv x nv matrix (col-major, so column
 // `col` is the inner range [col nv, col nv + nv)), outer dimension = configurations with stride ldM.  A tensor store needs
-// 16-byte aligned box starts, a box whose inner extent is a multiple of 16 bytes and 16-byte strides, i.e. (FP64) even nv
-// and even ldM — talos (nv 38), humanoid_random (32), humanoid (34); measured: box starts at odd elements raise "illegal
-// instruction" (scripts/tma_probe.py), so odd nv (simple_humanoid, 35: every other column segment starts 8 bytes off a
-// 16-byte boundary) stays on crba_tmem_kernel.
+// 16-byte aligned box starts (a box starting at an odd FP64 element raises "illegal instruction", scripts/tma_probe.py), a
+// box whose inner extent is a multiple of 16 bytes and 16-byte strides.
+//   * even nv, even ldM (talos 38, humanoid_random 32, humanoid 34): box = the column block itself (ODD = false).
+//   * odd nv (FP64; simple_humanoid 35) — every other column segment starts 8 bytes off a 16-byte boundary (ODD = true):
+//     the box is nv + 1 wide and starts EARLY, inside the previous column — one element early where the segment starts at
+//     an odd element (the extra element is M[nv-1, col-1]), two where it starts at an even one (M[nv-2, col-1], M[nv-1, col-1];
+//     the column's own last entry M[nv-1, col] is then left to the box of column col + 1, whose parity is the opposite).
+//     All of these are entries of the strictly lower triangle, i.e. structural zeros of the result (crba.hpp:15-22), so the
+//     extra elements always store the value that belongs there.  Column 0 (nothing in front of it) and column nv - 1 where
+//     it would need the two-early box (M[nv-2, nv-2] is not a zero) are written by plain stores — 1.5 columns per tile.
+//     With an odd ldM the parity also alternates with the configuration: two maps over PAIRS of configurations
+//     (stride 2 ldM), the odd ones based at Mout + ldM - 1 with every inner coordinate shifted by one; the tile keeps the
+//     even configurations in rows 0..15 and the odd ones in rows 16..31 and is stored in two halves.
 // The emitter tile is rewritten only after cp.async.bulk.wait_group.read, lazily — just before the next column is
 // assembled — so the wait hides behind the forward step / the Y J product in between.
 // ------------------------------------------------------------------------------------------------------
 struct CrbaTmaGeom
 {
-  int bx; // box inner extent = emitter row length (elements) = nv
+  int bx;    // box inner extent = emitter row length (elements): nv, or nv + 1 for odd nv
+  int odd;   // odd nv (FP64): shifted boxes, see above
+  int pairs; // odd nv and odd ldM: even / odd configurations over two maps
 };
 BRBD_DI void tma_store_2d(const void * tmap, const void * ssrc, int x, int y)
 {
@@ -333,10 +344,11 @@ BRBD_DI void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" 
 BRBD_DI void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 BRBD_DI void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-template<class T, int NT>
+template<class T, int NT, bool ODD>
 __global__ void __launch_bounds__(NT, 1)
-crba_tma_kernel(const __grid_constant__ TreePOD<T> m, const CrbaTmemLayout L, const __grid_constant__ CUtensorMap map0,
-                const T * __restrict__ q, int64_t ldq, int64_t B)
+crba_tma_kernel(const __grid_constant__ TreePOD<T> m, const CrbaTmemLayout L, const CrbaTmaGeom G,
+                const __grid_constant__ CUtensorMap map0, const __grid_constant__ CUtensorMap map1,
+                const T * __restrict__ q, int64_t ldq, T * __restrict__ Mout, int64_t ldM, int64_t B)
 {
   extern __shared__ __align__(128) unsigned char dyn_smem128[];
   __shared__ uint32_t tmem_base_slot;
@@ -346,15 +358,20 @@ crba_tma_kernel(const __grid_constant__ TreePOD<T> m, const CrbaTmemLayout L, co
   // [tiles of the warps (128-byte aligned, TMA source) | J slots]
   T * em = sm + (size_t)warp * 32 * L.epad;
   const Slots<T, NT> st{sm + (size_t)nw * 32 * L.epad + tid};
-  T * row = em + lane * L.epad;
+  // ODD: with two maps the tile keeps the even configurations in rows 0..15 and the odd ones in rows 16..31
+  const int half = (ODD && G.pairs) ? (lane & 1) : 0;
+  T * myrow = em + ((ODD && G.pairs) ? (lane >> 1) + 16 * half : lane) * L.epad;
+  T * row = myrow; // ODD: myrow + shift of the column being assembled
   const int nj = m.njoints, nv = m.nv;
-  for (int k = 0; k < L.epad; ++k) row[k] = T(0);
+  for (int k = 0; k < L.epad; ++k) myrow[k] = T(0);
   const uint32_t tbase = tmem_alloc_cta(L.tcols, &tmem_base_slot); // includes __syncthreads()
   const TmemSlots<T> tm{tbase + (((uint32_t)(warp & 3) * 32u) << 16) + (uint32_t)((warp >> 2) * L.tvals * (int)(sizeof(T) / 4))};
   const bool ffroot = m.ffroot != 0;
   const int joff = ffroot ? CRBA_FF_SAVED : 0;
   const int64_t ntiles = (B + 31) / 32;
-  int pj = 0; // joint of the column in flight (0: none)
+  int pj = 0;            // joint of the column in flight (0: none)
+  int ps = 0;            // ODD: shift of its entries in this lane's row
+  bool inflight = false; // ODD: a tensor store of this warp may still be reading the tile
   for (int64_t tile = (int64_t)blockIdx.x * nw + warp; tile < ntiles; tile += (int64_t)gridDim.x * nw)
   {
     const int64_t c0 = tile * 32;
@@ -426,7 +443,27 @@ crba_tma_kernel(const __grid_constant__ TreePOD<T> m, const CrbaTmemLayout L, co
           }
           else
             F = Y * get_motion<T>(st, L.oJ + 6 * (r.pdof + k));
-          if (pj)
+          int sh = 0;          // ODD: shift of this lane's entries; plain: this lane stores the column itself
+          bool plain = false;
+          if constexpr (ODD)
+          {
+            // parity of the segment start (elements): nv is odd, an odd ldM moves the odd configurations by one more
+            const int a = (half + col) & 1;
+            plain = col == 0 || (col == nv - 1 && a == 0);
+            sh = plain ? 0 : (a ? 1 : 2);
+            if (inflight)
+            {
+              if (lane == 0) bulk_wait_read();
+              __syncwarp();
+            }
+            if (pj)
+            { // the shift changes from column to column: clear what the previous column left
+              const int np = m.j[pj].pdof + m.j[pj].nvj;
+              for (int t = 0; t < np; ++t) myrow[ps + m.path_row[pj][t]] = T(0);
+            }
+            row = myrow + sh;
+          }
+          else if (pj)
           { // the tile is free again once the engine has read the previous column block out of it
             if (lane == 0) bulk_wait_read();
             __syncwarp();
@@ -447,7 +484,32 @@ crba_tma_kernel(const __grid_constant__ TreePOD<T> m, const CrbaTmemLayout L, co
           row[col] += m.armature[col];
           fence_async_smem();
           __syncwarp();
-          if (lane == 0)
+          if constexpr (ODD)
+          {
+            // per half: box one element early (segment starts at an odd element) or two (even), see the header comment
+            const int a0 = col & 1, a1 = (col + 1) & 1;
+            const bool plain0 = col == 0 || (col == nv - 1 && a0 == 0), plain1 = col == 0 || (col == nv - 1 && a1 == 0);
+            if (lane == 0)
+            {
+              if (G.pairs)
+              {
+                const int y = (int)(c0 >> 1);
+                if (!plain0) tma_store_2d(&map0, em, col * nv - (a0 ? 1 : 2), y);
+                if (!plain1 && c0 + 1 < B) tma_store_2d(&map1, em + 16 * L.epad, col * nv - (a1 ? 1 : 2) + 1, y);
+              }
+              else if (!plain0)
+                tma_store_2d(&map0, em, col * nv - (a0 ? 1 : 2), (int)c0);
+              bulk_commit();
+            }
+            inflight = G.pairs ? !(plain0 && plain1) : !plain0;
+            if (plain && live)
+            {
+              T * __restrict__ g = Mout + cfg * ldM + (int64_t)col * nv;
+              for (int e = 0; e < nv; ++e) g[e] = myrow[e];
+            }
+            ps = sh;
+          }
+          else if (lane == 0)
           {
             tma_store_2d(&map0, em, col * nv, (int)c0); // rows past the batch are clipped by the tensor map
             bulk_commit();
