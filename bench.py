@@ -309,7 +309,7 @@ def main():
     # `bound` is "hbm" | "tensor") describes; ABA is bound by the FP64 pipe (AI 24 flop/B, no tensor cores on this
     # path) and is reported against the measured DFMA peak under `fp64_roofline`.  `share_of_step` says how the
     # step's time splits, so the dominant kernel can be read off either way.
-    kname = {"aba": "aba_rr_kernel<double>", "crba": "crba_tmem_kernel<double>"}
+    kname = {"aba": "aba_rr_kernel<double>", "crba": "crba_tma_kernel<double>"}
     roofline = {"bound": "hbm", "kernel": kname["crba"], "achieved": kern["crba"]["achieved_GBs"], "peak": hbm_peak,
                 "unit": "GB/s", "frac": kern["crba"]["hbm_frac"], "traffic": NCU_TRAFFIC.get("crba"), "peak_source": peak_src,
                 "share_of_step": crba_ms / (aba_ms + crba_ms)}
