@@ -31,10 +31,10 @@ MODEL = "simple_humanoid_ff"
 BATCH = 65536
 L2_BYTES = 126 * 1024 * 1024
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures
-# (profiles/r1_v7_step_ncu_full.csv: crba_tmem_kernel<double,224> 43.4 MB read + 597.7 MB written; aba_rr_kernel<double,224>
-# 386.9 MB read + 427.0 MB written — the ABA figure is 11x its 74 MB of algorithmic bytes: the per-thread pass-3 record
+# (profiles/r1_v8_step_ncu_full.csv: crba_tma_kernel<double,224,true> 47.3 MB read + 596.1 MB written; aba_rr_kernel<double,224>
+# 388.1 MB read + 426.1 MB written — the ABA figure is 11x its 74 MB of algorithmic bytes: the per-thread pass-3 record
 # store, 186 MB for a resident wave, does not stay L2-resident); bytes per launch of 65536 configurations
-NCU_TRAFFIC = {"crba": 641.0e6, "aba": 813.9e6}
+NCU_TRAFFIC = {"crba": 643.4e6, "aba": 814.2e6}
 
 
 def load_model(name):
