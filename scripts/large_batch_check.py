@@ -20,7 +20,7 @@ build_oracle()
 CASES = [("manipulator", 1 << 20, ["rnea_derivatives", "aba_derivatives", "rnea", "aba", "crba"]),
          ("talos_reduced_ff", 1 << 22, ["rnea", "aba"]),
          ("talos_reduced_ff", 1 << 20, ["crba", "rnea_derivatives"]),
-         ("simple_humanoid_ff", 1 << 20, ["aba_derivatives", "euler_step"])]
+         ("simple_humanoid_ff", 1 << 20, ["crba", "aba_derivatives", "euler_step"])]
 if args.quick:
     CASES = [(m, b >> 4, a) for m, b, a in CASES]
 

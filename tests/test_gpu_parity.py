@@ -161,6 +161,13 @@ def test_fp32_mode_tolerance(ctx):
     M32 = pb.crbaInParallel(1, pool, q.astype(np.float32))
     refM = orc.crba(q, world=True)
     assert np.abs(M32 - refM).max() / np.abs(refM).max() < 5e-5
+    # nv % 4 == 0: the FP32 column blocks leave through TMA tensor stores (talos, nv 38, takes the LSU emitter above)
+    model, pool, orc = ctx("humanoid_random")
+    q, _, _ = random_inputs(model, 77, 83)
+    M32 = pb.crbaInParallel(1, pool, q.astype(np.float32))
+    refM = orc.crba(q, world=True)
+    assert M32.dtype == np.float32 and np.abs(M32 - refM).max() / np.abs(refM).max() < 5e-5
+    assert not M32[~structural_mask(model)].any(), "entries outside the tree sparsity must be exact zeros"
 
 
 def test_error_behaviour(ctx):
