@@ -1,9 +1,10 @@
 #!/bin/bash
 mkdir -p gpurun_out
-for x in 0 8 24; do
-echo "== BRBD_ABA_X=$x"
-BRBD_ABA_X=$x timeout 300 python scripts/bench_all.py --models simple_humanoid_ff,talos_reduced_ff --algos aba --reps 9 2>/dev/null | python -c "
+timeout 900 python -m pytest tests -q -m gpu -x -k "crba or leading or fp32 or device_pointers" 2>&1 | tail -3
+for v in tma; do
+echo "== BRBD_CRBA_V=$v"
+BRBD_CRBA_V=$v timeout 300 python scripts/bench_all.py --models simple_humanoid_ff,talos_reduced_ff,humanoid_random,manipulator --algos crba --reps 9 2>/dev/null | python -c "
 import sys, json
 for l in sys.stdin:
-    d = json.loads(l); print(d['model'], d['algo'], d['ms'], 'ms  fp64', round(d['fp64_frac_of_measured'], 3))"
-done | tee gpurun_out/aba_x.txt
+    d = json.loads(l); print(d['model'], d['algo'], d['ms'], 'ms  hbm', round(d['hbm_frac_of_measured'], 3))"
+done | tee gpurun_out/crba_x.txt
