@@ -303,7 +303,7 @@ crba_tmem_kernel(const __grid_constant__ TreePOD<T> m, const CrbaTmemLayout L, c
 // ------------------------------------------------------------------------------------------------------
 // crba_tma_kernel: crba_tmem_kernel with the column blocks leaving the SM through TMA tensor stores.
 //
-// Measured on the kernel above (65 536 x simple_humanoid, scripts/gpu_x.sh): 0.245 ms, of which
+// Measured on the kernel above (65 536 x simple_humanoid, temporary variants): 0.245 ms, of which
 // 0.11 ms are the column flush; the LSU stores do not overlap with the other warps' arithmetic whatever the unrolling, the
 // address table, the store width or the phase of the warps, and one cp.async.bulk per lane and column (256..304 bytes
 // each) is bound by the copy engine's issue rate.  Here the warp's (32 configurations x nv) column block is ONE (or two)
