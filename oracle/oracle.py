@@ -52,6 +52,17 @@ def _p(a):
     return None if a is None else a.ctypes.data_as(ctypes.c_void_p)
 
 
+def _nt(nthreads, B):
+    """0 = every host thread for batches worth forking a team for, one thread otherwise."""
+    if nthreads and nthreads > 0:
+        return int(nthreads)
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    return n if B >= 512 else 1
+
+
 def _cols(a, rows):
     a = np.asarray(a, dtype=np.float64)
     if a.ndim == 1:
@@ -64,7 +75,8 @@ class Oracle:
     """CPU restatement of rnea / aba(WORLD) / crba / computeRNEADerivatives / computeABADerivatives.
 
     All batched arguments are (rows x B) arrays whose columns are configurations, as in
-    rneaInParallel (include/pinocchio/algorithm/parallel/rnea.hpp:38).
+    rneaInParallel (include/pinocchio/algorithm/parallel/rnea.hpp:38).  `long_double`: 0 / False = double,
+    1 / True = x87 80-bit, 2 = IEEE binary128 (__float128); `nthreads` 0 = all host threads for B >= 512.
     """
 
     def __init__(self, model):
@@ -99,62 +111,62 @@ class Oracle:
     def max_threads() -> int:
         return int(_lib().oracle_max_threads())
 
-    def rnea(self, q, v, a, nthreads=1, long_double=False):
+    def rnea(self, q, v, a, nthreads=0, long_double=False):
         q, v, a = _cols(q, self.nq), _cols(v, self.nv), _cols(a, self.nv)
         B = q.shape[1]
         tau = np.empty((self.nv, B), order="F")
-        _lib().oracle_rnea(self._h, _p(q), _p(v), _p(a), _p(tau), ctypes.c_int64(B), int(nthreads), int(long_double))
+        _lib().oracle_rnea(self._h, _p(q), _p(v), _p(a), _p(tau), ctypes.c_int64(B), _nt(nthreads, B), int(long_double))
         return tau
 
-    def aba(self, q, v, tau, nthreads=1, long_double=False):
+    def aba(self, q, v, tau, nthreads=0, long_double=False):
         q, v, tau = _cols(q, self.nq), _cols(v, self.nv), _cols(tau, self.nv)
         B = q.shape[1]
         a = np.empty((self.nv, B), order="F")
-        _lib().oracle_aba(self._h, _p(q), _p(v), _p(tau), _p(a), ctypes.c_int64(B), int(nthreads), int(long_double))
+        _lib().oracle_aba(self._h, _p(q), _p(v), _p(tau), _p(a), ctypes.c_int64(B), _nt(nthreads, B), int(long_double))
         return a
 
-    def crba(self, q, nthreads=1, long_double=False, world=False):
+    def crba(self, q, nthreads=0, long_double=False, world=False):
         """(nv*nv x B); each column a col-major nv x nv matrix, upper triangle + zeros."""
         q = _cols(q, self.nq)
         B = q.shape[1]
         M = np.empty((self.nv * self.nv, B), order="F")
-        _lib().oracle_crba(self._h, _p(q), _p(M), ctypes.c_int64(B), int(nthreads), int(long_double), int(world))
+        _lib().oracle_crba(self._h, _p(q), _p(M), ctypes.c_int64(B), _nt(nthreads, B), int(long_double), int(world))
         return M
 
-    def rnea_derivatives(self, q, v, a, nthreads=1, long_double=False):
+    def rnea_derivatives(self, q, v, a, nthreads=0, long_double=False):
         q, v, a = _cols(q, self.nq), _cols(v, self.nv), _cols(a, self.nv)
         B = q.shape[1]
         nn = self.nv * self.nv
         dq, dv, da = (np.empty((nn, B), order="F") for _ in range(3))
         tau = np.empty((self.nv, B), order="F")
         _lib().oracle_rnea_derivatives(self._h, _p(q), _p(v), _p(a), _p(dq), _p(dv), _p(da), _p(tau),
-                                       ctypes.c_int64(B), int(nthreads), int(long_double))
+                                       ctypes.c_int64(B), _nt(nthreads, B), int(long_double))
         return dq, dv, da, tau
 
-    def aba_derivatives(self, q, v, tau, nthreads=1, long_double=False):
+    def aba_derivatives(self, q, v, tau, nthreads=0, long_double=False):
         q, v, tau = _cols(q, self.nq), _cols(v, self.nv), _cols(tau, self.nv)
         B = q.shape[1]
         nn = self.nv * self.nv
         dq, dv, dtau = (np.empty((nn, B), order="F") for _ in range(3))
         ddq = np.empty((self.nv, B), order="F")
         _lib().oracle_aba_derivatives(self._h, _p(q), _p(v), _p(tau), _p(dq), _p(dv), _p(dtau), _p(ddq),
-                                      ctypes.c_int64(B), int(nthreads), int(long_double))
+                                      ctypes.c_int64(B), _nt(nthreads, B), int(long_double))
         return dq, dv, dtau, ddq
 
     # ---- the callers' other needs (SURVEY.md §8f rank 2 and 4) ----
-    def nle(self, q, v, nthreads=1):
+    def nle(self, q, v, nthreads=0):
         """nonLinearEffects (algorithm/rnea.hxx:227-343): the same two sweeps as rnea with the S*a term dropped, i.e.
         rnea(q, v, 0) — the identity the reference asserts in unittest/rnea.cpp:201-206."""
         q, v = _cols(q, self.nq), _cols(v, self.nv)
         return self.rnea(q, v, np.zeros_like(v), nthreads=nthreads)
 
-    def gravity(self, q, nthreads=1):
+    def gravity(self, q, nthreads=0):
         """computeGeneralizedGravity (algorithm/rnea.hxx:346-452) == rnea(q, 0, 0), unittest/rnea.cpp:225-228."""
         q = _cols(q, self.nq)
         z = np.zeros((self.nv, q.shape[1]), order="F")
         return self.rnea(q, z, z, nthreads=nthreads)
 
-    def minverse(self, q, nthreads=1):
+    def minverse(self, q, nthreads=0):
         """computeMinverse (algorithm/aba.hxx:613-902): upper triangle of M^-1, strictly-lower part zero (a fresh
         data.Minv).  Taken from the Minv recursion of abaDerivatives, which the reference asserts equal to
         computeMinverse (unittest/aba-derivatives.cpp:96-100); it does not depend on v or tau."""

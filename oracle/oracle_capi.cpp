@@ -3,6 +3,9 @@
 // (reference: include/pinocchio/algorithm/parallel/rnea.hpp:69-82, parallel/aba.hpp:70-83,
 // parallel/omp.hpp:12-16): one private (Model, Data) workspace per OpenMP thread and
 // `#pragma omp parallel for schedule(static)` over the batch columns.
+#define ORACLE_WITH_QUAD 1
+#include <quadmath.h>
+
 #include "rbd_oracle.hpp"
 
 #include <omp.h>
@@ -16,7 +19,8 @@ struct oracle_model
   Model<double> md;
   Model<long double> ml;
   Model<Counted> mc;
-  explicit oracle_model(const brbd_flat_model & f) : md(f), ml(f), mc(f) {}
+  Model<__float128> mq;
+  explicit oracle_model(const brbd_flat_model & f) : md(f), ml(f), mc(f), mq(f) {}
 };
 
 namespace
@@ -147,38 +151,43 @@ oracle_model * oracle_model_create(const brbd_flat_model * f) { return new oracl
 void oracle_model_destroy(oracle_model * m) { delete m; }
 int oracle_max_threads(void) { return omp_get_max_threads(); }
 
-// precision: 0 = double, 1 = long double (x87 80-bit; inputs/outputs are double)
+// precision: 0 = double, 1 = long double (x87 80-bit), 2 = __float128 (IEEE binary128); inputs/outputs are double
 void oracle_rnea(const oracle_model * m, const double * q, const double * v, const double * a, double * tau,
                  int64_t B, int nthreads, int precision)
 {
-  if (precision) rnea_batch(m->ml, q, v, a, tau, B, nthreads);
+  if (precision == 2) rnea_batch(m->mq, q, v, a, tau, B, nthreads);
+  else if (precision) rnea_batch(m->ml, q, v, a, tau, B, nthreads);
   else rnea_batch(m->md, q, v, a, tau, B, nthreads);
 }
 void oracle_aba(const oracle_model * m, const double * q, const double * v, const double * tau, double * a,
                 int64_t B, int nthreads, int precision)
 {
-  if (precision) aba_batch(m->ml, q, v, tau, a, B, nthreads);
+  if (precision == 2) aba_batch(m->mq, q, v, tau, a, B, nthreads);
+  else if (precision) aba_batch(m->ml, q, v, tau, a, B, nthreads);
   else aba_batch(m->md, q, v, tau, a, B, nthreads);
 }
 // world: 1 = crbaWorldConvention, 0 = crbaLocalConvention (the default of crba(), crba.hpp:51)
 void oracle_crba(const oracle_model * m, const double * q, double * M, int64_t B, int nthreads, int precision,
                  int world)
 {
-  if (precision) crba_batch(m->ml, q, M, B, nthreads, world);
+  if (precision == 2) crba_batch(m->mq, q, M, B, nthreads, world);
+  else if (precision) crba_batch(m->ml, q, M, B, nthreads, world);
   else crba_batch(m->md, q, M, B, nthreads, world);
 }
 void oracle_rnea_derivatives(const oracle_model * m, const double * q, const double * v, const double * a,
                              double * dq, double * dv, double * da, double * tau, int64_t B, int nthreads,
                              int precision)
 {
-  if (precision) rnea_derivs_batch(m->ml, q, v, a, dq, dv, da, tau, B, nthreads);
+  if (precision == 2) rnea_derivs_batch(m->mq, q, v, a, dq, dv, da, tau, B, nthreads);
+  else if (precision) rnea_derivs_batch(m->ml, q, v, a, dq, dv, da, tau, B, nthreads);
   else rnea_derivs_batch(m->md, q, v, a, dq, dv, da, tau, B, nthreads);
 }
 void oracle_aba_derivatives(const oracle_model * m, const double * q, const double * v, const double * tau,
                             double * dq, double * dv, double * dtau, double * ddq, int64_t B, int nthreads,
                             int precision)
 {
-  if (precision) aba_derivs_batch(m->ml, q, v, tau, dq, dv, dtau, ddq, B, nthreads);
+  if (precision == 2) aba_derivs_batch(m->mq, q, v, tau, dq, dv, dtau, ddq, B, nthreads);
+  else if (precision) aba_derivs_batch(m->ml, q, v, tau, dq, dv, dtau, ddq, B, nthreads);
   else aba_derivs_batch(m->md, q, v, tau, dq, dv, dtau, ddq, B, nthreads);
 }
 

@@ -70,12 +70,20 @@ inline void sincos_s(Counted x, Counted & s, Counted & c)
   flop_counter().sincos++;
   ::sincos(x.x, &s.x, &c.x);
 }
+#ifdef ORACLE_WITH_QUAD
+// IEEE binary128 (libquadmath): the second, wider independent guard of the double-precision oracle
+inline void sincos_s(__float128 x, __float128 & s, __float128 & c) { ::sincosq(x, &s, &c); }
+inline __float128 sqrt_s(__float128 x) { return sqrtq(x); }
+#endif
 inline double sqrt_s(double x) { return std::sqrt(x); }
 inline long double sqrt_s(long double x) { return sqrtl(x); }
 inline float sqrt_s(float x) { return std::sqrt(x); }
 inline Counted sqrt_s(Counted x) { flop_counter().sqrt_++; return Counted(std::sqrt(x.x)); }
 template<class S> inline S eps_s() { return std::numeric_limits<S>::epsilon(); }
 template<> inline Counted eps_s<Counted>() { return Counted(std::numeric_limits<double>::epsilon()); }
+#ifdef ORACLE_WITH_QUAD
+template<> inline __float128 eps_s<__float128>() { return FLT128_EPSILON; }
+#endif
 template<class S> inline S max_s(S a, S b) { return (a < b) ? b : a; }
 template<class S> inline double to_double(S x) { return (double)x; }
 
@@ -1294,6 +1302,9 @@ void abaDerivatives(const Model<S> & model, Data<S> & data, const S * q, const S
 // ---------------------------------------------------------------------------------------------
 template<class S> inline S taylor_precision3() { return S(0.0001220703125); } // pow(epsilon, 1/4), math/taylor-expansion.hpp:30-36 (2^-13 for double)
 template<> inline float taylor_precision3<float>() { return std::pow(std::numeric_limits<float>::epsilon(), 0.25f); }
+#ifdef ORACLE_WITH_QUAD
+template<> inline __float128 taylor_precision3<__float128>() { return powq(FLT128_EPSILON, 0.25Q); }
+#endif
 template<> inline long double taylor_precision3<long double>() { return powl(std::numeric_limits<long double>::epsilon(), 0.25L); }
 
 // Eigen::Quaternion operator* (Eigen/src/Geometry/Quaternion.h, quat_product)

@@ -16,8 +16,8 @@
 namespace brbd
 {
 
-constexpr int MAXJ = 48;     // joints including the universe
-constexpr int MAXNV = 48;    // tangent dimension
+constexpr int MAXJ = 64;     // joints including the universe
+constexpr int MAXNV = 64;    // tangent dimension
 constexpr int MAXDEPTH = 16; // tree depth (universe = 0)
 
 enum JointTag : int { J_RX = 0, J_RY = 1, J_RZ = 2, J_PX = 3, J_PY = 4, J_PZ = 5, J_FF = 6, J_SPH = 7, J_PLANAR = 8 };

@@ -290,5 +290,24 @@ brbd_status launch_minverse(brbd_pool * p, DeviceCtx & d, const T * q, int64_t l
 template<class T, bool EULER>
 brbd_status launch_integrate(brbd_pool * p, DeviceCtx & d, const T * q, int64_t ldq, const T * v, int64_t ldv, const T * a,
                              int64_t lda, T dt, T * qout, int64_t ldqo, T * vout, int64_t ldvo, int64_t B);
+// generic thread-local-state kernels (launch_v1.cu): fit any accepted model
+template<class T>
+brbd_status launch_rnea_v1(brbd_pool * p, DeviceCtx & d, const T * q, int64_t ldq, const T * v, int64_t ldv, const T * a,
+                           int64_t lda, T * tau, int64_t ldtau, int64_t B);
+template<class T>
+brbd_status launch_aba_v1(brbd_pool * p, DeviceCtx & d, const T * q, int64_t ldq, const T * v, int64_t ldv, const T * tau,
+                          int64_t ldtau, T * a, int64_t lda, int64_t B);
+template<class T>
+brbd_status launch_crba_v1(brbd_pool * p, DeviceCtx & d, const T * q, int64_t ldq, T * Mout, int64_t ldM, int64_t B);
+template<class T>
+brbd_status launch_rnea_derivs_v1(brbd_pool * p, DeviceCtx & d, const T * q, int64_t ldq, const T * v, int64_t ldv,
+                                  const T * a, int64_t lda, T * dq, int64_t ld_dq, T * dv, int64_t ld_dv, T * da,
+                                  int64_t ld_da, T * tau, int64_t ldtau, int64_t B);
 brbd_status measure_fp64_peak(brbd_pool * p, double * flops_per_s, double * elapsed_ms);
+// BRBD_<ALGO>_V=<name> forces one device path of an algorithm (tests, experiments)
+inline bool forced_path(const char * var, const char * name)
+{
+  const char * e = std::getenv(var);
+  return e && std::strcmp(e, name) == 0;
+}
 } // namespace brbd

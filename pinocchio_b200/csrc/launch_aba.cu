@@ -11,6 +11,8 @@ brbd_status launch_aba(brbd_pool * p, DeviceCtx & d, const T * q, int64_t ldq, c
 {
   const TreePOD<T> & t = tree_of<T>(p);
   brbd_status st = BRBD_OK;
+  const char * ver = std::getenv("BRBD_ABA_V"); // "v3" (aba_tmem_kernel), "dfs" (aba_dfs_kernel), "v1" (aba_kernel)
+  if (ver && std::strcmp(ver, "v1") == 0) return launch_aba_v1<T>(p, d, q, ldq, v, ldv, tau, ldtau, a, lda, B);
   {
     bool done = false;
     st = launch_aba_coop<T>(p, d, q, ldq, v, ldv, tau, ldtau, a, lda, B, &done);
@@ -18,7 +20,7 @@ brbd_status launch_aba(brbd_pool * p, DeviceCtx & d, const T * q, int64_t ldq, c
   }
   // preferred (v4): the backward sweep recomputes the per-depth quantities; (sin, cos, v) per depth and the branch slots in
   // tensor memory, only the pass-3 record ring in shared memory -> up to 8 warps per SM
-  if (!std::getenv("BRBD_ABA_V3"))
+  if (!ver)
   {
     const int wpv = (int)(sizeof(T) / 4);
     AbaRRLayout L = aba_rr_layout<T>(t.maxdepth, t.nbranch, 4);
@@ -60,9 +62,10 @@ brbd_status launch_aba(brbd_pool * p, DeviceCtx & d, const T * q, int64_t ldq, c
     }
   }
   // v3: per-depth (Y, f, a_bias) in tensor memory, J of the root path + branch slots in shared memory
+  if (!ver || std::strcmp(ver, "v3") == 0)
   {
     AbaTmemLayout L = aba_tmem_layout<T>(t.maxpathdof, t.maxdepth, t.nbranch, 4);
-    if (L.tvals * (int)(sizeof(T) / 4) <= 512)
+    if (L.tvals * (int)(sizeof(T) / 4) <= 512 && (size_t)32 * L.nstate * sizeof(T) <= (size_t)d.max_smem_optin)
     {
       const Geometry2 g = pick_geometry2(d, (size_t)L.nstate * sizeof(T), 0, B, 4, 1);
       L = aba_tmem_layout<T>(t.maxpathdof, t.maxdepth, t.nbranch, g.warps);
@@ -83,6 +86,8 @@ brbd_status launch_aba(brbd_pool * p, DeviceCtx & d, const T * q, int64_t ldq, c
   }
   // fallback for very deep trees: per-depth state in shared memory
   const AbaLayout L = aba_layout(t.maxdepth, t.nbranch);
+  if ((size_t)32 * L.nstate * sizeof(T) > (size_t)d.max_smem_optin) // not even one warp fits: generic kernel
+    return launch_aba_v1<T>(p, d, q, ldq, v, ldv, tau, ldtau, a, lda, B);
   const Geometry2 g = pick_geometry2(d, (size_t)L.nstate * sizeof(T), 0, B, 4, 2);
   // per-thread persistent store (J, a_bias, U Dinv, Dinv, u of every joint), [slot][thread]
   st = ensure_work(d, (size_t)g.grid * g.warps * 32 * (size_t)t.pslots * sizeof(T));

@@ -16,7 +16,7 @@ brbd_status launch_aba_derivs(brbd_pool * p, DeviceCtx & d, const T * q, int64_t
     const AbaCoopLayout L = aba_coop_layout(M.nq, M.nv, M.njoints, G);
     const size_t static_bytes = sizeof(ModelPOD<T>) + sizeof(CoopTables) + 1024;
     const GeometryCoop g = pick_geometry_coop(d, (size_t)L.per_group * sizeof(T), G, static_bytes, B);
-    if (p->model.coop.nbranch <= A_MAXBRANCH && g.dyn_bytes + static_bytes <= (size_t)d.max_smem_optin + 1024)
+    if (!forced_path("BRBD_DABA_V", "v1") && p->model.coop.nbranch <= A_MAXBRANCH && g.dyn_bytes + static_bytes <= (size_t)d.max_smem_optin + 1024)
     {
       brbd_status st = BRBD_OK;
 #define BRBD_LAUNCH_COOP(GG)                                                                                     \

@@ -57,17 +57,19 @@ brbd_status launch_crba(brbd_pool * p, DeviceCtx & d, const T * q, int64_t ldq, 
   const TreePOD<T> & t = tree_of<T>(p);
   if (ldM >= (int64_t(1) << 25)) return fail(BRBD_EINVAL, "crba: leading dimension of M too large");
   brbd_status st = BRBD_OK;
+  const char * ver = std::getenv("BRBD_CRBA_V"); // "tmem" (LSU emitter), "dfs" (crba_dfs_kernel), "v1" (crba_kernel)
+  if (ver && std::strcmp(ver, "v1") == 0) return launch_crba_v1<T>(p, d, q, ldq, Mout, ldM, B);
   // preferred: oYcrb / oMi stacks in tensor memory (<= 8 warps per CTA, one CTA per SM)
+  if (!(ver && std::strcmp(ver, "dfs") == 0))
   {
     const int wpv = (int)(sizeof(T) / 4);
     CrbaTmemLayout L = crba_tmem_layout<T>(t.maxpathdof, t.maxdepth, t.nbranch, t.nv, 4, t.ffroot);
     const int cols_per_slice = L.tvals * wpv;
     const int max_warps_tmem = cols_per_slice <= 256 ? 8 : (cols_per_slice <= 512 ? 4 : 0);
-    if (max_warps_tmem > 0)
+    if (max_warps_tmem > 0 && (size_t)32 * (L.nstate + L.epad + 2) * sizeof(T) + 128 * (size_t)t.nv + 64 <= (size_t)d.max_smem_optin)
     {
       // default: column blocks leave through TMA tensor stores (crba_tma_kernel) where the caller's layout allows a tensor
       // map (see crba_dfs.cuh); BRBD_CRBA_V=tmem keeps the LSU emitter
-      const char * ver = std::getenv("BRBD_CRBA_V");
       CrbaTmaGeom G{0, 0, 0};
       CUtensorMap map0, map1;
       const bool tma = !(ver && std::strcmp(ver, "tmem") == 0) && crba_tma_setup<T>(Mout, ldM, B, t.nv, G, map0, map1);
@@ -128,6 +130,8 @@ brbd_status launch_crba(brbd_pool * p, DeviceCtx & d, const T * q, int64_t ldq, 
   }
   // fallback for very deep trees: all state in shared memory
   const CrbaLayout L = crba_layout(t.maxpathdof, t.maxdepth, t.nbranch, t.nv);
+  if ((size_t)32 * (L.nstate + L.epad) * sizeof(T) + 128 * (size_t)t.nv > (size_t)d.max_smem_optin)
+    return launch_crba_v1<T>(p, d, q, ldq, Mout, ldM, B);
   const Geometry2 g = pick_geometry2(d, (size_t)L.nstate * sizeof(T), (size_t)32 * L.epad * sizeof(T) + 128 * t.nv, B, 4, 2);
 #define BRBD_LAUNCH(NT)                                                                              \
   {                                                                                                  \

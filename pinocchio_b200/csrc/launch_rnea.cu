@@ -9,6 +9,7 @@ brbd_status launch_rnea(brbd_pool * p, DeviceCtx & d, const T * q, int64_t ldq, 
                         int64_t lda, T * tau, int64_t ldtau, int64_t B)
 {
   const TreePOD<T> & t = tree_of<T>(p);
+  if (forced_path("BRBD_RNEA_V", "v1")) return launch_rnea_v1<T>(p, d, q, ldq, v, ldv, a, lda, tau, ldtau, B);
   if (B <= coop_max_batch(false, p->model.pd.nv))
   {
     const ModelPOD<double> & M = p->model.pd;
@@ -38,6 +39,8 @@ brbd_status launch_rnea(brbd_pool * p, DeviceCtx & d, const T * q, int64_t ldq, 
   const RneaLayout L = rnea_layout(t.maxdepth, t.nbranch);
   // one CTA per SM, up to 8 warps, chosen by the number of rounds (as CRBA)
   const size_t per_warp = (size_t)32 * L.nstate * sizeof(T);
+  if (per_warp > (size_t)d.max_smem_optin) // deeper / more branched than one warp's shared-memory state allows
+    return launch_rnea_v1<T>(p, d, q, ldq, v, ldv, a, lda, tau, ldtau, B);
   int warps = (int)std::max<size_t>(1, std::min<size_t>(8, (size_t)d.max_smem_optin / per_warp));
   warps = pick_warps_by_rounds(d, B, warps);
   if (const char * e = std::getenv("BRBD_RNEA_WARPS")) warps = std::max(1, std::min(warps, std::atoi(e)));

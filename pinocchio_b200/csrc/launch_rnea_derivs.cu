@@ -13,8 +13,9 @@ brbd_status launch_rnea_derivs(brbd_pool * p, DeviceCtx & d, const T * q, int64_
   const int G = coop_group_size(M.nv);
   const size_t static_bytes = sizeof(ModelPOD<T>) + sizeof(CoopTables) + 1024;
   const GeometryCoop g = pick_geometry_coop(d, (size_t)L.per_group * sizeof(T), G, static_bytes, B);
-  if (g.dyn_bytes + static_bytes > (size_t)d.max_smem_optin + 1024)
-    return fail(BRBD_EINVAL, "computeRNEADerivatives: model too large for the shared-memory state of one configuration");
+  // models whose per-configuration state does not fit the cooperative layout run the generic kernel
+  if (g.dyn_bytes + static_bytes > (size_t)d.max_smem_optin + 1024 || forced_path("BRBD_DRNEA_V", "v1"))
+    return launch_rnea_derivs_v1<T>(p, d, q, ldq, v, ldv, a, lda, dq, ld_dq, dv, ld_dv, da, ld_da, tau, ldtau, B);
   brbd_status st = BRBD_OK;
 #define BRBD_LAUNCH_COOP(GG)                                                                                     \
   {                                                                                                              \

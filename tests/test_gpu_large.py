@@ -1,0 +1,240 @@
+"""GPU parity at the BASELINE.json batch sizes, through device pointers, against the OpenMP oracle.
+
+* C2 (configs[1]): ABA + CRBA on 65 536 configurations of simple_humanoid + free-flyer — EVERY column is compared.
+* C3 (configs[2]): computeRNEADerivatives + computeABADerivatives on 2^20 configurations of the 6-dof manipulator —
+  first 2 048 + 2 048 random + the last columns.
+* C4 (configs[3]): RNEA / ABA on 4 * 2^20 and CRBA on 2^20 configurations of talos (free-flyer + 32 revolute), sampled alike.
+* every one-configuration-per-thread kernel over more than one round of its persistent grid (148 CTAs x <= 256 threads).
+* every device path of every algorithm forced once (BRBD_*_V): the fallbacks must match the oracle too.
+* a 58-dof model beyond the on-chip layouts of the tuned kernels.
+
+Mirrors unittest/parallel-rnea.cpp:21-55 / parallel-aba.cpp:21-55 (batched == serial per column) at the sizes the
+benchmark runs.
+"""
+import numpy as np
+import pytest
+
+from conftest import assert_close, load_model, make_extra_models, random_inputs
+
+pytestmark = pytest.mark.gpu
+
+
+def to_dev(*xs):
+    import torch
+    return tuple(torch.from_numpy(np.ascontiguousarray(x.T)).cuda() for x in xs)
+
+
+def to_host(t):
+    return np.ascontiguousarray(t.cpu().numpy()).T
+
+
+@pytest.fixture(scope="module")
+def ctx(oracle_cls):
+    import pinocchio_b200 as pb
+    extra = make_extra_models()
+    cache = {}
+
+    def get(name):
+        if name not in cache:
+            model = extra[name] if name in extra else load_model(name)
+            cache[name] = (model, pb.ModelPool(model, [0]), oracle_cls(model))
+        return cache[name]
+    yield get
+    for _, pool, _ in cache.values():
+        pool.close()
+
+
+def sample_columns(B, seed):
+    rng = np.random.default_rng(seed)
+    head = np.arange(min(2048, B))
+    mid = rng.choice(B, size=min(2048, B), replace=False)
+    return np.unique(np.concatenate([head, mid, np.arange(max(0, B - 33), B)]))
+
+
+def test_bench_config_parity(ctx):
+    """BASELINE configs[1] exactly as bench.py runs it: 65 536 x simple_humanoid + FF, ABA then CRBA, FP64, device
+    pointers; all 65 536 columns against the oracle."""
+    import torch
+    import pinocchio_b200 as pb
+    model, pool, orc = ctx("simple_humanoid_ff")
+    B = 65536
+    q, v, tau = random_inputs(model, B, 2024)
+    tq, tv, tt = to_dev(q, v, tau)
+    a = pb.abaInParallel(1, pool, tq, tv, tt)
+    ref = orc.aba(q, v, tau)
+    scale = np.abs(ref).max(axis=0, keepdims=True)
+    assert_close(to_host(a), ref, rtol=1e-10, atol=1e-12 + 1e-10 * scale, what="aba C2 simple_humanoid_ff B=65536 (all columns)")
+    M = pb.crbaInParallel(1, pool, tq)
+    torch.cuda.synchronize()
+    for c0 in range(0, B, 8192):  # the dense reference is 642 MB: compare in slabs
+        refM = orc.crba(np.asfortranarray(q[:, c0:c0 + 8192]), world=True)
+        got = to_host(M[c0:c0 + 8192])
+        assert_close(got, refM, rtol=1e-10, atol=1e-12 + 1e-12 * np.abs(refM).max(axis=0, keepdims=True),
+                     what=f"crba C2 simple_humanoid_ff B=65536 columns {c0}..")
+        assert not got[refM == 0].any(), "entries outside the tree sparsity must be exact zeros"
+
+
+def test_c3_manipulator_derivatives_1M(ctx):
+    """BASELINE configs[2]: computeRNEADerivatives + computeABADerivatives, manipulator, 2^20 configurations."""
+    import torch
+    import pinocchio_b200 as pb
+    model, pool, orc = ctx("manipulator")
+    B = 1 << 20
+    q, v, a = random_inputs(model, B, 31337)
+    tq, tv, ta = to_dev(q, v, a)
+    cols = sample_columns(B, 5)
+    qs, vs, as_ = (np.asfortranarray(x[:, cols]) for x in (q, v, a))
+    dq, dv, da, tau = pb.computeRNEADerivativesInParallel(1, pool, tq, tv, ta)
+    rdq, rdv, rda, rtau = orc.rnea_derivatives(qs, vs, as_)
+    tc = torch.from_numpy(cols).cuda()
+    for got, ref, nm in ((dq, rdq, "dtau_dq"), (dv, rdv, "dtau_dv"), (da, rda, "dtau_da"), (tau, rtau, "tau")):
+        scale = np.abs(ref).max(axis=0, keepdims=True)
+        assert_close(to_host(got[tc]), ref, rtol=1e-10, atol=1e-12 + 1e-11 * scale, what=f"{nm} C3 manipulator B=2^20 (sampled)")
+    del dq, dv, da
+    torch.cuda.empty_cache()
+    dq, dv, dtau, ddq = pb.computeABADerivativesInParallel(1, pool, tq, tv, ta)
+    rdq, rdv, rdtau, rddq = orc.aba_derivatives(qs, vs, as_)
+    for got, ref, nm in ((dq, rdq, "ddq_dq"), (dv, rdv, "ddq_dv"), (dtau, rdtau, "ddq_dtau"), (ddq, rddq, "ddq")):
+        scale = np.abs(ref).max(axis=0, keepdims=True)
+        assert_close(to_host(got[tc]), ref, rtol=1e-10, atol=1e-12 + 1e-10 * scale, what=f"{nm} C3 manipulator B=2^20 (sampled)")
+
+
+def test_c4_talos_4M(ctx):
+    """BASELINE configs[3] on one GPU: talos (free-flyer + 32 revolute), RNEA / ABA on 4 * 2^20 configurations, CRBA on 2^20."""
+    import torch
+    import pinocchio_b200 as pb
+    model, pool, orc = ctx("talos_reduced_ff")
+    B = 4 << 20
+    q, v, a = random_inputs(model, B, 4242)
+    tq, tv, ta = to_dev(q, v, a)
+    cols = sample_columns(B, 6)
+    tc = torch.from_numpy(cols).cuda()
+    qs, vs, as_ = (np.asfortranarray(x[:, cols]) for x in (q, v, a))
+    tau = pb.rneaInParallel(1, pool, tq, tv, ta)
+    assert_close(to_host(tau[tc]), orc.rnea(qs, vs, as_), what="rnea C4 talos B=4*2^20 (sampled)")
+    ddq = pb.abaInParallel(1, pool, tq, tv, ta)
+    ref = orc.aba(qs, vs, as_)
+    assert_close(to_host(ddq[tc]), ref, rtol=1e-10, atol=1e-12 + 1e-10 * np.abs(ref).max(axis=0, keepdims=True),
+                 what="aba C4 talos B=4*2^20 (sampled)")
+    del tau, ddq
+    B2 = 1 << 20
+    M = pb.crbaInParallel(1, pool, tq[:B2])
+    cols2 = sample_columns(B2, 7)
+    refM = orc.crba(np.asfortranarray(q[:, cols2]), world=True)
+    assert_close(to_host(M[torch.from_numpy(cols2).cuda()]), refM, rtol=1e-10,
+                 atol=1e-12 + 1e-12 * np.abs(refM).max(axis=0, keepdims=True), what="crba C4 talos B=2^20 (sampled)")
+
+
+@pytest.mark.parametrize("name", ["manipulator", "humanoid_random", "mixed"])
+def test_persistent_grid_rounds(ctx, name, monkeypatch):
+    """More than two rounds of the persistent grid (148 CTAs x <= 256 threads) with a ragged tail, for every
+    one-configuration-per-thread kernel; all columns compared."""
+    import pinocchio_b200 as pb
+    model, pool, orc = ctx(name)
+    monkeypatch.setenv("BRBD_COOP_MAX_BATCH", "0")
+    B = 148 * 256 * 2 + 1234 + 7
+    q, v, a = random_inputs(model, B, 99)
+    tq, tv, ta = to_dev(q, v, a)
+    assert_close(to_host(pb.rneaInParallel(1, pool, tq, tv, ta)), orc.rnea(q, v, a), what=f"rnea rounds {name} B={B}")
+    ref = orc.aba(q, v, a)
+    assert_close(to_host(pb.abaInParallel(1, pool, tq, tv, ta)), ref, rtol=1e-10,
+                 atol=1e-12 + 1e-10 * np.abs(ref).max(axis=0, keepdims=True), what=f"aba rounds {name} B={B}")
+    refM = orc.crba(q, world=True)
+    assert_close(to_host(pb.crbaInParallel(1, pool, tq)), refM, rtol=1e-10,
+                 atol=1e-12 + 1e-12 * np.abs(refM).max(axis=0, keepdims=True), what=f"crba rounds {name} B={B}")
+    qn = to_host(pb.integrateInParallel(1, pool, tq, 0.25 * tv))
+    assert_close(qn, orc.integrate(q, 0.25 * v), what=f"integrate rounds {name} B={B}")
+
+
+FORCED = [("BRBD_ABA_V", "v3", "aba"), ("BRBD_ABA_V", "dfs", "aba"), ("BRBD_ABA_V", "v1", "aba"),
+          ("BRBD_CRBA_V", "tmem", "crba"), ("BRBD_CRBA_V", "dfs", "crba"), ("BRBD_CRBA_V", "v1", "crba"),
+          ("BRBD_RNEA_V", "v1", "rnea"), ("BRBD_DRNEA_V", "v1", "drnea"), ("BRBD_DABA_V", "v1", "daba")]
+
+
+@pytest.mark.parametrize("var,val,algo", FORCED)
+@pytest.mark.parametrize("name", ["simple_humanoid_ff", "mixed", "double_ff"])
+def test_forced_paths(ctx, name, var, val, algo, monkeypatch):
+    """Every fallback kernel the launch code can pick is forced once and must match the oracle like the default path."""
+    import pinocchio_b200 as pb
+    model, pool, orc = ctx(name)
+    monkeypatch.setenv("BRBD_COOP_MAX_BATCH", "0")
+    monkeypatch.setenv(var, val)
+    B = 300
+    q, v, a = random_inputs(model, B, 17)
+    n0 = pool.launch_count()
+    if algo == "rnea":
+        assert_close(pb.rneaInParallel(1, pool, q, v, a), orc.rnea(q, v, a), what=f"rnea[{val}] {name}")
+    elif algo == "aba":
+        ref = orc.aba(q, v, a)
+        assert_close(pb.abaInParallel(1, pool, q, v, a), ref, rtol=1e-10,
+                     atol=1e-12 + 1e-10 * np.abs(ref).max(axis=0, keepdims=True), what=f"aba[{val}] {name}")
+    elif algo == "crba":
+        refM = orc.crba(q, world=True)
+        M = pb.crbaInParallel(1, pool, q)
+        assert_close(M, refM, rtol=1e-10, atol=1e-12 + 1e-12 * np.abs(refM).max(axis=0, keepdims=True), what=f"crba[{val}] {name}")
+        assert not M[refM == 0].any()
+    elif algo == "drnea":
+        got = pb.computeRNEADerivativesInParallel(1, pool, q, v, a)
+        for g, r, nm in zip(got, orc.rnea_derivatives(q, v, a), ("dtau_dq", "dtau_dv", "dtau_da", "tau")):
+            assert_close(g, r, rtol=1e-10, atol=1e-12 + 1e-11 * np.abs(r).max(axis=0, keepdims=True), what=f"{nm}[{val}] {name}")
+    else:
+        got = pb.computeABADerivativesInParallel(1, pool, q, v, a)
+        for g, r, nm in zip(got, orc.aba_derivatives(q, v, a), ("ddq_dq", "ddq_dv", "ddq_dtau", "ddq")):
+            assert_close(g, r, rtol=1e-10, atol=1e-12 + 1e-10 * np.abs(r).max(axis=0, keepdims=True), what=f"{nm}[{val}] {name}")
+    assert pool.launch_count() > n0
+
+
+def test_model_beyond_the_on_chip_layouts(ctx):
+    """humanoid_hands: 54 joints, nv = 58, depth 14, three branching joints on one root path.  Every entry point must
+    accept it (round 1 refused nv > 48 and returned EINVAL from the cooperative derivative kernels)."""
+    import pinocchio_b200 as pb
+    model, pool, orc = ctx("humanoid_hands")
+    for B, coop in ((1, "1000000"), (97, "0"), (97, "1000000")):
+        import os
+        os.environ["BRBD_COOP_MAX_BATCH"] = coop
+        try:
+            q, v, a = random_inputs(model, B, 23)
+            tau = pb.rneaInParallel(1, pool, q, v, a)
+            assert_close(tau, orc.rnea(q, v, a), atol=1e-12 * max(1.0, np.abs(tau).max()), what=f"rnea humanoid_hands B={B}")
+            ref = orc.aba(q, v, tau)
+            assert_close(pb.abaInParallel(1, pool, q, v, tau), ref, rtol=1e-10, atol=1e-12 + 1e-10 * np.abs(ref).max(),
+                         what=f"aba humanoid_hands B={B}")
+        finally:
+            del os.environ["BRBD_COOP_MAX_BATCH"]
+    q, v, a = random_inputs(model, 40, 29)
+    refM = orc.crba(q, world=True)
+    assert_close(pb.crbaInParallel(1, pool, q), refM, rtol=1e-10, atol=1e-12 + 1e-12 * np.abs(refM).max(), what="crba humanoid_hands")
+    for g, r, nm in zip(pb.computeRNEADerivativesInParallel(1, pool, q, v, a), orc.rnea_derivatives(q, v, a),
+                        ("dtau_dq", "dtau_dv", "dtau_da", "tau")):
+        assert_close(g, r, rtol=1e-10, atol=1e-12 + 1e-11 * np.abs(r).max(), what=f"{nm} humanoid_hands")
+    tau = orc.rnea(q, v, a)
+    for g, r, nm in zip(pb.computeABADerivativesInParallel(1, pool, q, v, tau), orc.aba_derivatives(q, v, tau),
+                        ("ddq_dq", "ddq_dv", "ddq_dtau", "ddq")):
+        assert_close(g, r, rtol=1e-10, atol=1e-12 + 1e-10 * np.abs(r).max(), what=f"{nm} humanoid_hands")
+    mref = orc.minverse(q)
+    assert_close(pb.computeMinverseInParallel(1, pool, q), mref, atol=1e-12 + 1e-10 * np.abs(mref).max(), what="Minv humanoid_hands")
+    assert_close(pb.integrateInParallel(1, pool, q, 0.3 * v), orc.integrate(q, 0.3 * v), what="integrate humanoid_hands")
+
+
+def test_fp32_solves_tolerance(ctx):
+    """FP32 mode of the solves: the stated tolerance, measured as max |err| / max |ref| against the FP64 oracle.
+    ABA / computeABADerivatives lose three more digits than the products on talos (worst-conditioned joint-space inertia of the
+    config models): 9e-5 / 3.3e-4 measured; asserted at 5e-4 / 2e-3.  humanoid_random: 2.1e-6 / 2.4e-6 -> 2e-5."""
+    import pinocchio_b200 as pb
+    for name, tol_aba, tol_d in (("talos_reduced_ff", 5e-4, 2e-3), ("humanoid_random", 2e-5, 2e-5)):
+        model, pool, orc = ctx(name)
+        q, v, tau = random_inputs(model, 256, 87)
+        f = lambda x: np.asfortranarray(x.astype(np.float32))
+        a32 = pb.abaInParallel(1, pool, f(q), f(v), f(tau))
+        ref = orc.aba(q, v, tau)
+        assert a32.dtype == np.float32
+        rel = np.abs(a32 - ref).max() / np.abs(ref).max()
+        assert rel < tol_aba, (name, rel)
+        got = pb.computeABADerivativesInParallel(1, pool, f(q), f(v), f(tau))
+        for g, r, nm in zip(got, orc.aba_derivatives(q, v, tau), ("ddq_dq", "ddq_dv", "ddq_dtau", "ddq")):
+            rel = np.abs(g - r).max() / np.abs(r).max()
+            assert rel < tol_d, (name, nm, rel)
+        got = pb.computeRNEADerivativesInParallel(1, pool, f(q), f(v), f(tau))
+        for g, r, nm in zip(got, orc.rnea_derivatives(q, v, tau), ("dtau_dq", "dtau_dv", "dtau_da", "tau")):
+            rel = np.abs(g - r).max() / np.abs(r).max()
+            assert rel < 5e-5, (name, nm, rel)
