@@ -1,17 +1,23 @@
 #!/usr/bin/env python
 """bench.py — headline benchmark of the batched-dynamics hot path (BASELINE.json metric).
 
-A "step" is one pass of the hot path over one batch of synthetic input.  Workload at every N
-(weak scaling, per-GPU work fixed): BASELINE.json configs[1] —
-    ABA + CRBA on a batch of 65536 configurations of simple_humanoid.urdf + free-flyer, FP64
-(one eval = one configuration through one algorithm, so one step = 2 * 65536 evals per GPU).
+A "step" is one pass of the hot path over one batch of synthetic input: every algorithm of the chosen
+configuration once.  One eval = one configuration through one algorithm.
+
+    --config C2 (default)  BASELINE.json configs[1]: ABA + CRBA, 65 536 x simple_humanoid.urdf + free-flyer, FP64
+    --config C3            configs[2]: computeRNEADerivatives + computeABADerivatives, 2^20 x manipulator (6-dof)
+    --config C4            configs[3]: RNEA + ABA + CRBA, 4 * 2^20 x talos (free-flyer + 32 revolute)
+    --scaling weak|strong  weak (default for C2 / C3): the batch above is PER GPU; strong (default for C4): the batch
+                           above is the whole job, sharded over the ranks in contiguous column ranges
+                           (reference benchmark being mirrored: benchmark/timings-parallel.cpp:38-64,81-112)
 
     python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
     python bench.py --impl reference --gpus N ...             # CPU arm: the OpenMP restatement of
-                                                              # rneaInParallel/abaInParallel (oracle/)
-Prints ONE JSON line (rank 0).  `value` = device-resident throughput (inputs already in HBM, CUDA
-events on the launching stream, max over ranks); `e2e` = same metric through the public host-pointer
-API with pinned HOST buffers (H2D + kernels + D2H inside the timed region).
+                                                              # rneaInParallel/abaInParallel (oracle/), same batch
+Prints ONE JSON line (rank 0).  `value` = device-resident throughput (inputs already in HBM, CUDA events on the
+launching stream, max over ranks); `e2e` = same metric through the public host-pointer API with pinned HOST buffers
+(H2D + kernels + D2H inside the timed region).  No NCCL anywhere: the path has no exchange step; the barrier and the
+max-over-ranks of the timings go through a gloo group.
 """
 import argparse
 import json
@@ -27,14 +33,26 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
-MODEL = "simple_humanoid_ff"
-BATCH = 65536
 L2_BYTES = 126 * 1024 * 1024
-# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures
-# (profiles/r1_v8_step_ncu_full.csv: crba_tma_kernel<double,224,true> 47.3 MB read + 596.1 MB written; aba_rr_kernel<double,224>
-# 388.1 MB read + 426.1 MB written — the ABA figure is 11x its 74 MB of algorithmic bytes: the per-thread pass-3 record
-# store, 186 MB for a resident wave, does not stay L2-resident); bytes per launch of 65536 configurations
-NCU_TRAFFIC = {"crba": 643.4e6, "aba": 814.2e6}
+
+CONFIGS = {
+    "C2": {"model": "simple_humanoid_ff", "batch": 65536, "algos": ["aba", "crba"], "scaling": "weak",
+           "desc": "simple_humanoid.urdf + free-flyer, nq=36 nv=35"},
+    "C3": {"model": "manipulator", "batch": 1 << 20, "algos": ["rnea_derivatives", "aba_derivatives"], "scaling": "weak",
+           "desc": "buildModels::manipulator, 6-dof"},
+    "C4": {"model": "talos_reduced_ff", "batch": 4 << 20, "algos": ["rnea", "aba", "crba"], "scaling": "strong",
+           "desc": "talos_reduced.urdf + free-flyer (free-flyer + 32 revolute), nq=39 nv=38"},
+}
+ORACLE_KEY = {"rnea": "rnea", "aba": "aba", "crba": "crba_world", "rnea_derivatives": "rnea_derivatives",
+              "aba_derivatives": "aba_derivatives"}
+KERNEL_NAME = {"rnea": "rnea_dfs_kernel<double>", "aba": "aba_rr_kernel<double>", "crba": "crba_tma_kernel<double>",
+               "rnea_derivatives": "rnea_derivatives_coop_kernel<double>", "aba_derivatives": "aba_derivatives_coop_kernel<double>"}
+# dram__bytes_read.sum + dram__bytes_write.sum per launch, RECORDED from the committed `ncu --set full` capture named in
+# `source` (not measured in this run); only quoted for the exact configuration / batch of that capture, null otherwise.
+NCU_TRAFFIC = {
+    ("C2", 65536, "crba"): {"bytes": 643.4e6, "source": "profiles/r1_v8_step_ncu_full.csv (crba_tma_kernel<double,224,1>, commit 74f969d)"},
+    ("C2", 65536, "aba"): {"bytes": 814.2e6, "source": "profiles/r1_v8_step_ncu_full.csv (aba_rr_kernel<double,224>, commit 74f969d)"},
+}
 
 
 def load_model(name):
@@ -88,17 +106,20 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def algorithmic_numbers(model, orc):
-    """Per-configuration algorithmic bytes (exact) and FLOPs (counted by the oracle's
-    counting scalar on one random configuration)."""
+def algorithmic_numbers(model, orc, algos):
+    """Per-configuration algorithmic bytes (exact) and FLOPs: the operation count of the reference algorithm as
+    restated in the oracle, from a run with the counting scalar that does NOT count products / sums with the structural 0 / 1
+    of the joints' motion subspaces (the reference's specialised joints and the kernels never execute those)."""
     from conftest import random_inputs
     nq, nv = model.nq, model.nv
     q, v, a = random_inputs(model, 1, 3)
-    fl = {k: orc.count_flops(k, q[:, 0], v[:, 0], a[:, 0]) for k in ("aba", "crba_world")}
-    return {
-        "aba": {"bytes": 8 * (nq + 3 * nv), "flops": fl["aba"]["flops"], "sincos": fl["aba"]["sincos"]},
-        "crba": {"bytes": 8 * (nq + nv * nv), "flops": fl["crba_world"]["flops"], "sincos": fl["crba_world"]["sincos"]},
-    }
+    by = {"rnea": 8 * (nq + 3 * nv), "aba": 8 * (nq + 3 * nv), "crba": 8 * (nq + nv * nv),
+          "rnea_derivatives": 8 * (nq + 3 * nv + 3 * nv * nv), "aba_derivatives": 8 * (nq + 3 * nv + 3 * nv * nv)}
+    out = {}
+    for k in algos:
+        fl = orc.count_flops(ORACLE_KEY[k], q[:, 0], v[:, 0], a[:, 0])
+        out[k] = {"bytes": by[k], "flops": fl["flops"], "sincos": fl["sincos"]}
+    return out
 
 
 def host_threads():
@@ -110,57 +131,107 @@ def host_threads():
         return max(1, os.cpu_count() or 1)
 
 
-def cpu_sample(orc, model, nthreads, target_s=12.0):
-    """ABA + CRBA with the OpenMP oracle on a bounded sample of the workload; returns (evals/s, sample size)."""
+def column_range(B, world, rank):
+    """Contiguous column range of `rank` (the split brbd's own multi-device pool uses)."""
+    per = (B + world - 1) // world
+    c0 = min(B, rank * per)
+    return c0, min(B, c0 + per)
+
+
+def oracle_outputs(orc, algos, n):
+    """Caller-owned output blocks of the CPU arm, allocated (and touched) once, as a caller of the reference reuses its Data."""
+    nv, nn = orc.nv, orc.nv * orc.nv
+    out = {}
+    for k in algos:
+        if k in ("rnea", "aba"):
+            out[k] = np.zeros((nv, n), order="F")
+        elif k == "crba":
+            out[k] = np.zeros((nn, n), order="F")
+        else:
+            out[k] = tuple(np.zeros((nn, n), order="F") for _ in range(3)) + (np.zeros((nv, n), order="F"),)
+    return out
+
+
+def oracle_step(orc, algos, q, v, x, nthreads, outs):
+    for k in algos:
+        if k == "rnea":
+            orc.rnea(q, v, x, nthreads=nthreads, out=outs[k])
+        elif k == "aba":
+            orc.aba(q, v, x, nthreads=nthreads, out=outs[k])
+        elif k == "crba":
+            orc.crba(q, nthreads=nthreads, world=True, out=outs[k])
+        elif k == "rnea_derivatives":
+            orc.rnea_derivatives(q, v, x, nthreads=nthreads, out=outs[k])
+        else:
+            orc.aba_derivatives(q, v, x, nthreads=nthreads, out=outs[k])
+
+
+def cpu_sample(orc, model, algos, B, nthreads, target_s=12.0):
+    """The step's algorithms with the OpenMP oracle on a bounded sample of the workload; (evals/s, sample size, seconds)."""
     from conftest import random_inputs
-    n = 2048
-    q, v, tau = random_inputs(model, n, 77)
+    n = min(B, 2048)
+    q, v, x = random_inputs(model, n, 77)
+    outs = oracle_outputs(orc, algos, n)
+    oracle_step(orc, algos, q, v, x, nthreads, outs)  # warm-up
     t0 = time.perf_counter()
-    orc.aba(q, v, tau, nthreads=nthreads)
-    orc.crba(q, nthreads=nthreads, world=True)
+    oracle_step(orc, algos, q, v, x, nthreads, outs)
     probe = time.perf_counter() - t0
-    n2 = int(min(BATCH, max(n, n * target_s / max(probe, 1e-6))))
-    q, v, tau = random_inputs(model, n2, 78)
-    orc.aba(q[:, :256], v[:, :256], tau[:, :256], nthreads=nthreads)  # warm-up
+    n2 = int(min(B, max(n, n * target_s / max(probe, 1e-6))))
+    q, v, x = random_inputs(model, n2, 78)
+    outs = oracle_outputs(orc, algos, n2)
     t0 = time.perf_counter()
-    orc.aba(q, v, tau, nthreads=nthreads)
-    orc.crba(q, nthreads=nthreads, world=True)
+    oracle_step(orc, algos, q, v, x, nthreads, outs)
     dt = time.perf_counter() - t0
-    return 2.0 * n2 / dt, n2, dt
+    return len(algos) * n2 / dt, n2, dt
 
 
-def run_reference(args):
-    """CPU arm: the restated reference path (oracle port) with all host threads, bounded sample per step."""
+def workload_text(cfg_name, cfg, B_rank, world, scaling):
+    total = B_rank * world if scaling == "weak" else cfg["batch"]
+    return (f"{cfg_name}: {' + '.join(cfg['algos'])} on {total} configurations "
+            f"({B_rank} per GPU x {world} GPU(s), {scaling} scaling) of {cfg['model']} ({cfg['desc']}), FP64; "
+            f"one eval = one configuration through one algorithm")
+
+
+def run_reference(args, cfg_name, cfg, scaling):
+    """CPU arm: the restated reference path (oracle port) with all host threads on the SAME batch as the GPU arm's rank 0,
+    after a warm-up of at least 3 s (benchmark/timings-parallel.cpp:103)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     from oracle import Oracle, build_oracle
     build_oracle()
-    model = load_model(MODEL)
+    model = load_model(cfg["model"])
     orc = Oracle(model)
     nthreads = host_threads()
     from conftest import random_inputs
-    n = 4096
-    q, v, tau = random_inputs(model, n, 5)
+    world = max(1, args.gpus)
+    B = args.batch or cfg["batch"]
+    n = B if scaling == "weak" else (column_range(B, world, 0)[1] - column_range(B, world, 0)[0])
+    algos = cfg["algos"]
+    q, v, x = random_inputs(model, n, 5)
+    outs = oracle_outputs(orc, algos, n)
+    t_w, nwarm = time.perf_counter(), 0
+    while nwarm < args.warmup or time.perf_counter() - t_w < 3.0:
+        oracle_step(orc, algos, q, v, x, nthreads, outs)
+        nwarm += 1
     times = []
-    for s in range(args.warmup + args.steps):
+    for s in range(args.steps):
         t0 = time.perf_counter()
-        orc.aba(q, v, tau, nthreads=nthreads)
-        orc.crba(q, nthreads=nthreads, world=True)
-        dt = time.perf_counter() - t0
-        if s >= args.warmup:
-            times.append(dt)
+        oracle_step(orc, algos, q, v, x, nthreads, outs)
+        times.append(time.perf_counter() - t0)
     ms = 1e3 * float(np.mean(times))
-    value = 2.0 * n / (ms * 1e-3)
+    value = len(algos) * n / (ms * 1e-3)
     line = {
-        "impl": "reference", "metric": "batched dynamics evals/sec (ABA + CRBA)", "value": value, "unit": "evals/s",
-        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"ABA + CRBA, {MODEL} (simple_humanoid.urdf + free-flyer, nq=36 nv=35), FP64; "
-                               f"CPU arm times a bounded sample of {n} configurations per step"},
+        "impl": "reference", "metric": f"batched dynamics evals/sec ({' + '.join(algos)})", "value": value, "unit": "evals/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": nwarm, "ms_per_step": ms, "higher_is_better": True,
+        "scaling": scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload_text(cfg_name, cfg, n, 1, "weak") + f"; CPU arm: the whole {n}-configuration batch of one "
+                                                                           f"GPU rank per step, {nthreads} OpenMP threads",
+                   "batch_per_gpu": n},
         "cpu_baseline": {"value": value, "unit": "evals/s", "cores": nthreads, "kind": "port",
-                         "sample": f"{n} configurations per step through ABA(WORLD) + CRBA(WORLD), OpenMP schedule(static), "
-                                   f"the restated rneaInParallel/abaInParallel driver (oracle/), {nthreads} threads"},
+                         "sample": f"{n} configurations per step (the full per-GPU batch) through {' + '.join(algos)}, OpenMP "
+                                   f"schedule(static), the restated rneaInParallel/abaInParallel driver (oracle/), {nthreads} threads, "
+                                   f"{nwarm} warm-up steps (>= 3 s)"},
         "e2e": {"value": value, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -173,12 +244,17 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=BATCH, help="configurations per GPU per step")
+    ap.add_argument("--config", default="C2", choices=sorted(CONFIGS))
+    ap.add_argument("--scaling", default=None, choices=["weak", "strong"])
+    ap.add_argument("--batch", type=int, default=0, help="override the configuration's batch (per GPU if weak, total if strong)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end leg")
     args = ap.parse_args()
-    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    cfg_name, cfg = args.config, CONFIGS[args.config]
+    scaling = args.scaling or cfg["scaling"]
+    args.warmup = max(args.warmup, 3)
     if args.impl == "reference":
-        return run_reference(args)
+        return run_reference(args, cfg_name, cfg, scaling)
 
     import torch
     import pinocchio_b200 as pb
@@ -191,42 +267,72 @@ def main():
     if world > 1:
         import torch.distributed as dist
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        torch.cuda.set_device(local_rank)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        dist.init_process_group("gloo")  # barrier + max of three timings; the data path has no collective
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
 
-    model = load_model(MODEL)
-    nq, nv, B = model.nq, model.nv, args.batch
+    model = load_model(cfg["model"])
+    algos = cfg["algos"]
+    nq, nv = model.nq, model.nv
+    Btot = args.batch or cfg["batch"]
+    if scaling == "weak":
+        B, c0 = Btot, 0
+    else:
+        c0, c1 = column_range(Btot, world, rank)
+        B = c1 - c0
     pool = pb.ModelPool(model, [local_rank])
     stream = torch.cuda.current_stream()
     pool.set_stream(stream.cuda_stream)
 
-    # Rotating input sets so that consecutive steps never find their inputs in L2 (126 MB):
+    # Rotating input sets so that consecutive steps never find their inputs in L2 (126 MB); one set when a single one
+    # is already larger than L2
     in_bytes = 8 * B * (nq + 2 * nv)
-    nsets = max(2, int(np.ceil(2.5 * L2_BYTES / in_bytes)))
+    nsets = max(2, int(np.ceil(2.5 * L2_BYTES / in_bytes))) if in_bytes < 2 * L2_BYTES else 1
     sets = []
     for s in range(nsets):
-        q, v, tau = random_inputs(model, B, 1000 * rank + 10 * s)
-        sets.append(tuple(torch.from_numpy(np.ascontiguousarray(x.T)).to(dev) for x in (q, v, tau)))
-    a_out = torch.empty((B, nv), dtype=torch.float64, device=dev)
-    M_out = torch.empty((B, nv * nv), dtype=torch.float64, device=dev)
+        q, v, x = random_inputs(model, B, 1000 * rank + 10 * s + (c0 % 9973))
+        sets.append(tuple(torch.from_numpy(np.ascontiguousarray(t.T)).to(dev) for t in (q, v, x)))
+    outs = {}
+    for k in algos:
+        if k in ("rnea", "aba"):
+            outs[k] = (torch.empty((B, nv), dtype=torch.float64, device=dev),)
+        elif k == "crba":
+            outs[k] = (torch.empty((B, nv * nv), dtype=torch.float64, device=dev),)
+        else:
+            outs[k] = tuple(torch.empty((B, nv * nv), dtype=torch.float64, device=dev) for _ in range(3)) + \
+                      (torch.empty((B, nv), dtype=torch.float64, device=dev),)
+
+    def launch(k, q, v, x):
+        if k == "rnea":
+            pb.rneaInParallel(1, pool, q, v, x, outs[k][0], async_=True)
+        elif k == "aba":
+            pb.abaInParallel(1, pool, q, v, x, outs[k][0], async_=True)
+        elif k == "crba":
+            pb.crbaInParallel(1, pool, q, outs[k][0], async_=True)
+        elif k == "rnea_derivatives":
+            pb.computeRNEADerivativesInParallel(1, pool, q, v, x, *outs[k], async_=True)
+        else:
+            pb.computeABADerivativesInParallel(1, pool, q, v, x, *outs[k], async_=True)
 
     def step(i, ev=None):
-        q, v, tau = sets[i % nsets]
+        q, v, x = sets[i % nsets]
+        for n, k in enumerate(algos):
+            if ev is not None:
+                ev[n].record(stream)
+            launch(k, q, v, x)
         if ev is not None:
-            ev[0].record(stream)
-        pb.abaInParallel(1, pool, q, v, tau, a_out, async_=True)
-        if ev is not None:
-            ev[1].record(stream)
-        pb.crbaInParallel(1, pool, q, M_out, async_=True)
-        if ev is not None:
-            ev[2].record(stream)
+            ev[len(algos)].record(stream)
 
     def barrier():
         if dist is not None:
             dist.barrier()
         torch.cuda.synchronize()
+
+    def max_over_ranks(vals):
+        t = torch.tensor(vals, dtype=torch.float64)
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return [float(x) for x in t]
 
     for i in range(args.warmup):
         step(i)
@@ -236,7 +342,7 @@ def main():
         sampler.start()
         time.sleep(0.3)
     launches0 = pool.launch_count()
-    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(len(algos) + 1)] for _ in range(args.steps)]
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record(stream)
@@ -247,98 +353,118 @@ def main():
     launches = pool.launch_count() - launches0
     total_ms = e0.elapsed_time(e1)
     clocks = sampler.stop() if sampler else None
-    aba_ms = float(np.mean([e[0].elapsed_time(e[1]) for e in evs]))
-    crba_ms = float(np.mean([e[1].elapsed_time(e[2]) for e in evs]))
-    t = torch.tensor([total_ms, aba_ms, crba_ms], dtype=torch.float64, device=dev)
-    if dist is not None:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms, aba_ms, crba_ms = (float(x) for x in t.cpu())
+    algo_ms = [float(np.mean([e[n].elapsed_time(e[n + 1]) for e in evs])) for n in range(len(algos))]
+    red = max_over_ranks([total_ms] + algo_ms)
+    total_ms, algo_ms = red[0], red[1:]
     ms_per_step = total_ms / args.steps
-    value = 2.0 * B * world / (ms_per_step * 1e-3)
+    evals_per_step = len(algos) * (B * world if scaling == "weak" else Btot)
+    value = evals_per_step / (ms_per_step * 1e-3)
 
     # ---- end to end through the public API with pinned HOST buffers (H2D + kernels + D2H timed) ----
-    pool.set_stream(None)
-    e2e_steps = max(3, min(args.steps, 5))
-    hq, hv, ht = (torch.from_numpy(np.ascontiguousarray(x.cpu().numpy())).pin_memory() for x in sets[0])
-    ha = torch.empty((B, nv), dtype=torch.float64).pin_memory()
-    hM = torch.empty((B, nv * nv), dtype=torch.float64).pin_memory()
-    nq_, nv_ = nq, nv
-    hq_n, hv_n, ht_n, ha_n, hM_n = (x.numpy().T for x in (hq, hv, ht, ha, hM))  # (rows x B) column-major views
+    e2e = None
+    if not args.no_e2e:
+        pool.set_stream(None)
+        out_rows = {"rnea": nv, "aba": nv, "crba": nv * nv, "rnea_derivatives": 3 * nv * nv + nv, "aba_derivatives": 3 * nv * nv + nv}
+        per_cfg_out = 8 * sum(out_rows[k] for k in algos)
+        Be = int(min(B, max(4096, (6 << 30) // per_cfg_out)))  # host blocks capped at ~6 GB of pinned memory
+        e2e_steps = max(3, min(args.steps, 5))
+        hin = [torch.from_numpy(np.ascontiguousarray(t[:Be].cpu().numpy())).pin_memory() for t in sets[0]]
+        hq, hv, hx = (t.numpy().T for t in hin)
+        houts = {k: [torch.empty(tuple(o[:Be].shape), dtype=torch.float64).pin_memory() for o in outs[k]] for k in algos}
+        hviews = {k: [t.numpy().T for t in houts[k]] for k in algos}
 
-    def e2e_step():
-        pb.abaInParallel(1, pool, hq_n, hv_n, ht_n, ha_n)
-        pb.crbaInParallel(1, pool, hq_n, hM_n)
-        return float(ha_n[0, 0]) + float(hM_n[0, 0])
+        def e2e_step():
+            acc = 0.0
+            for k in algos:
+                o = hviews[k]
+                if k == "rnea":
+                    pb.rneaInParallel(1, pool, hq, hv, hx, o[0])
+                elif k == "aba":
+                    pb.abaInParallel(1, pool, hq, hv, hx, o[0])
+                elif k == "crba":
+                    pb.crbaInParallel(1, pool, hq, o[0])
+                elif k == "rnea_derivatives":
+                    pb.computeRNEADerivativesInParallel(1, pool, hq, hv, hx, *o)
+                else:
+                    pb.computeABADerivativesInParallel(1, pool, hq, hv, hx, *o)
+                acc += float(o[0][0, 0])
+            return acc
 
-    e2e_step()
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
         e2e_step()
-    barrier()
-    e2e_s = time.perf_counter() - t0
-    tt = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-    if dist is not None:
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-    e2e_s = float(tt.cpu()[0])
-    e2e_value = 2.0 * B * world * e2e_steps / e2e_s
-    h2d = 8 * B * ((nq + 2 * nv) + nq)   # ABA inputs + CRBA input
-    d2h = 8 * B * (nv + nv * nv)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            e2e_step()
+        barrier()
+        e2e_s = max_over_ranks([time.perf_counter() - t0])[0]
+        in_rows = {"rnea": nq + 2 * nv, "aba": nq + 2 * nv, "crba": nq, "rnea_derivatives": nq + 2 * nv, "aba_derivatives": nq + 2 * nv}
+        e2e = {"value": len(algos) * Be * world * e2e_steps / e2e_s, "unit": "evals/s",
+               "h2d_bytes_per_step": int(8 * Be * sum(in_rows[k] for k in algos)),
+               "d2h_bytes_per_step": int(Be * per_cfg_out), "steps": e2e_steps, "batch_per_gpu": Be,
+               "note": "pinned host buffers -> brbd_*_batch(BRBD_PTR_HOST): H2D + kernels + D2H, wall clock, max over ranks"
+                       + ("" if Be == B else f"; host blocks capped at {Be} configurations per GPU (6 GB of pinned memory)")}
 
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
         return
 
-    # ---- roofline of the dominant kernel + CPU baseline (rank 0) ----------------------------------
+    # ---- rooflines of the step's kernels + CPU baseline (rank 0) ----------------------------------
     from oracle import Oracle, build_oracle
     build_oracle()
     orc = Oracle(model)
-    alg = algorithmic_numbers(model, orc)
+    alg = algorithmic_numbers(model, orc, algos)
     hbm_peak, peak_src = measured_peaks()
     fp64_peak, _ = pool.measure_fp64_peak()
     kern = {}
-    for name, ms in (("aba", aba_ms), ("crba", crba_ms)):
+    step_sum = sum(algo_ms)
+    for name, ms in zip(algos, algo_ms):
         gbs = alg[name]["bytes"] * B / (ms * 1e-3) / 1e9
         tfl = alg[name]["flops"] * B / (ms * 1e-3) / 1e12
-        kern[name] = {"ms_per_launch": ms, "configs_per_s": B / (ms * 1e-3), "algorithmic_bytes_per_config": alg[name]["bytes"],
-                      "algorithmic_flops_per_config": alg[name]["flops"], "sincos_per_config": alg[name]["sincos"],
-                      "achieved_GBs": gbs, "hbm_frac": gbs / hbm_peak, "achieved_fp64_TFLOPs": tfl,
-                      "fp64_frac_of_measured_dfma_peak": tfl / (fp64_peak / 1e12)}
-    # The step has two kernels.  CRBA is HBM-bound (AI 1.5 flop/B) and is the kernel the `roofline` object (whose
-    # `bound` is "hbm" | "tensor") describes; ABA is bound by the FP64 pipe (AI 24 flop/B, no tensor cores on this
-    # path) and is reported against the measured DFMA peak under `fp64_roofline`.  `share_of_step` says how the
-    # step's time splits, so the dominant kernel can be read off either way.
-    kname = {"aba": "aba_rr_kernel<double>", "crba": "crba_tma_kernel<double>"}
-    roofline = {"bound": "hbm", "kernel": kname["crba"], "achieved": kern["crba"]["achieved_GBs"], "peak": hbm_peak,
-                "unit": "GB/s", "frac": kern["crba"]["hbm_frac"], "traffic": NCU_TRAFFIC.get("crba"), "peak_source": peak_src,
-                "share_of_step": crba_ms / (aba_ms + crba_ms)}
-    fp64_roofline = {"bound": "fp64", "kernel": kname["aba"], "achieved": kern["aba"]["achieved_fp64_TFLOPs"],
-                     "peak": fp64_peak / 1e12, "unit": "TFLOP/s", "frac": kern["aba"]["fp64_frac_of_measured_dfma_peak"],
-                     "traffic": NCU_TRAFFIC.get("aba"), "peak_source": "measured in this run (register-resident DFMA loop)",
-                     "share_of_step": aba_ms / (aba_ms + crba_ms)}
+        hbm_frac, fp64_frac = gbs / hbm_peak, tfl / (fp64_peak / 1e12)
+        kern[name] = {"kernel": KERNEL_NAME[name], "ms_per_launch": ms, "share_of_step": ms / step_sum, "configs_per_s": B / (ms * 1e-3),
+                      "algorithmic_bytes_per_config": alg[name]["bytes"], "algorithmic_flops_per_config": alg[name]["flops"],
+                      "sincos_per_config": alg[name]["sincos"], "achieved_GBs": gbs, "hbm_frac": hbm_frac,
+                      "achieved_fp64_TFLOPs": tfl, "fp64_frac_of_measured_dfma_peak": fp64_frac,
+                      # the roofline that bounds the kernel is the slower of the two ceilings, i.e. the larger fraction
+                      "bound": "fp64" if fp64_frac >= hbm_frac else "hbm"}
+
+    def roofline_of(name):
+        k = kern[name]
+        tr = NCU_TRAFFIC.get((cfg_name, B, name))
+        if k["bound"] == "fp64":
+            r = {"bound": "fp64", "kernel": k["kernel"], "achieved": k["achieved_fp64_TFLOPs"], "peak": fp64_peak / 1e12, "unit": "TFLOP/s",
+                 "frac": k["fp64_frac_of_measured_dfma_peak"], "peak_source": "measured in this run (register-resident DFMA loop)"}
+        else:
+            r = {"bound": "hbm", "kernel": k["kernel"], "achieved": k["achieved_GBs"], "peak": hbm_peak, "unit": "GB/s", "frac": k["hbm_frac"],
+                 "peak_source": peak_src}
+        r["traffic"] = tr["bytes"] if tr else None
+        r["traffic_source"] = tr["source"] if tr else None
+        r["share_of_step"] = k["share_of_step"]
+        return r
+
+    order = sorted(algos, key=lambda n: -kern[n]["share_of_step"])
     line = {
-        "metric": "batched dynamics evals/sec (ABA + CRBA)", "value": value, "unit": "evals/s", "n_gpus": world,
+        "metric": f"batched dynamics evals/sec ({' + '.join(algos)})", "value": value, "unit": "evals/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"ABA + CRBA on {B} configurations per GPU of {MODEL} (simple_humanoid.urdf + free-flyer, "
-                               f"nq={nq} nv={nv}), FP64; one eval = one configuration through one algorithm",
-                   "batch_per_gpu": B, "l2_policy": f"inputs rotate over {nsets} resident sets ({nsets * in_bytes >> 20} MiB > 126 MiB L2); "
-                                                    f"the {8 * B * nv * nv >> 20} MiB CRBA output streams through L2 every step",
-                   "parallelism": f"batch sharded over {world} GPU(s), no collective"},
+        "scaling": scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload_text(cfg_name, cfg, B, world, scaling), "batch_per_gpu": B,
+                   "l2_policy": (f"inputs rotate over {nsets} resident sets ({nsets * in_bytes >> 20} MiB > 126 MiB L2)" if nsets > 1
+                                 else f"one input set of {in_bytes >> 20} MiB (> 126 MiB L2)") + "; outputs stream through L2 every step",
+                   "parallelism": f"batch sharded over {world} GPU(s) in contiguous column ranges, no collective (gloo barrier only)"},
         "clocks": clocks, "gpu_launches": int(launches),
-        "e2e": {"value": e2e_value, "unit": "evals/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                "steps": e2e_steps, "note": "pinned host buffers -> brbd_*_batch(BRBD_PTR_HOST): H2D + kernels + D2H, wall clock"},
-        "roofline": roofline,
-        "fp64_roofline": fp64_roofline,
+        "e2e": e2e,
+        "roofline": roofline_of(order[0]),          # the kernel with the largest share of the step
+        "other_rooflines": [roofline_of(n) for n in order[1:]],
         "kernels": kern,
+        "flop_count": "oracle counting scalar, structural 0 / 1 of the joints' motion subspaces not counted (oracle/rbd_oracle.hpp Counted)",
         "fp64_peak_measured_TFLOPs": fp64_peak / 1e12,
     }
     if world == 1 and not args.no_cpu:
         nthreads = host_threads()
-        cpu_v, n2, dt = cpu_sample(orc, model, nthreads)
+        cpu_v, n2, dt = cpu_sample(orc, model, algos, B, nthreads)
         line["cpu_baseline"] = {"value": cpu_v, "unit": "evals/s", "cores": nthreads, "kind": "port",
-                                "sample": f"{n2} configurations through ABA(WORLD) + CRBA(WORLD) in {dt:.1f} s with the OpenMP "
+                                "sample": f"{n2} configurations through {' + '.join(algos)} in {dt:.1f} s with the OpenMP "
                                           f"restatement of rneaInParallel/abaInParallel (oracle/), schedule(static)"}
     print(json.dumps(line))
     if dist is not None:

@@ -93,6 +93,9 @@ void brbd_model_destroy(brbd_model * m);
 int brbd_model_nq(const brbd_model * m);
 int brbd_model_nv(const brbd_model * m);
 int brbd_model_njoints(const brbd_model * m);
+/* The model as it was given to brbd_model_create (ModelPoolTpl::getModel, pool/model.hpp:60-74): the pointers of
+ * `out` refer to storage owned by `m` and stay valid until brbd_model_destroy(m). */
+brbd_status brbd_model_get_flat(const brbd_model * m, brbd_flat_model * out);
 
 /* One staged model replica + one scratch arena + one stream per listed device
  * (device analogue of ModelPoolTpl(model, pool_size), pool/model.hpp:41-46). */
@@ -100,10 +103,20 @@ brbd_status brbd_pool_create(const brbd_model * m, const int * device_ids, int n
                              brbd_pool ** out);
 void brbd_pool_destroy(brbd_pool * p);
 int brbd_pool_size(const brbd_pool * p);               /* number of devices */
+/* ModelPoolTpl::resize (pool/model.hpp:110-131): replace the set of devices (replicas); NULL / 0 = device 0.
+ * Staging and workspaces of the dropped replicas are released, the model is re-staged on the new ones. */
+brbd_status brbd_pool_resize(brbd_pool * p, const int * device_ids, int n_devices);
+/* ModelPoolTpl::getModel(index): the model every replica holds (owned by the pool). */
+const brbd_model * brbd_pool_model(const brbd_pool * p);
+/* ModelPoolTpl::getData(index) has no per-thread Data here; what a replica owns is a device and its grow-only arenas:
+ * CUDA ordinal of replica `index` (-1 if out of range) and the bytes it currently holds on that device. */
+int brbd_pool_device_id(const brbd_pool * p, int index);
+uint64_t brbd_pool_workspace_bytes(const brbd_pool * p, int index);
 /* Replace the model held by every replica (ModelPoolTpl::update, pool/model.hpp:100-108). */
 brbd_status brbd_pool_update(brbd_pool * p, const brbd_model * m);
 /* Use an external CUDA stream (cudaStream_t as void*) for device-pointer calls on a
- * single-device pool; NULL restores the pool's own stream. */
+ * single-device pool; NULL restores the pool's own (non-blocking) stream.  The legacy default
+ * stream is selected by its CUDA handle cudaStreamLegacy ((cudaStream_t)0x1). */
 brbd_status brbd_pool_set_stream(brbd_pool * p, void * cuda_stream);
 brbd_status brbd_pool_synchronize(brbd_pool * p);
 /* Number of kernels this pool has launched since creation (bench.py's gpu_launches). */

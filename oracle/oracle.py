@@ -111,44 +111,43 @@ class Oracle:
     def max_threads() -> int:
         return int(_lib().oracle_max_threads())
 
-    def rnea(self, q, v, a, nthreads=0, long_double=False):
+    def rnea(self, q, v, a, nthreads=0, long_double=False, out=None):
         q, v, a = _cols(q, self.nq), _cols(v, self.nv), _cols(a, self.nv)
         B = q.shape[1]
-        tau = np.empty((self.nv, B), order="F")
+        tau = np.empty((self.nv, B), order="F") if out is None else out
         _lib().oracle_rnea(self._h, _p(q), _p(v), _p(a), _p(tau), ctypes.c_int64(B), _nt(nthreads, B), int(long_double))
         return tau
 
-    def aba(self, q, v, tau, nthreads=0, long_double=False):
+    def aba(self, q, v, tau, nthreads=0, long_double=False, out=None):
         q, v, tau = _cols(q, self.nq), _cols(v, self.nv), _cols(tau, self.nv)
         B = q.shape[1]
-        a = np.empty((self.nv, B), order="F")
+        a = np.empty((self.nv, B), order="F") if out is None else out
         _lib().oracle_aba(self._h, _p(q), _p(v), _p(tau), _p(a), ctypes.c_int64(B), _nt(nthreads, B), int(long_double))
         return a
 
-    def crba(self, q, nthreads=0, long_double=False, world=False):
-        """(nv*nv x B); each column a col-major nv x nv matrix, upper triangle + zeros."""
+    def crba(self, q, nthreads=0, long_double=False, world=False, out=None):
+        """(nv*nv x B); each column a col-major nv x nv matrix, upper triangle + zeros.  `out`: caller-owned F-order block
+        (the timed CPU arm of bench.py reuses one, as a caller of the reference would reuse its Data)."""
         q = _cols(q, self.nq)
         B = q.shape[1]
-        M = np.empty((self.nv * self.nv, B), order="F")
+        M = np.empty((self.nv * self.nv, B), order="F") if out is None else out
         _lib().oracle_crba(self._h, _p(q), _p(M), ctypes.c_int64(B), _nt(nthreads, B), int(long_double), int(world))
         return M
 
-    def rnea_derivatives(self, q, v, a, nthreads=0, long_double=False):
+    def rnea_derivatives(self, q, v, a, nthreads=0, long_double=False, out=None):
         q, v, a = _cols(q, self.nq), _cols(v, self.nv), _cols(a, self.nv)
         B = q.shape[1]
         nn = self.nv * self.nv
-        dq, dv, da = (np.empty((nn, B), order="F") for _ in range(3))
-        tau = np.empty((self.nv, B), order="F")
+        dq, dv, da, tau = out if out is not None else (*(np.empty((nn, B), order="F") for _ in range(3)), np.empty((self.nv, B), order="F"))
         _lib().oracle_rnea_derivatives(self._h, _p(q), _p(v), _p(a), _p(dq), _p(dv), _p(da), _p(tau),
                                        ctypes.c_int64(B), _nt(nthreads, B), int(long_double))
         return dq, dv, da, tau
 
-    def aba_derivatives(self, q, v, tau, nthreads=0, long_double=False):
+    def aba_derivatives(self, q, v, tau, nthreads=0, long_double=False, out=None):
         q, v, tau = _cols(q, self.nq), _cols(v, self.nv), _cols(tau, self.nv)
         B = q.shape[1]
         nn = self.nv * self.nv
-        dq, dv, dtau = (np.empty((nn, B), order="F") for _ in range(3))
-        ddq = np.empty((self.nv, B), order="F")
+        dq, dv, dtau, ddq = out if out is not None else (*(np.empty((nn, B), order="F") for _ in range(3)), np.empty((self.nv, B), order="F"))
         _lib().oracle_aba_derivatives(self._h, _p(q), _p(v), _p(tau), _p(dq), _p(dv), _p(dtau), _p(ddq),
                                       ctypes.c_int64(B), _nt(nthreads, B), int(long_double))
         return dq, dv, dtau, ddq

@@ -44,18 +44,43 @@ inline FlopCounter & flop_counter()
   static thread_local FlopCounter c;
   return c;
 }
+// `kind` marks the STRUCTURAL entries of a joint's motion subspace (0 and 1 of S): the reference's specialised joints never
+// multiply by them (joint-revolute.hpp:290-340: S^T f = f.angular[axis], S x = one component) and neither do the kernels, so
+// a product with a structural 0 / 1 and a sum with a structural 0 are not counted.  Data that merely happens to be 0 or 1
+// (an identity rotation in a placement) is NOT marked: the reference multiplies by it.
 struct Counted
 {
   double x;
-  Counted() : x(0) {}
-  Counted(double v) : x(v) {}
+  unsigned char kind; // 0 general, 1 structural zero, 2 structural one
+  Counted() : x(0), kind(0) {}
+  Counted(double v) : x(v), kind(0) {}
+  Counted(double v, unsigned char k) : x(v), kind(k) {}
   explicit operator double() const { return x; }
 };
-inline Counted operator+(Counted a, Counted b) { flop_counter().add++; return Counted(a.x + b.x); }
-inline Counted operator-(Counted a, Counted b) { flop_counter().add++; return Counted(a.x - b.x); }
-inline Counted operator*(Counted a, Counted b) { flop_counter().mul++; return Counted(a.x * b.x); }
+inline Counted operator+(Counted a, Counted b)
+{
+  if (a.kind == 1) return Counted(b.x);
+  if (b.kind == 1) return Counted(a.x);
+  flop_counter().add++;
+  return Counted(a.x + b.x);
+}
+inline Counted operator-(Counted a, Counted b)
+{
+  if (b.kind == 1) return Counted(a.x);
+  if (a.kind == 1) return Counted(-b.x);
+  flop_counter().add++;
+  return Counted(a.x - b.x);
+}
+inline Counted operator*(Counted a, Counted b)
+{
+  if (a.kind == 1 || b.kind == 1) return Counted(0.0, 1);
+  if (a.kind == 2) return b;
+  if (b.kind == 2) return a;
+  flop_counter().mul++;
+  return Counted(a.x * b.x);
+}
 inline Counted operator/(Counted a, Counted b) { flop_counter().div++; return Counted(a.x / b.x); }
-inline Counted operator-(Counted a) { return Counted(-a.x); }
+inline Counted operator-(Counted a) { return Counted(-a.x, a.kind == 1 ? 1 : 0); }
 inline Counted & operator+=(Counted & a, Counted b) { a = a + b; return a; }
 inline Counted & operator-=(Counted & a, Counted b) { a = a - b; return a; }
 inline Counted & operator*=(Counted & a, Counted b) { a = a * b; return a; }
@@ -85,6 +110,11 @@ template<> inline Counted eps_s<Counted>() { return Counted(std::numeric_limits<
 template<> inline __float128 eps_s<__float128>() { return FLT128_EPSILON; }
 #endif
 template<class S> inline S max_s(S a, S b) { return (a < b) ? b : a; }
+// structural entries of a motion subspace (see Counted)
+template<class S> inline S structural_zero() { return S(0); }
+template<class S> inline S structural_one() { return S(1); }
+template<> inline Counted structural_zero<Counted>() { return Counted(0.0, 1); }
+template<> inline Counted structural_one<Counted>() { return Counted(1.0, 2); }
 template<class S> inline double to_double(S x) { return (double)x; }
 
 // ---------------------------------------------------------------------------------------------
@@ -590,7 +620,7 @@ inline void jointCalc(const Model<S> & model, int i, const S * q, const S * vq, 
   const int t = model.type[i];
   const SE3<S> & P = model.jointPlacements[i];
   jd.nvj = model.nvs[i];
-  for (int r = 0; r < 6; ++r) for (int c = 0; c < 6; ++c) jd.Sm[r][c] = S(0);
+  for (int r = 0; r < 6; ++r) for (int c = 0; c < 6; ++c) jd.Sm[r][c] = structural_zero<S>();
   jd.v = Motion<S>();
   const S * qj = q + model.idx_q[i];
   const S * vj = vq ? vq + model.idx_v[i] : nullptr;
@@ -607,7 +637,7 @@ inline void jointCalc(const Model<S> & model, int i, const S * q, const S * vq, 
     if (axis == 0) { jd.M.R(1, 1) = ca; jd.M.R(1, 2) = -sa; jd.M.R(2, 1) = sa; jd.M.R(2, 2) = ca; }
     else if (axis == 1) { jd.M.R(0, 0) = ca; jd.M.R(0, 2) = sa; jd.M.R(2, 0) = -sa; jd.M.R(2, 2) = ca; }
     else { jd.M.R(0, 0) = ca; jd.M.R(0, 1) = -sa; jd.M.R(1, 0) = sa; jd.M.R(1, 1) = ca; }
-    jd.Sm[ANGULAR + axis][0] = S(1);
+    jd.Sm[ANGULAR + axis][0] = structural_one<S>();
     if (vj) jd.v.ang[axis] = vj[0];
   }
   else if (t <= BRBD_JOINT_PZ)
@@ -616,7 +646,7 @@ inline void jointCalc(const Model<S> & model, int i, const S * q, const S * vq, 
     const int axis = t - BRBD_JOINT_PX;
     jd.M = SE3<S>::Identity();
     jd.M.p[axis] = qj[0];
-    jd.Sm[LINEAR + axis][0] = S(1);
+    jd.Sm[LINEAR + axis][0] = structural_one<S>();
     if (vj) jd.v.lin[axis] = vj[0];
   }
   else if (t == BRBD_JOINT_REVOLUTE_UNALIGNED)
@@ -652,14 +682,14 @@ inline void jointCalc(const Model<S> & model, int i, const S * q, const S * vq, 
   {
     jd.M.p = V3<S>(qj[0], qj[1], qj[2]);
     jd.M.R = quatToMatrix(qj[3], qj[4], qj[5], qj[6]);
-    for (int k = 0; k < 6; ++k) jd.Sm[k][k] = S(1);
+    for (int k = 0; k < 6; ++k) jd.Sm[k][k] = structural_one<S>();
     if (vj) { jd.v.lin = V3<S>(vj[0], vj[1], vj[2]); jd.v.ang = V3<S>(vj[3], vj[4], vj[5]); }
   }
   else if (t == BRBD_JOINT_SPHERICAL)
   {
     jd.M.p = V3<S>();
     jd.M.R = quatToMatrix(qj[0], qj[1], qj[2], qj[3]);
-    for (int k = 0; k < 3; ++k) jd.Sm[ANGULAR + k][k] = S(1);
+    for (int k = 0; k < 3; ++k) jd.Sm[ANGULAR + k][k] = structural_one<S>();
     if (vj) jd.v.ang = V3<S>(vj[0], vj[1], vj[2]);
   }
   else // planar
@@ -668,7 +698,7 @@ inline void jointCalc(const Model<S> & model, int i, const S * q, const S * vq, 
     jd.M.R = M3<S>::Identity();
     jd.M.R(0, 0) = c; jd.M.R(0, 1) = -s; jd.M.R(1, 0) = s; jd.M.R(1, 1) = c;
     jd.M.p = V3<S>(qj[0], qj[1], S(0));
-    jd.Sm[0][0] = S(1); jd.Sm[1][1] = S(1); jd.Sm[5][2] = S(1);
+    jd.Sm[0][0] = structural_one<S>(); jd.Sm[1][1] = structural_one<S>(); jd.Sm[5][2] = structural_one<S>();
     if (vj) { jd.v.lin = V3<S>(vj[0], vj[1], S(0)); jd.v.ang = V3<S>(S(0), S(0), vj[2]); }
   }
   liMi = P * jd.M;

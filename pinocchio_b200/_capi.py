@@ -25,7 +25,8 @@ SYMBOLS = [
     "brbd_pool_launch_count", "brbd_pool_last_kernel_ms", "brbd_rnea_batch", "brbd_aba_batch", "brbd_crba_batch",
     "brbd_rnea_derivatives_batch", "brbd_aba_derivatives_batch", "brbd_measure_fp64_peak",
     "brbd_host_register", "brbd_host_unregister", "brbd_nle_batch", "brbd_gravity_batch", "brbd_minverse_batch",
-    "brbd_integrate_batch", "brbd_aba_euler_step_batch",
+    "brbd_integrate_batch", "brbd_aba_euler_step_batch", "brbd_model_get_flat", "brbd_pool_resize", "brbd_pool_model",
+    "brbd_pool_device_id", "brbd_pool_workspace_bytes",
 ]
 
 
@@ -72,6 +73,13 @@ def lib():
     L.brbd_pool_destroy.argtypes = [vp]
     L.brbd_pool_destroy.restype = None
     L.brbd_pool_size.argtypes = [vp]
+    L.brbd_model_get_flat.argtypes = [vp, ctypes.POINTER(FlatModel)]
+    L.brbd_pool_resize.argtypes = [vp, ctypes.POINTER(ci), ci]
+    L.brbd_pool_model.argtypes = [vp]
+    L.brbd_pool_model.restype = vp
+    L.brbd_pool_device_id.argtypes = [vp, ci]
+    L.brbd_pool_workspace_bytes.argtypes = [vp, ci]
+    L.brbd_pool_workspace_bytes.restype = ctypes.c_uint64
     L.brbd_pool_update.argtypes = [vp, vp]
     L.brbd_pool_set_stream.argtypes = [vp, vp]
     L.brbd_pool_synchronize.argtypes = [vp]

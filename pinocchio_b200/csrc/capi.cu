@@ -79,8 +79,10 @@ brbd_status run_call(brbd_pool * p, std::vector<Arg> & args, int64_t B, int flag
     }
     return BRBD_OK;
   }
-  // host pointers: shard columns contiguously over the devices; every shard moves through the device in
-  // chunks on three streams (upload | kernels | download) with double-buffered staging
+  // host pointers: shard columns contiguously over the devices; every shard moves through its device in chunks on three
+  // streams (upload | kernels | download) with double-buffered staging.  The chunk loop is the OUTER loop and the devices the
+  // inner one, so that every device has work queued before the host blocks in a copy from pageable memory (with pinned
+  // blocks — brbd_host_register — nothing blocks and the devices overlap fully either way).
   const int nd = (int)p->devs.size();
   const int64_t per = (B + nd - 1) / nd;
   if (args.size() > 8) return fail(BRBD_EINVAL, "too many arguments");
@@ -91,28 +93,65 @@ brbd_status run_call(brbd_pool * p, std::vector<Arg> & args, int64_t B, int flag
   int64_t chunk = (int64_t)((48u << 20) / std::max<size_t>(bytes_per_col, 1));
   chunk = std::max<int64_t>(4096, (chunk / 1024) * 1024);
   const std::vector<Arg> saved = args;
-  brbd_status result = BRBD_OK;
-  for (int g = 0; g < nd && result == BRBD_OK; ++g)
+  // whatever happens below, every device gets its stream selection back and is idle when the call returns
+  struct Restore
   {
-    const int64_t c0 = (int64_t)g * per, c1 = std::min<int64_t>(B, c0 + per);
-    if (c0 >= c1) break;
+    brbd_pool * p;
+    std::vector<char> user;
+    explicit Restore(brbd_pool * pool) : p(pool)
+    {
+      for (DeviceCtx & d : p->devs) { user.push_back(d.use_user_stream ? 1 : 0); d.use_user_stream = false; }
+    }
+    ~Restore()
+    {
+      for (size_t g = 0; g < p->devs.size(); ++g)
+      {
+        DeviceCtx & d = p->devs[g];
+        d.use_user_stream = user[g] != 0;
+        if (cudaSetDevice(d.dev) != cudaSuccess) continue;
+        cudaStreamSynchronize(d.s_in);
+        cudaStreamSynchronize(d.stream);
+        cudaStreamSynchronize(d.s_out);
+      }
+    }
+  } restore(p); // kernels of host-pointer calls run on the pool's own streams
+  struct Shard { int64_t c0, c1, cw, next; int it; };
+  std::vector<Shard> shards(nd);
+  for (int g = 0; g < nd; ++g)
+  {
+    Shard & sh = shards[g];
+    sh.c0 = std::min<int64_t>(B, (int64_t)g * per);
+    sh.c1 = std::min<int64_t>(B, sh.c0 + per);
+    sh.cw = std::max<int64_t>(1, std::min<int64_t>(chunk, sh.c1 - sh.c0));
+    sh.next = sh.c0;
+    sh.it = 0;
+    if (sh.c0 >= sh.c1) continue;
     DeviceCtx & d = p->devs[g];
     CUDA_TRY(cudaSetDevice(d.dev));
-    const bool user = d.use_user_stream;
-    d.use_user_stream = false; // kernels of host-pointer calls run on the pool's own stream
-    const int64_t cw = std::min<int64_t>(chunk, c1 - c0);
     for (size_t k = 0; k < args.size(); ++k)
       if (args[k].in || args[k].out)
         for (int b = 0; b < 2; ++b)
         {
-          brbd_status st = ensure_stage(d, (int)(2 * k + b), (size_t)args[k].rows * cw * sizeof(T));
-          if (st != BRBD_OK) { d.use_user_stream = user; return st; }
+          brbd_status st = ensure_stage(d, (int)(2 * k + b), (size_t)args[k].rows * sh.cw * sizeof(T));
+          if (st != BRBD_OK) return st;
         }
-    int it = 0;
-    for (int64_t b0 = c0; b0 < c1; b0 += cw, ++it)
+  }
+  for (bool any = true; any;)
+  {
+    any = false;
+    for (int g = 0; g < nd; ++g)
     {
+      Shard & sh = shards[g];
+      if (sh.next >= sh.c1) continue;
+      any = true;
+      DeviceCtx & d = p->devs[g];
+      CUDA_TRY(cudaSetDevice(d.dev));
+      const int64_t b0 = sh.next;
+      const int it = sh.it;
       const int buf = it & 1;
-      const int64_t nb = std::min<int64_t>(cw, c1 - b0);
+      const int64_t nb = std::min<int64_t>(sh.cw, sh.c1 - b0);
+      sh.next += nb;
+      sh.it += 1;
       std::vector<void *> ptrs(args.size(), nullptr);
       // upload may start once the kernel that read this input buffer two chunks ago is done
       if (it >= 2) CUDA_TRY(cudaStreamWaitEvent(d.s_in, d.ev_k[buf], 0));
@@ -135,9 +174,9 @@ brbd_status run_call(brbd_pool * p, std::vector<Arg> & args, int64_t B, int flag
       // the kernel overwrites the output buffer whose download was queued two chunks ago
       if (it >= 2) CUDA_TRY(cudaStreamWaitEvent(d.stream, d.ev_out[buf], 0));
       for (size_t k = 0; k < args.size(); ++k) args[k].ld = args[k].rows; // staged blocks are dense
-      result = launch(d, ptrs, nb);
+      const brbd_status result = launch(d, ptrs, nb);
       args = saved;
-      if (result != BRBD_OK) break;
+      if (result != BRBD_OK) return result;
       CUDA_TRY(cudaEventRecord(d.ev_k[buf], d.stream));
       CUDA_TRY(cudaStreamWaitEvent(d.s_out, d.ev_k[buf], 0));
       for (size_t k = 0; k < args.size(); ++k)
@@ -152,8 +191,8 @@ brbd_status run_call(brbd_pool * p, std::vector<Arg> & args, int64_t B, int flag
       }
       CUDA_TRY(cudaEventRecord(d.ev_out[buf], d.s_out));
     }
-    d.use_user_stream = user;
   }
+  // errors of the asynchronous work surface here (the guard synchronises again, harmlessly, on the way out)
   for (int g = 0; g < nd; ++g)
   {
     CUDA_TRY(cudaSetDevice(p->devs[g].dev));
@@ -161,7 +200,7 @@ brbd_status run_call(brbd_pool * p, std::vector<Arg> & args, int64_t B, int flag
     CUDA_TRY(cudaStreamSynchronize(p->devs[g].stream));
     CUDA_TRY(cudaStreamSynchronize(p->devs[g].s_out));
   }
-  return result;
+  return BRBD_OK;
 }
 } // namespace
 
@@ -201,10 +240,33 @@ brbd_status brbd_model_create(const brbd_flat_model * f, brbd_model ** out)
     delete m;
     return fail(BRBD_ETOPOLOGY, "more than " + std::to_string(MAXPATH) + " degrees of freedom on one root path");
   }
+  const int n = f->njoints;
+  m->f_parents.assign(f->parents, f->parents + n);
+  m->f_type.assign(f->joint_type, f->joint_type + n);
+  m->f_idx_q.assign(f->idx_q, f->idx_q + n);
+  m->f_idx_v.assign(f->idx_v, f->idx_v + n);
+  m->f_placement.assign(f->placement, f->placement + 12 * n);
+  m->f_inertia.assign(f->inertia, f->inertia + 10 * n);
+  m->f_armature.assign(f->nv, 0.0);
+  if (f->armature) m->f_armature.assign(f->armature, f->armature + f->nv);
+  m->f_axis.assign(3 * n, 0.0);
+  if (f->axis) m->f_axis.assign(f->axis, f->axis + 3 * n);
+  for (int k = 0; k < 3; ++k) m->f_gravity[k] = f->gravity[k];
   *out = m;
   return BRBD_OK;
 }
 void brbd_model_destroy(brbd_model * m) { delete m; }
+brbd_status brbd_model_get_flat(const brbd_model * m, brbd_flat_model * out)
+{
+  if (!m || !out) return fail(BRBD_EINVAL, "null argument");
+  out->njoints = m->pd.njoints; out->nq = m->pd.nq; out->nv = m->pd.nv;
+  out->parents = m->f_parents.data(); out->joint_type = m->f_type.data();
+  out->idx_q = m->f_idx_q.data(); out->idx_v = m->f_idx_v.data();
+  out->placement = m->f_placement.data(); out->inertia = m->f_inertia.data();
+  out->armature = m->f_armature.data(); out->axis = m->f_axis.data();
+  for (int k = 0; k < 3; ++k) out->gravity[k] = m->f_gravity[k];
+  return BRBD_OK;
+}
 int brbd_model_nq(const brbd_model * m) { return m ? m->pd.nq : -1; }
 int brbd_model_nv(const brbd_model * m) { return m ? m->pd.nv : -1; }
 int brbd_model_njoints(const brbd_model * m) { return m ? m->pd.njoints : -1; }
@@ -259,6 +321,9 @@ brbd_status brbd_pool_create(const brbd_model * m, const int * device_ids, int n
   std::vector<int> ids;
   if (!device_ids || n_devices <= 0) ids.push_back(0);
   else ids.assign(device_ids, device_ids + n_devices);
+  for (size_t a = 0; a < ids.size(); ++a)
+    for (size_t b = a + 1; b < ids.size(); ++b)
+      if (ids[a] == ids[b]) return fail(BRBD_EINVAL, "device id " + std::to_string(ids[a]) + " listed twice");
   brbd_pool * p = new brbd_pool();
   p->model = *m;
   for (int id : ids)
@@ -317,6 +382,31 @@ brbd_status brbd_pool_create(const brbd_model * m, const int * device_ids, int n
   return BRBD_OK;
 }
 int brbd_pool_size(const brbd_pool * p) { return p ? (int)p->devs.size() : 0; }
+const brbd_model * brbd_pool_model(const brbd_pool * p) { return p ? &p->model : nullptr; }
+int brbd_pool_device_id(const brbd_pool * p, int index)
+{
+  return (p && index >= 0 && index < (int)p->devs.size()) ? p->devs[index].dev : -1;
+}
+uint64_t brbd_pool_workspace_bytes(const brbd_pool * p, int index)
+{
+  if (!p || index < 0 || index >= (int)p->devs.size()) return 0;
+  const DeviceCtx & d = p->devs[index];
+  uint64_t n = d.work_bytes + d.aux_bytes + sizeof(ModelPOD<double>) + sizeof(ModelPOD<float>) + MAXNV * sizeof(double);
+  for (int k = 0; k < 16; ++k) n += d.stage_bytes[k];
+  return n;
+}
+brbd_status brbd_pool_resize(brbd_pool * p, const int * device_ids, int n_devices)
+{
+  if (!p) return fail(BRBD_EINVAL, "null pool");
+  brbd_status st = brbd_pool_synchronize(p);
+  if (st != BRBD_OK) return st;
+  brbd_pool * fresh = nullptr;
+  st = brbd_pool_create(&p->model, device_ids, n_devices, &fresh);
+  if (st != BRBD_OK) return st;
+  std::swap(p->devs, fresh->devs); // the old replicas (streams, arenas, staged models) go away with `fresh`
+  brbd_pool_destroy(fresh);
+  return BRBD_OK;
+}
 brbd_status brbd_pool_update(brbd_pool * p, const brbd_model * m)
 {
   if (!p || !m) return fail(BRBD_EINVAL, "null argument");
@@ -329,8 +419,10 @@ brbd_status brbd_pool_set_stream(brbd_pool * p, void * cuda_stream)
 {
   if (!p) return fail(BRBD_EINVAL, "null pool");
   if (p->devs.size() != 1) return fail(BRBD_EINVAL, "external streams require a single-device pool");
+  // NULL restores the pool's own (non-blocking) stream, as include/pinocchio_b200.h documents; the legacy default stream
+  // is selected with its CUDA handle cudaStreamLegacy ((cudaStream_t)0x1), the per-thread one with cudaStreamPerThread
   p->devs[0].user_stream = static_cast<cudaStream_t>(cuda_stream);
-  p->devs[0].use_user_stream = true;
+  p->devs[0].use_user_stream = cuda_stream != nullptr;
   return BRBD_OK;
 }
 brbd_status brbd_pool_synchronize(brbd_pool * p)

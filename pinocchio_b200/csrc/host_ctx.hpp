@@ -39,6 +39,10 @@ struct brbd_model
   brbd::TreePOD<double> td; // v2 kernels: passed by value as a __grid_constant__ kernel parameter
   brbd::TreePOD<float> tf;
   brbd::CoopTables coop; // warp-cooperative derivative kernels: level lists, ancestor masks
+  // the model as the caller gave it (brbd_model_get_flat)
+  std::vector<int32_t> f_parents, f_type, f_idx_q, f_idx_v;
+  std::vector<double> f_placement, f_inertia, f_armature, f_axis;
+  double f_gravity[3] = {0, 0, 0};
 };
 
 namespace brbd

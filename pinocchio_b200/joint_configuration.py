@@ -203,10 +203,9 @@ def integrate(model: Model, q: np.ndarray, v: np.ndarray) -> np.ndarray:
                 res = -res
             out[iq + 3:iq + 7] = _first_order_normalize(res)
         elif t == JOINT_SPHERICAL:
+            # SpecialOrthogonalOperationTpl<3>::integrate_impl (special-orthogonal.hpp:467-481): no sign fix-up (only SE(3) has one)
             quat = q[iq:iq + 4]
             res = _quat_mul(quat, _exp3_quat(v[iv:iv + 3]))
-            if float(res @ quat) < 0.0:
-                res = -res
             out[iq:iq + 4] = _first_order_normalize(res)
         else:  # planar: SE(2), q = (x, y, cos, sin), v = (vx, vy, wz) body frame
             c0, s0 = q[iq + 2], q[iq + 3]
@@ -220,7 +219,6 @@ def integrate(model: Model, q: np.ndarray, v: np.ndarray) -> np.ndarray:
                 tx, ty = vx, vy
             out[iq] = q[iq] + c0 * tx - s0 * ty
             out[iq + 1] = q[iq + 1] + s0 * tx + c0 * ty
-            c1, s1 = c0 * cw - s0 * sw, s0 * cw + c0 * sw
-            n = (3.0 - (c1 * c1 + s1 * s1)) / 2.0
-            out[iq + 2], out[iq + 3] = c1 * n, s1 * n
+            # out.tail<2>() = R0 * R.col(0) (special-euclidean.hpp:304-305): (cos, sin) is not re-normalised
+            out[iq + 2], out[iq + 3] = c0 * cw - s0 * sw, s0 * cw + c0 * sw
     return out

@@ -45,6 +45,8 @@ class ModelPool:
         self._model = model
         self._h_model = ctypes.c_void_p()
         self._h_pool = ctypes.c_void_p()
+        self._stream_pinned = False   # True once the caller chose a stream with set_stream()
+        self._stream_handle = None    # what brbd_pool_set_stream was last given
         self._create_model(model)
         L = _capi.lib()
         if devices is None:
@@ -76,7 +78,51 @@ class ModelPool:
         return int(_capi.lib().brbd_pool_size(self._h_pool))
 
     def getModel(self, index: int = 0):
+        """ModelPoolTpl::getModel (pool/model.hpp:60-74): every replica holds the same model."""
+        if not (0 <= int(index) < self.size()):
+            raise ValueError(f"Index greater than the size of the model vector: {index} >= {self.size()}")
         return self._model
+
+    def getModels(self):
+        """ModelPoolTpl::getModels (pool/model.hpp:77-89)."""
+        return [self._model] * self.size()
+
+    def getData(self, index: int = 0):
+        """ModelPoolTpl::getData has no counterpart with per-thread Data on the device; what replica `index` owns is a CUDA
+        device and its grow-only arenas."""
+        if not (0 <= int(index) < self.size()):
+            raise ValueError(f"Index greater than the size of the data vector: {index} >= {self.size()}")
+        L = _capi.lib()
+        return {"device": int(L.brbd_pool_device_id(self._h_pool, int(index))),
+                "workspace_bytes": int(L.brbd_pool_workspace_bytes(self._h_pool, int(index)))}
+
+    def getDatas(self):
+        return [self.getData(i) for i in range(self.size())]
+
+    def devices(self):
+        L = _capi.lib()
+        return [int(L.brbd_pool_device_id(self._h_pool, i)) for i in range(self.size())]
+
+    def resize(self, devices: Sequence[int]):
+        """ModelPoolTpl::resize (pool/model.hpp:110-131): the replicas of a device pool are devices."""
+        arr = (ctypes.c_int * len(devices))(*[int(d) for d in devices])
+        try:
+            _capi.check(_capi.lib().brbd_pool_resize(self._h_pool, arr, len(devices)))
+        except EngineError as e:
+            _raise(e)
+        self._stream_pinned, self._stream_handle = False, None
+
+    def flat_model(self):
+        """The model as the engine holds it (brbd_model_get_flat), as a dict of numpy arrays."""
+        fm = _capi.FlatModel()
+        _capi.check(_capi.lib().brbd_model_get_flat(self._h_model, ctypes.byref(fm)))
+        n, nv = fm.njoints, fm.nv
+        a = lambda ptr, k, dt: np.ctypeslib.as_array(ptr, shape=(k,)).astype(dt).copy() if k else np.zeros(0, dtype=dt)
+        return {"njoints": n, "nq": fm.nq, "nv": nv, "parents": a(fm.parents, n, np.int32), "joint_type": a(fm.joint_type, n, np.int32),
+                "idx_q": a(fm.idx_q, n, np.int32), "idx_v": a(fm.idx_v, n, np.int32),
+                "placement": a(fm.placement, 12 * n, np.float64).reshape(n, 12), "inertia": a(fm.inertia, 10 * n, np.float64).reshape(n, 10),
+                "armature": a(fm.armature, nv, np.float64), "axis": a(fm.axis, 3 * n, np.float64),
+                "gravity": np.array([fm.gravity[0], fm.gravity[1], fm.gravity[2]])}
 
     def update(self, model):
         """ModelPoolTpl::update (pool/model.hpp:100-108)."""
@@ -89,7 +135,24 @@ class ModelPool:
         _capi.check(_capi.lib().brbd_pool_synchronize(self._h_pool))
 
     def set_stream(self, cuda_stream: Optional[int]):
-        _capi.check(_capi.lib().brbd_pool_set_stream(self._h_pool, ctypes.c_void_p(cuda_stream or 0)))
+        """Pin device-pointer calls to one CUDA stream (a cudaStream_t handle; torch: `stream.cuda_stream`).  A handle of 0 is
+        the legacy default stream (what torch's default stream is).  `None` un-pins: torch tensors then run on torch's
+        current stream of their device, raw device pointers on the pool's own stream."""
+        if cuda_stream is None:
+            self._stream_pinned = False
+            self._set_stream_handle(None)
+            return
+        self._stream_pinned = True
+        self._set_stream_handle(int(cuda_stream))
+
+    _CUDA_STREAM_LEGACY = 1  # cudaStreamLegacy
+
+    def _set_stream_handle(self, handle: Optional[int]):
+        if handle == self._stream_handle and handle is not None:
+            return
+        raw = 0 if handle is None else (self._CUDA_STREAM_LEGACY if handle == 0 else handle)
+        _capi.check(_capi.lib().brbd_pool_set_stream(self._h_pool, ctypes.c_void_p(raw)))
+        self._stream_handle = handle
 
     def launch_count(self) -> int:
         return int(_capi.lib().brbd_pool_launch_count(self._h_pool))
@@ -193,9 +256,22 @@ def _call(pool: ModelPool, fn_name: str, ins, outs, async_: bool = False, mid=()
         raise ValueError("mixing host and device arguments in one call is not supported")
     if len(dt) != 1:
         raise ValueError("all arguments must share one dtype (float64 or float32)")
-    flags = (BRBD_PTR_DEVICE if dev.pop() else BRBD_PTR_HOST) | (BRBD_FP32 if dt.pop() is np.float32 else BRBD_FP64)
+    on_device = dev.pop()
+    flags = (BRBD_PTR_DEVICE if on_device else BRBD_PTR_HOST) | (BRBD_FP32 if dt.pop() is np.float32 else BRBD_FP64)
     if async_:
         flags |= BRBD_ASYNC
+    if on_device:
+        # Device tensors: every block must live on the pool's device, and the kernels must be ordered after whatever
+        # produced the inputs — so, unless the caller pinned a stream with set_stream(), the call runs on torch's CURRENT
+        # stream of that device (as any torch op would), not on the pool's private non-blocking stream.
+        devs = {a.keep.device.index for a in args if _is_torch(a.keep)}
+        pool_devs = pool.devices()
+        if len(pool_devs) != 1:
+            raise ValueError("device tensors require a single-device pool")
+        if devs and devs != {pool_devs[0]}:
+            raise ValueError(f"tensors on cuda device(s) {sorted(devs)} passed to a pool on device {pool_devs[0]}")
+        if not pool._stream_pinned and devs:
+            pool._set_stream_handle(int(torch.cuda.current_stream(pool_devs[0]).cuda_stream))
     cargs = [pool._h_pool]
     for group in (ins, None, outs):
         if group is None:

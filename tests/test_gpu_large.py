@@ -238,3 +238,87 @@ def test_fp32_solves_tolerance(ctx):
         for g, r, nm in zip(got, orc.rnea_derivatives(q, v, tau), ("dtau_dq", "dtau_dv", "dtau_da", "tau")):
             rel = np.abs(g - r).max() / np.abs(r).max()
             assert rel < 5e-5, (name, nm, rel)
+
+
+def test_torch_stream_ordering(ctx):
+    """Device tensors produced on torch's current stream are consumed without an explicit synchronisation: the call must run
+    on that stream (the pool's private non-blocking stream raced with the producer)."""
+    import torch
+    import pinocchio_b200 as pb
+    model, pool, orc = ctx("humanoid_random")
+    pool.set_stream(None)
+    B = 20000
+    q, v, a = random_inputs(model, B, 3)
+    tq, tv, ta = to_dev(q, v, a)
+    side = torch.cuda.Stream()
+    for stream in (torch.cuda.current_stream(), side):
+        with torch.cuda.stream(stream):
+            # a long producer right before the call: scale the inputs on the device, no host sync
+            big = torch.randn(64 << 20, device="cuda")
+            for _ in range(4):
+                big = big * 1.0001
+            v2 = tv * 2.0
+            tau = pb.rneaInParallel(1, pool, tq, v2, ta, async_=True)
+            out = tau * 1.0  # consumer on the same stream
+        stream.synchronize()
+        assert_close(to_host(out), orc.rnea(q, 2.0 * v, a), what="rnea after an unsynchronised producer")
+    with pytest.raises(ValueError):
+        pb.rneaInParallel(1, pool, tq.cpu().numpy().T, tv, ta)  # host / device mix
+
+
+def test_pool_surface(ctx):
+    """ModelPoolTpl::getModel / getModels / getData / getDatas / resize / update (pool/model.hpp:60-131)."""
+    import pinocchio_b200 as pb
+    model, _, orc = ctx("manipulator")
+    pool = pb.ModelPool(model, [0])
+    assert pool.size() == 1 and pool.getModel(0) is model and pool.getModels() == [model]
+    assert pool.getData(0)["device"] == 0 and len(pool.getDatas()) == 1
+    with pytest.raises(ValueError):
+        pool.getModel(1)
+    flat = pool.flat_model()
+    assert flat["njoints"] == model.njoints and np.array_equal(flat["parents"], np.asarray(model.parents))
+    q, v, a = random_inputs(model, 50, 1)
+    t0 = pb.rneaInParallel(1, pool, q, v, a)
+    pool.resize([0])
+    assert pool.size() == 1
+    assert np.array_equal(pb.rneaInParallel(1, pool, q, v, a), t0)
+    # update: heavier links change the result, the old model gives the old result back
+    m2 = load_model("manipulator")
+    for Y in m2.inertias[1:]:
+        Y.mass *= 2.0
+        Y.sym = Y.sym * 2.0
+    pool.update(m2)
+    t2 = pb.rneaInParallel(1, pool, q, v, a)
+    from oracle import Oracle
+    assert_close(t2, Oracle(m2).rnea(q, v, a), what="rnea after pool.update")
+    assert not np.allclose(t2, t0)
+    pool.update(model)
+    assert np.array_equal(pb.rneaInParallel(1, pool, q, v, a), t0)
+    with pytest.raises(ValueError):
+        pb.ModelPool(model, [0, 0])
+    pool.close()
+
+
+def test_multi_device_pool(ctx):
+    """A pool over several devices shards a host-pointer call itself (contiguous column ranges, no exchange): results are
+    bit-identical to the single-device pool.  Needs >= 2 GPUs."""
+    import torch
+    import pinocchio_b200 as pb
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs at least two GPUs")
+    model, pool1, orc = ctx("simple_humanoid_ff")
+    n = min(4, torch.cuda.device_count())
+    pooln = pb.ModelPool(model, list(range(n)))
+    assert pooln.size() == n and pooln.devices() == list(range(n))
+    for B in (1, 5, 9000, 70001):
+        q, v, a = random_inputs(model, B, 13)
+        assert np.array_equal(pb.rneaInParallel(1, pooln, q, v, a), pb.rneaInParallel(1, pool1, q, v, a))
+        assert np.array_equal(pb.abaInParallel(1, pooln, q, v, a), pb.abaInParallel(1, pool1, q, v, a))
+    q, v, a = random_inputs(model, 9000, 14)
+    assert np.array_equal(pb.crbaInParallel(1, pooln, q), pb.crbaInParallel(1, pool1, q))
+    with pytest.raises(ValueError):
+        pb.rneaInParallel(1, pooln, *to_dev(q, v, a))  # device pointers need a single-device pool
+    pooln.resize([1])
+    assert pooln.devices() == [1]
+    assert np.array_equal(pb.rneaInParallel(1, pooln, q, v, a), pb.rneaInParallel(1, pool1, q, v, a))
+    pooln.close()
