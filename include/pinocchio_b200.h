@@ -173,6 +173,35 @@ brbd_status brbd_aba_euler_step_batch(brbd_pool * p, const void * q, int64_t ldq
                                       const void * tau, int64_t ldtau, double dt, void * q_next,
                                       int64_t ldqn, void * v_next, int64_t ldvn, int64_t batch, int flags);
 
+/* ---- per-model code generation (the GPU analogue of include/pinocchio/codegen/code-generator-algo.hpp:22-570) --------
+ * brbd_codegen_source runs the algorithm once on a recording scalar and returns the CUDA source of a kernel specialised
+ * for THIS model: the tree unrolled, joint types resolved, placements / inertias folded in as constants.  *source is
+ * malloc'ed; release it with brbd_codegen_free.  brbd_pool_specialize compiles it (NVRTC) and makes the pool's
+ * brbd_rnea_batch / brbd_aba_batch use it for large batches. */
+enum { BRBD_GEN_RNEA = 0, BRBD_GEN_ABA = 1, BRBD_GEN_CRBA = 2 };
+enum {
+  BRBD_GEN_EXPLICIT_SLOTS = 1, /* long-lived values in explicit on-chip slots instead of compiler-managed local memory */
+  BRBD_GEN_HOST = 2,           /* emit the host-callable variant (tests of the generator only)                          */
+  BRBD_GEN_FP32 = 4,           /* element type float                                                                     */
+  BRBD_GEN_DIRECT_IO = 8       /* no shared-memory input / output tiles: every lane reads its own column from global memory */
+  /* bits 8..19: threads per block (0 = default), bits 20..23: min blocks per SM of __launch_bounds__                     */
+};
+typedef struct brbd_codegen_info {
+  int32_t record_slots, park_slots, nodes, live_nodes, adds, muls, recips, sqrts, sincos, loads, stores, threads_per_block;
+  int32_t smem_slots, tmem_slots; /* explicit slots: values per configuration in shared memory / tensor memory */
+  int32_t dynamic_smem_bytes;     /* per CTA: the warps' input / output tiles + the shared-memory park slots     */
+  int32_t copies;                 /* identical kernels brbd_gen_<algo>_<c> at different code addresses            */
+} brbd_codegen_info;
+brbd_status brbd_codegen_source(const brbd_model * m, int algo, int flags, char ** source, brbd_codegen_info * info);
+void brbd_codegen_free(char * source);
+/* Generate, compile (NVRTC, sm_100a) and load kernels specialised for the pool's model.  algo_mask: bit (1 << BRBD_GEN_*);
+ * flags: BRBD_GEN_FP32 to specialise the float instantiation, BRBD_GEN_EXPLICIT_SLOTS.  Afterwards brbd_rnea_batch /
+ * brbd_aba_batch (and the calls built on them) run the specialised kernel for batches of at least
+ * brbd_pool_set_specialized_min_batch (default 8192) configurations per device; brbd_pool_update drops them. */
+brbd_status brbd_pool_specialize(brbd_pool * p, int algo_mask, int flags);
+int brbd_pool_specialized(const brbd_pool * p); /* mask of algorithms that have a specialised kernel */
+brbd_status brbd_pool_set_specialized_min_batch(brbd_pool * p, int64_t min_batch);
+
 /* Page-lock caller-owned host memory (cudaHostRegister / cudaHostUnregister).  Host-pointer calls work on
  * pageable memory too, but only pinned memory reaches the full link bandwidth (measured on this pool's
  * B200 hosts: 57 GB/s pinned vs 11-22 GB/s pageable) and lets the upload / compute / download pipeline of a

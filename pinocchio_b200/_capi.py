@@ -26,7 +26,8 @@ SYMBOLS = [
     "brbd_rnea_derivatives_batch", "brbd_aba_derivatives_batch", "brbd_measure_fp64_peak",
     "brbd_host_register", "brbd_host_unregister", "brbd_nle_batch", "brbd_gravity_batch", "brbd_minverse_batch",
     "brbd_integrate_batch", "brbd_aba_euler_step_batch", "brbd_model_get_flat", "brbd_pool_resize", "brbd_pool_model",
-    "brbd_pool_device_id", "brbd_pool_workspace_bytes",
+    "brbd_pool_device_id", "brbd_pool_workspace_bytes", "brbd_codegen_source", "brbd_codegen_free", "brbd_pool_specialize",
+    "brbd_pool_specialized", "brbd_pool_set_specialized_min_batch",
 ]
 
 
@@ -80,6 +81,9 @@ def lib():
     L.brbd_pool_device_id.argtypes = [vp, ci]
     L.brbd_pool_workspace_bytes.argtypes = [vp, ci]
     L.brbd_pool_workspace_bytes.restype = ctypes.c_uint64
+    L.brbd_pool_specialize.argtypes = [vp, ci, ci]
+    L.brbd_pool_specialized.argtypes = [vp]
+    L.brbd_pool_set_specialized_min_batch.argtypes = [vp, i64]
     L.brbd_pool_update.argtypes = [vp, vp]
     L.brbd_pool_set_stream.argtypes = [vp, vp]
     L.brbd_pool_synchronize.argtypes = [vp]

@@ -285,6 +285,7 @@ static brbd_status upload_model(brbd_pool * p)
 void brbd_pool_destroy(brbd_pool * p)
 {
   if (!p) return;
+  release_generated(p);
   for (DeviceCtx & d : p->devs)
   {
     if (cudaSetDevice(d.dev) != cudaSuccess) continue;
@@ -412,8 +413,37 @@ brbd_status brbd_pool_update(brbd_pool * p, const brbd_model * m)
   if (!p || !m) return fail(BRBD_EINVAL, "null argument");
   brbd_status st = brbd_pool_synchronize(p);
   if (st != BRBD_OK) return st;
+  release_generated(p); // kernels generated for the previous model
   p->model = *m;
   return upload_model(p);
+}
+brbd_status brbd_pool_specialize(brbd_pool * p, int algo_mask, int flags)
+{
+  if (!p) return fail(BRBD_EINVAL, "null pool");
+  brbd_status st = brbd_pool_synchronize(p);
+  if (st != BRBD_OK) return st;
+  if (!p->devs.empty()) CUDA_TRY(cudaSetDevice(p->devs[0].dev));
+  for (int algo = 0; algo < 2; ++algo)
+    if (algo_mask & (1 << algo))
+    {
+      st = specialize_one(p, algo, (flags & BRBD_GEN_FP32) != 0, flags);
+      if (st != BRBD_OK) return st;
+    }
+  return BRBD_OK;
+}
+int brbd_pool_specialized(const brbd_pool * p)
+{
+  int mask = 0;
+  if (p)
+    for (int algo = 0; algo < 3; ++algo)
+      if (p->gen[algo][0].nvar || p->gen[algo][1].nvar) mask |= 1 << algo;
+  return mask;
+}
+brbd_status brbd_pool_set_specialized_min_batch(brbd_pool * p, int64_t min_batch)
+{
+  if (!p) return fail(BRBD_EINVAL, "null pool");
+  p->gen_min_batch = min_batch;
+  return BRBD_OK;
 }
 brbd_status brbd_pool_set_stream(brbd_pool * p, void * cuda_stream)
 {

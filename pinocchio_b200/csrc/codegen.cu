@@ -1,0 +1,300 @@
+// codegen.cu — per-model code generation behind the C ABI (host code only; compiled by nvcc because it instantiates the
+// engine's device headers with the recording scalar, BRBD_DI = __host__ __device__).
+//   brbd_codegen_source : model + algorithm -> CUDA source of a kernel specialised for that model (codegen/trace.hpp,
+//                         codegen/emit.hpp); also the host-callable variant used by the CPU tests of the generator.
+// The GPU analogue of the reference's code generation (include/pinocchio/codegen/code-generator-algo.hpp:22-570).
+#define BRBD_DI __host__ __device__ __forceinline__
+#define BRBD_SYNCWARP() ((void)0) // no kernel of this translation unit is ever launched
+#include "codegen/sym.hpp"
+#include "host_ctx.hpp"
+#include "codegen/trace.hpp"
+#include "codegen/emit.hpp"
+
+#include <sstream>
+
+using namespace brbd;
+
+namespace
+{
+const char * algo_name(int algo) { return algo == BRBD_GEN_RNEA ? "rnea" : (algo == BRBD_GEN_ABA ? "aba" : "crba"); }
+
+const char * math_macros(bool fp32)
+{
+  return fp32 ? "typedef float real;\n#define BRBD_C(x) ((real)(x))\n#define BRBD_SINCOS(x, s, c) sincosf((x), (s), (c))\n#define BRBD_SIN(x) sinf(x)\n"
+                "#define BRBD_COS(x) cosf(x)\n#define BRBD_SQRT(x) sqrtf(x)\n#define BRBD_MAX(a, b) fmaxf((a), (b))\n"
+              : "typedef double real;\n#define BRBD_C(x) (x)\n#define BRBD_SINCOS(x, s, c) sincos((x), (s), (c))\n#define BRBD_SIN(x) sin(x)\n"
+                "#define BRBD_COS(x) cos(x)\n#define BRBD_SQRT(x) sqrt(x)\n#define BRBD_MAX(a, b) fmax((a), (b))\n";
+}
+
+// park_st / park_ld helpers of the generated kernel for one group shape.  Tensor memory (space 0): the group is a run of
+// 32-bit columns of the warp's slice, written / read with tcgen05.st / tcgen05.ld 32x32b in power-of-two chunks (SASS STTM /
+// LDTM; thread t of a warp owns lane 32 * (warp % 4) + t, see tmem.cuh).  Shared memory (space 1): slot-major, [slot][thread].
+void emit_park_helpers(std::ostringstream & os, int n, int space, bool fp32, int nt)
+{
+  const int wpv = fp32 ? 1 : 2, words = n * wpv;
+  auto word = [&](int w) -> std::string {
+    const std::string v = "v" + std::to_string(w / wpv);
+    if (fp32) return "__float_as_uint(" + v + ")";
+    return (w % 2 == 0) ? "(unsigned)__double2loint(" + v + ")" : "(unsigned)__double2hiint(" + v + ")";
+  };
+  const char sp = space == 0 ? 'T' : 'S';
+  // store
+  os << "__device__ __forceinline__ void park_st" << sp << n << "(" << (space == 0 ? "unsigned a" : "real * a");
+  for (int k = 0; k < n; ++k) os << ", real v" << k;
+  os << ")\n{\n";
+  if (space == 1)
+    for (int k = 0; k < n; ++k) os << "  a[" << k * nt << "] = v" << k << ";\n";
+  else
+    for (int w0 = 0; w0 < words;)
+    {
+      int c = 16;
+      while (c > words - w0) c >>= 1;
+      os << "  asm volatile(\"tcgen05.st.sync.aligned.32x32b.x" << c << ".b32 [%0], {";
+      for (int k = 0; k < c; ++k) os << (k ? ", " : "") << "%" << k + 1;
+      os << "};\" ::\"r\"(a + " << w0 << ")";
+      for (int k = 0; k < c; ++k) os << ", \"r\"(" << word(w0 + k) << ")";
+      os << " : \"memory\");\n";
+      w0 += c;
+    }
+  os << "}\n";
+  // load
+  os << "__device__ __forceinline__ void park_ld" << sp << n << "(" << (space == 0 ? "unsigned a" : "const real * a");
+  for (int k = 0; k < n; ++k) os << ", real & v" << k;
+  os << ")\n{\n";
+  if (space == 1)
+    for (int k = 0; k < n; ++k) os << "  v" << k << " = a[" << k * nt << "];\n";
+  else
+  {
+    os << "  unsigned w[" << words << "];\n  asm volatile(\"tcgen05.wait::st.sync.aligned;\" ::: \"memory\");\n";
+    for (int w0 = 0; w0 < words;)
+    {
+      int c = 16;
+      while (c > words - w0) c >>= 1;
+      os << "  asm volatile(\"tcgen05.ld.sync.aligned.32x32b.x" << c << ".b32 {";
+      for (int k = 0; k < c; ++k) os << (k ? ", " : "") << "%" << k;
+      os << "}, [%" << c << "];\" : ";
+      for (int k = 0; k < c; ++k) os << (k ? ", " : "") << "\"=r\"(w[" << w0 + k << "])";
+      os << " : \"r\"(a + " << w0 << ") : \"memory\");\n";
+      w0 += c;
+    }
+    os << "  asm volatile(\"tcgen05.wait::ld.sync.aligned;\" ::: \"memory\");\n";
+    for (int k = 0; k < n; ++k)
+    {
+      if (fp32) os << "  v" << k << " = __uint_as_float(w[" << k << "]);\n";
+      else os << "  v" << k << " = __hiloint2double((int)w[" << 2 * k + 1 << "], (int)w[" << 2 * k << "]);\n";
+    }
+  }
+  os << "}\n";
+}
+
+// Device wrapper.  A warp owns 32 consecutive configurations per round of the persistent grid.  Its q / v / x columns (the
+// caller's layout: one configuration = `rows` contiguous elements) are copied with COALESCED loads into a per-warp tile in
+// shared memory, row per configuration with an odd pitch, so that each lane then walks its own row conflict-free; the result
+// overwrites the x row and leaves through the same tile with coalesced stores.  (First version: one strided LDG per element and
+// lane, 32 sectors per instruction — the generated RNEA was bound by exactly that.)
+std::string wrap_device(const std::string & body, const char * name, bool fp32, int nrec, const cg::EmitStats & st, int nt, int minb,
+                        int tmem_cols, int nq, int nv, int copies, bool direct_io)
+{
+  std::ostringstream os;
+  // direct_io: no shared-memory tiles, every lane reads / writes its own column in global memory (strided, through L1); leaves
+  // shared memory free, so more warps fit per SM
+  const int qp = nq | 1, vp = nv | 1, tile = direct_io ? 0 : 32 * (qp + 2 * vp), warps = nt / 32;
+  os << "// generated by pinocchio_b200 codegen: " << name << (fp32 ? " (FP32)" : " (FP64)") << ", " << nrec << " record slots, "
+     << st.tmem_slots << " tensor-memory + " << st.smem_slots << " shared-memory park slots per configuration\n";
+  os << math_macros(fp32);
+  os << (fp32 ? "__device__ __forceinline__ real ld_rec(const real * p) { real v; asm volatile(\"ld.global.cg.f32 %0, [%1];\" : \"=f\"(v) : \"l\"(p) : \"memory\"); return v; }\n"
+              : "__device__ __forceinline__ real ld_rec(const real * p) { real v; asm volatile(\"ld.global.cg.f64 %0, [%1];\" : \"=d\"(v) : \"l\"(p) : \"memory\"); return v; }\n");
+  // warp-cooperative tile copies: `rows` elements per configuration, configurations `ld` apart in global memory, `pitch` apart
+  // in the tile; lanes beyond the batch end re-read the last valid configuration (their results are never stored)
+  // global -> shared with cp.async (LDGSTS): every lane fires all its element copies without waiting for any of them; one
+  // wait per tile.  (A plain `t[..] = g[..]` loop serialises one L2 round trip per element: 106 of them per tile.)
+  os << "__device__ __forceinline__ void cp_elem(real * dst, const real * src)\n{\n"
+        "  asm volatile(\"cp.async.ca.shared.global [%0], [%1], " << (fp32 ? 4 : 8) << ";\" ::\"r\"((unsigned)__cvta_generic_to_shared(dst)), \"l\"(src) : \"memory\");\n}\n";
+  os << "__device__ __forceinline__ void tile_in(real * t, int pitch, const real * __restrict__ g, long long ld, int rows, int nvalid, int lane)\n{\n"
+        "  if (ld == rows && nvalid == 32)\n  {\n    int c = 0, r = lane;\n    while (r >= rows) { r -= rows; ++c; }\n"
+        "    for (int k = lane; k < 32 * rows; k += 32)\n    {\n      cp_elem(t + c * pitch + r, g + k);\n      r += 32;\n"
+        "      while (r >= rows) { r -= rows; ++c; }\n    }\n  }\n  else\n"
+        "    for (int c = 0; c < 32; ++c)\n    {\n      const long long cs = c < nvalid ? c : nvalid - 1;\n"
+        "      for (int r = lane; r < rows; r += 32) cp_elem(t + c * pitch + r, g + cs * ld + r);\n    }\n}\n";
+  os << "__device__ __forceinline__ void tile_out(real * __restrict__ g, long long ld, const real * t, int pitch, int rows, int nvalid, int lane)\n{\n"
+        "  if (ld == rows && nvalid == 32)\n  {\n    int c = 0, r = lane;\n    while (r >= rows) { r -= rows; ++c; }\n"
+        "    for (int k = lane; k < 32 * rows; k += 32)\n    {\n      g[k] = t[c * pitch + r];\n      r += 32;\n"
+        "      while (r >= rows) { r -= rows; ++c; }\n    }\n  }\n  else\n"
+        "    for (int c = 0; c < nvalid; ++c)\n      for (int r = lane; r < rows; r += 32) g[c * ld + r] = t[c * pitch + r];\n}\n";
+  if (direct_io)
+  {
+    os << (fp32 ? "__device__ __forceinline__ real ld_in(const real * p) { real v; asm volatile(\"ld.global.nc.f32 %0, [%1];\" : \"=f\"(v) : \"l\"(p)); return v; }\n"
+                : "__device__ __forceinline__ real ld_in(const real * p) { real v; asm volatile(\"ld.global.nc.f64 %0, [%1];\" : \"=d\"(v) : \"l\"(p)); return v; }\n");
+    os << "#define BRBD_IN0(k) ld_in(tq + (k))\n#define BRBD_IN1(k) ld_in(tv + (k))\n#define BRBD_IN2(k) ld_in(tx + (k))\n";
+  }
+  else
+    os << "#define BRBD_IN0(k) tq[(k)]\n#define BRBD_IN1(k) tv[(k)]\n#define BRBD_IN2(k) tx[(k)]\n";
+  // record store [CTA][slot][thread of the CTA]: a slot of a warp is one coalesced row, and the slot offset is an immediate
+  os << "#define BRBD_REC_ST(k, val) __stcg(rec + (k) * " << nt << ", (val))\n";
+  os << "#define BRBD_REC_LD(k) ld_rec(rec + (k) * " << nt << ")\n";
+  if (direct_io) os << "#define BRBD_OUT0(row, val) do { if (live) to[(row)] = (val); } while (0)\n#define BRBD_SYNC() __syncthreads()\n";
+  else os << "#define BRBD_OUT0(row, val) tx[(row)] = (val)\n#define BRBD_SYNC() __syncthreads()\n";
+  const int wpv = fp32 ? 1 : 2;
+  for (const auto & sh : st.park_shapes)
+  {
+    emit_park_helpers(os, sh.first, sh.second, fp32, nt);
+    const char sp = sh.second == 0 ? 'T' : 'S';
+    const std::string base = sh.second == 0 ? "tm + (s) * " + std::to_string(wpv) : "park + (s) * " + std::to_string(nt);
+    os << "#define BRBD_PARK_ST" << sp << sh.first << "(s, ...) park_st" << sp << sh.first << "(" << base << ", __VA_ARGS__)\n";
+    os << "#define BRBD_PARK_LD" << sp << sh.first << "(s, ...) park_ld" << sp << sh.first << "(" << base << ", __VA_ARGS__)\n";
+  }
+  // COPIES identical kernels (brbd_gen_<name>_<c>): the same code at DIFFERENT addresses, launched side by side on a slice of
+  // the batch each (launch_gen.cu).  With one copy all 148 SMs stream the same instruction lines from L2 at the same time and a
+  // pass of the 35-dof humanoid ABA takes 124 us instead of the 63 us it takes on <= 64 SMs (scripts/gen_fetch_probe.py).
+  for (int copy = 0; copy < copies; ++copy)
+  {
+  os << "extern \"C\" __global__ void __launch_bounds__(" << nt << ", " << minb << ")\nbrbd_gen_" << name << "_" << copy
+     << "(const real * __restrict__ q, long long ldq, const real * __restrict__ v, long long ldv, const real * __restrict__ x, long long ldx,\n"
+        "     real * __restrict__ out, long long ldo, real * __restrict__ recbase, long long B)\n{\n";
+  os << "  extern __shared__ __align__(16) unsigned char smem_raw[];\n  real * smem = reinterpret_cast<real *>(smem_raw);\n";
+  os << "  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;\n";
+  if (!direct_io)
+  {
+    os << "  real * tile_q = smem + warp * " << tile << ";\n  real * tile_v = tile_q + " << 32 * qp << ";\n  real * tile_x = tile_v + " << 32 * vp << ";\n";
+    os << "  real * tq = tile_q + lane * " << qp << ";\n  real * tv = tile_v + lane * " << vp << ";\n  real * tx = tile_x + lane * " << vp << ";\n";
+  }
+  os << "  real * park = smem + " << warps * tile << " + threadIdx.x;\n";
+  os << "  unsigned tm = 0;\n";
+  if (st.tmem_slots > 0)
+  { // the CTA's tensor-memory columns: warp w works in lane quadrant w % 4, warps 4.. in a second column range
+    os << "  __shared__ unsigned tmem_base_slot;\n";
+    os << "  if (warp == 0)\n  {\n";
+    os << "    asm volatile(\"tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], " << tmem_cols
+       << ";\" ::\"r\"((unsigned)__cvta_generic_to_shared(&tmem_base_slot)) : \"memory\");\n";
+    os << "    asm volatile(\"tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\" ::: \"memory\");\n  }\n";
+    os << "  asm volatile(\"tcgen05.fence::before_thread_sync;\" ::: \"memory\");\n  __syncthreads();\n"
+          "  asm volatile(\"tcgen05.fence::after_thread_sync;\" ::: \"memory\");\n";
+    os << "  tm = tmem_base_slot + ((((unsigned)warp) & 3u) * 32u << 16) + ((unsigned)warp >> 2) * " << st.tmem_slots * wpv << "u;\n";
+  }
+  if (!direct_io) os << "  for (int k = threadIdx.x; k < " << warps * tile << "; k += " << nt << ") smem[k] = BRBD_C(0.0);\n  __syncthreads();\n";
+  os << "  const long long nthreads = (long long)gridDim.x * " << nt << ";\n";
+  os << "  real * __restrict__ rec = recbase + (long long)blockIdx.x * " << (long long)nrec * nt << "ll + threadIdx.x;\n";
+  os << "  const long long rounds = (B + nthreads - 1) / nthreads;\n";
+  os << "  for (long long rd = 0; rd < rounds; ++rd)\n  {\n";
+  os << "    const long long cfg0 = rd * nthreads + (long long)blockIdx.x * " << nt << " + warp * 32; // first configuration of the warp's tile\n";
+  // a warp whose tile lies beyond the batch still walks the body (the CTA barriers in it count every warp) on whatever its
+  // tile holds, and stores nothing
+  if (direct_io)
+  {
+    os << "    const long long cfg_raw = cfg0 + lane;\n    const bool live = cfg_raw < B;\n    const long long cfg = live ? cfg_raw : B - 1;\n";
+    os << "    const real * __restrict__ tq = q + cfg * ldq;\n    const real * __restrict__ tv = v + cfg * ldv;\n"
+          "    const real * __restrict__ tx = x + cfg * ldx;\n    real * __restrict__ to = out + cfg * ldo;\n";
+  }
+  else
+  {
+    os << "    const int nvalid = cfg0 >= B ? 0 : (int)(B - cfg0 < 32 ? B - cfg0 : 32);\n";
+    os << "    if (nvalid > 0)\n    {\n";
+    os << "      tile_in(tile_q, " << qp << ", q + cfg0 * ldq, ldq, " << nq << ", nvalid, lane);\n";
+    os << "      tile_in(tile_v, " << vp << ", v + cfg0 * ldv, ldv, " << nv << ", nvalid, lane);\n";
+    os << "      tile_in(tile_x, " << vp << ", x + cfg0 * ldx, ldx, " << nv << ", nvalid, lane);\n    }\n";
+    os << "    asm volatile(\"cp.async.wait_all;\" ::: \"memory\");\n    __syncwarp();\n";
+  }
+  os << "    {\n" << body << "    }\n";
+  if (!direct_io)
+  {
+    os << "    __syncwarp();\n";
+    os << "    if (nvalid > 0) tile_out(out + cfg0 * ldo, ldo, tile_x, " << vp << ", " << nv << ", nvalid, lane);\n";
+    os << "    __syncwarp();\n";
+  }
+  os << "  }\n";
+  if (st.tmem_slots > 0)
+  {
+    os << "  asm volatile(\"tcgen05.wait::st.sync.aligned;\" ::: \"memory\");\n";
+    os << "  asm volatile(\"tcgen05.fence::before_thread_sync;\" ::: \"memory\");\n  __syncthreads();\n";
+    os << "  if (warp == 0)\n    asm volatile(\"tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, " << tmem_cols
+       << ";\" ::\"r\"(tmem_base_slot) : \"memory\");\n";
+  }
+  os << "}\n";
+  } // copies
+  return os.str();
+}
+
+std::string wrap_host(const std::string & body, const char * name, bool fp32, const cg::EmitStats & st)
+{
+  std::ostringstream os;
+  os << "// generated by pinocchio_b200 codegen (host variant, C++, tests only): " << name << "\n#include <math.h>\n";
+  os << math_macros(fp32);
+  os << "#define BRBD_IN0(k) qc[(k)]\n#define BRBD_IN1(k) vc[(k)]\n#define BRBD_IN2(k) xc[(k)]\n";
+  os << "#define BRBD_REC_ST(k, val) rec[(k)] = (val)\n#define BRBD_REC_LD(k) rec[(k)]\n#define BRBD_OUT0(row, val) oc[(row)] = (val)\n";
+  for (const auto & sh : st.park_shapes)
+  { // plain C: one pair of functions per group shape; tensor-memory groups sit after the shared-memory ones in `park`
+    const char sp = sh.second == 0 ? 'T' : 'S';
+    const int off = sh.second == 0 ? st.smem_slots : 0;
+    os << "static void park_st" << sp << sh.first << "(real * a";
+    for (int k = 0; k < sh.first; ++k) os << ", real v" << k;
+    os << ") {";
+    for (int k = 0; k < sh.first; ++k) os << " a[" << k << "] = v" << k << ";";
+    os << " }\nstatic void park_ld" << sp << sh.first << "(const real * a";
+    for (int k = 0; k < sh.first; ++k) os << ", real & v" << k;
+    os << ") {";
+    for (int k = 0; k < sh.first; ++k) os << " v" << k << " = a[" << k << "];";
+    os << " }\n";
+    os << "#define BRBD_PARK_ST" << sp << sh.first << "(s, ...) park_st" << sp << sh.first << "(park + " << off << " + (s), __VA_ARGS__)\n";
+    os << "#define BRBD_PARK_LD" << sp << sh.first << "(s, ...) park_ld" << sp << sh.first << "(park + " << off << " + (s), __VA_ARGS__)\n";
+  }
+  os << "extern \"C\" void brbd_gen_" << name << "_host(const real * qc, const real * vc, const real * xc, real * oc, real * rec, real * park)\n{\n";
+  os << body << "}\n";
+  return os.str();
+}
+} // namespace
+
+extern "C" {
+
+brbd_status brbd_codegen_source(const brbd_model * m, int algo, int flags, char ** source, brbd_codegen_info * info)
+{
+  if (!m || !source) return fail(BRBD_EINVAL, "null argument");
+  *source = nullptr;
+  if (algo != BRBD_GEN_RNEA && algo != BRBD_GEN_ABA) return fail(BRBD_EINVAL, "code generation: unknown algorithm");
+  cg::Tracer T(m->pd, (flags & BRBD_GEN_EXPLICIT_SLOTS) != 0);
+  if (algo == BRBD_GEN_ABA) cg::trace_aba(T);
+  else cg::trace_rnea(T);
+  cg::EmitStats st;
+  const int nt = (flags >> 8) & 0xfff ? (flags >> 8) & 0xfff : 128;
+  const int minb = (flags >> 20) & 0xf ? (flags >> 20) & 0xf : 1;
+  const bool fp32 = (flags & BRBD_GEN_FP32) != 0;
+  const bool direct_io = (flags & BRBD_GEN_DIRECT_IO) != 0;
+  // tensor memory: 512 columns of 32 bit per SM, shared by the resident CTAs; a CTA's warps 0-3 / 4-7 / ... use their lane
+  // quadrant, so the columns split over ceil(warps / 4) ranges
+  const int wpv = fp32 ? 1 : 2, ranges = (nt / 32 + 3) / 4;
+  const int cols_per_cta = 512 / (minb > 0 ? minb : 1);
+  int tmem_cols = 32;
+  while (tmem_cols * 2 <= cols_per_cta) tmem_cols *= 2;
+  const int tmem_capacity = (flags & BRBD_GEN_EXPLICIT_SLOTS) ? tmem_cols / ranges / wpv : 0;
+  // copies of the body at different code addresses (see wrap_device): 1 below ~6000 statements, 3 above
+  int copies = 1;
+  if (const char * e = std::getenv("BRBD_GEN_COPIES")) copies = std::max(1, std::min(8, std::atoi(e)));
+  int sync_every = 0;
+  if (const char * e = std::getenv("BRBD_GEN_SYNC")) sync_every = std::atoi(e);
+  if (flags & BRBD_GEN_HOST) sync_every = 0;
+  const std::string body = cg::emit_body(T.g, st, tmem_capacity, sync_every);
+  if (st.tmem_slots > 0)
+  { // allocate no more columns than the kernel uses
+    int need = 32;
+    while (need < st.tmem_slots * wpv * ranges) need *= 2;
+    tmem_cols = need;
+  }
+  const std::string src = (flags & BRBD_GEN_HOST) ? wrap_host(body, algo_name(algo), fp32, st)
+                                                  : wrap_device(body, algo_name(algo), fp32, T.nrec, st, nt, minb, tmem_cols, m->pd.nq, m->pd.nv, copies, direct_io);
+  char * buf = (char *)std::malloc(src.size() + 1);
+  if (!buf) return fail(BRBD_ENOMEM, "out of memory");
+  std::memcpy(buf, src.c_str(), src.size() + 1);
+  *source = buf;
+  if (info)
+  {
+    info->record_slots = T.nrec; info->park_slots = st.slots; info->smem_slots = st.smem_slots; info->tmem_slots = st.tmem_slots; info->nodes = st.nodes; info->live_nodes = st.live;
+    info->adds = st.add; info->muls = st.mul; info->recips = st.recip; info->sqrts = st.sqrt_; info->sincos = st.sincos;
+    info->loads = st.inputs + st.rec_ld + st.park_ld; info->stores = st.rec_st + st.park_st + st.outputs;
+    info->threads_per_block = nt;
+    info->copies = copies;
+    info->dynamic_smem_bytes = (int32_t)(((direct_io ? 0 : (size_t)(nt / 32) * 32 * ((m->pd.nq | 1) + 2 * (m->pd.nv | 1))) + (size_t)st.smem_slots * nt) * (fp32 ? 4 : 8));
+  }
+  return BRBD_OK;
+}
+void brbd_codegen_free(char * source) { std::free(source); }
+
+} // extern "C"

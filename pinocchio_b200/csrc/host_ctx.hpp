@@ -78,8 +78,31 @@ struct DeviceCtx
 };
 } // namespace brbd
 
+namespace brbd
+{
+// kernels generated for the pool's model (codegen.cu) and compiled at brbd_pool_specialize (launch_gen.cu)
+struct GenKernel
+{
+  void * lib = nullptr;    // cudaLibrary_t
+  void * kernel = nullptr; // cudaKernel_t
+  int nt = 0, nrec = 0;
+  size_t smem_bytes = 0;
+};
+// One algorithm / precision: up to three variants that differ in threads per CTA.  The generated code is hundreds of KB of
+// straight-line instructions and runs at the rate the SM can FETCH them, whatever the number of resident warps (measured:
+// scripts/gen_fetch_probe.py) — so a pass of the persistent grid costs ~ (c0 + warps) and the launch picks the variant with
+// the cheapest rounds * (c0 + warps) for the batch at hand.
+struct GenSet
+{
+  GenKernel var[3];
+  int nvar = 0;
+};
+} // namespace brbd
+
 struct brbd_pool
 {
+  brbd::GenSet gen[3][2]; // [BRBD_GEN_*][fp64, fp32]
+  int64_t gen_min_batch = 8192; // batches at least this large use a specialised kernel when there is one
   brbd_model model;
   std::vector<brbd::DeviceCtx> devs;
   int64_t launches = 0;
@@ -308,6 +331,16 @@ brbd_status launch_rnea_derivs_v1(brbd_pool * p, DeviceCtx & d, const T * q, int
                                   const T * a, int64_t lda, T * dq, int64_t ld_dq, T * dv, int64_t ld_dv, T * da,
                                   int64_t ld_da, T * tau, int64_t ldtau, int64_t B);
 brbd_status measure_fp64_peak(brbd_pool * p, double * flops_per_s, double * elapsed_ms);
+// specialised kernels (launch_gen.cu)
+brbd_status specialize_one(brbd_pool * p, int algo, bool fp32, int flags);
+void release_generated(brbd_pool * p);
+template<class T>
+brbd_status launch_generated(brbd_pool * p, DeviceCtx & d, int algo, const T * q, int64_t ldq, const T * v, int64_t ldv, const T * x,
+                             int64_t ldx, T * out, int64_t ldo, int64_t B);
+template<class T> inline bool use_generated(const brbd_pool * p, int algo, int64_t B)
+{
+  return p->gen[algo][sizeof(T) == 4 ? 1 : 0].nvar > 0 && B >= p->gen_min_batch;
+}
 // BRBD_<ALGO>_V=<name> forces one device path of an algorithm (tests, experiments)
 inline bool forced_path(const char * var, const char * name)
 {

@@ -13,6 +13,7 @@ brbd_status launch_aba(brbd_pool * p, DeviceCtx & d, const T * q, int64_t ldq, c
   brbd_status st = BRBD_OK;
   const char * ver = std::getenv("BRBD_ABA_V"); // "v3" (aba_tmem_kernel), "dfs" (aba_dfs_kernel), "v1" (aba_kernel)
   if (ver && std::strcmp(ver, "v1") == 0) return launch_aba_v1<T>(p, d, q, ldq, v, ldv, tau, ldtau, a, lda, B);
+  if (!ver && use_generated<T>(p, BRBD_GEN_ABA, B)) return launch_generated<T>(p, d, BRBD_GEN_ABA, q, ldq, v, ldv, tau, ldtau, a, lda, B);
   {
     bool done = false;
     st = launch_aba_coop<T>(p, d, q, ldq, v, ldv, tau, ldtau, a, lda, B, &done);

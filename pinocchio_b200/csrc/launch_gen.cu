@@ -1,0 +1,186 @@
+// launch_gen.cu — pool specialisation: the generated source of codegen.cu is compiled with NVRTC for sm_100a, loaded with
+// the runtime's library API and launched in place of the generic kernels for large batches.
+// NVRTC is opened lazily with dlopen: the engine loads and works without it (brbd_pool_specialize then fails with
+// BRBD_ECUDA and the pool keeps its generic kernels).
+#include <dlfcn.h>
+
+#include "host_ctx.hpp"
+
+namespace brbd
+{
+namespace
+{
+struct Nvrtc
+{
+  void * h = nullptr;
+  int (*CreateProgram)(void **, const char *, const char *, int, const char * const *, const char * const *) = nullptr;
+  int (*CompileProgram)(void *, int, const char * const *) = nullptr;
+  int (*GetCUBINSize)(void *, size_t *) = nullptr;
+  int (*GetCUBIN)(void *, char *) = nullptr;
+  int (*GetProgramLogSize)(void *, size_t *) = nullptr;
+  int (*GetProgramLog)(void *, char *) = nullptr;
+  int (*DestroyProgram)(void **) = nullptr;
+  bool ok = false;
+};
+const Nvrtc & nvrtc()
+{
+  static Nvrtc n = [] {
+    Nvrtc r;
+    const char * names[] = {"libnvrtc.so.12", "libnvrtc.so", "/usr/local/cuda/lib64/libnvrtc.so.12", "/usr/local/cuda/lib64/libnvrtc.so"};
+    for (const char * nm : names)
+      if ((r.h = dlopen(nm, RTLD_NOW | RTLD_LOCAL))) break;
+    if (!r.h) return r;
+#define BRBD_SYM(field, sym) *(void **)(&r.field) = dlsym(r.h, sym)
+    BRBD_SYM(CreateProgram, "nvrtcCreateProgram");
+    BRBD_SYM(CompileProgram, "nvrtcCompileProgram");
+    BRBD_SYM(GetCUBINSize, "nvrtcGetCUBINSize");
+    BRBD_SYM(GetCUBIN, "nvrtcGetCUBIN");
+    BRBD_SYM(GetProgramLogSize, "nvrtcGetProgramLogSize");
+    BRBD_SYM(GetProgramLog, "nvrtcGetProgramLog");
+    BRBD_SYM(DestroyProgram, "nvrtcDestroyProgram");
+#undef BRBD_SYM
+    r.ok = r.CreateProgram && r.CompileProgram && r.GetCUBINSize && r.GetCUBIN && r.GetProgramLogSize && r.GetProgramLog && r.DestroyProgram;
+    return r;
+  }();
+  return n;
+}
+
+brbd_status compile_cubin(const char * source, const char * name, std::vector<char> & cubin)
+{
+  const Nvrtc & N = nvrtc();
+  if (!N.ok) return fail(BRBD_ECUDA, "specialisation needs NVRTC (libnvrtc.so.12), which could not be loaded");
+  void * prog = nullptr;
+  if (N.CreateProgram(&prog, source, name, 0, nullptr, nullptr) != 0) return fail(BRBD_ECUDA, "nvrtcCreateProgram failed");
+  const char * opts[] = {"--gpu-architecture=sm_100a", "-std=c++17", "-lineinfo", "--fmad=true"};
+  const int rc = N.CompileProgram(prog, 4, opts);
+  if (rc != 0)
+  {
+    size_t n = 0;
+    N.GetProgramLogSize(prog, &n);
+    std::string log(n, '\0');
+    if (n) N.GetProgramLog(prog, &log[0]);
+    N.DestroyProgram(&prog);
+    return fail(BRBD_ECUDA, "NVRTC compilation of the specialised kernel failed: " + log.substr(0, 2000));
+  }
+  size_t n = 0;
+  N.GetCUBINSize(prog, &n);
+  cubin.resize(n);
+  N.GetCUBIN(prog, cubin.data());
+  N.DestroyProgram(&prog);
+  return BRBD_OK;
+}
+} // namespace
+
+void release_generated(brbd_pool * p)
+{
+  for (int a = 0; a < 3; ++a)
+    for (int f = 0; f < 2; ++f)
+    {
+      GenSet & g = p->gen[a][f];
+      for (int k = 0; k < g.nvar; ++k)
+        if (g.var[k].lib) cudaLibraryUnload((cudaLibrary_t)g.var[k].lib);
+      g = GenSet();
+    }
+}
+
+namespace
+{
+const char * kAlgoNames[] = {"rnea", "aba", "crba"};
+
+// generate + compile + load one variant; BRBD_OK with k.kernel == nullptr when it does not fit the SM (too much shared memory)
+brbd_status build_variant(brbd_pool * p, int algo, bool fp32, int nt, bool direct, bool slots, GenKernel & k)
+{
+  char * src = nullptr;
+  brbd_codegen_info info;
+  const int gflags = (direct ? BRBD_GEN_DIRECT_IO : 0) | (slots ? BRBD_GEN_EXPLICIT_SLOTS : 0) | (fp32 ? BRBD_GEN_FP32 : 0) | (nt << 8) | (1 << 20);
+  brbd_status st = brbd_codegen_source(&p->model, algo, gflags, &src, &info);
+  if (st != BRBD_OK) return st;
+  if ((size_t)info.dynamic_smem_bytes + 2048 > (size_t)p->devs[0].max_smem_optin)
+  {
+    brbd_codegen_free(src);
+    return BRBD_OK;
+  }
+  std::vector<char> cubin;
+  st = compile_cubin(src, (std::string("brbd_gen_") + kAlgoNames[algo] + ".cu").c_str(), cubin);
+  brbd_codegen_free(src);
+  if (st != BRBD_OK) return st;
+  cudaLibrary_t lib = nullptr;
+  CUDA_TRY(cudaLibraryLoadData(&lib, cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0));
+  cudaKernel_t kern = nullptr;
+  const cudaError_t e = cudaLibraryGetKernel(&kern, lib, (std::string("brbd_gen_") + kAlgoNames[algo] + "_0").c_str());
+  if (e != cudaSuccess)
+  {
+    cudaLibraryUnload(lib);
+    return fail(BRBD_ECUDA, std::string("cudaLibraryGetKernel: ") + cudaGetErrorString(e));
+  }
+  k.smem_bytes = (size_t)info.dynamic_smem_bytes;
+  if (k.smem_bytes > 48 * 1024)
+    for (const DeviceCtx & d : p->devs)
+      CUDA_TRY(cudaKernelSetAttributeForDevice(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k.smem_bytes, d.dev));
+  k.lib = lib; k.kernel = kern; k.nt = nt; k.nrec = info.record_slots;
+  return BRBD_OK;
+}
+} // namespace
+
+brbd_status specialize_one(brbd_pool * p, int algo, bool fp32, int flags)
+{
+  GenSet & g = p->gen[algo][fp32 ? 1 : 0];
+  if (g.nvar > 0) return BRBD_OK;
+  // RNEA: warp tiles of q / v / a in shared memory (coalesced), as many warps (<= 8) as the tiles leave room for — its state
+  // stays in registers.  ABA: long-lived values in explicit tensor-memory slots (168 registers and no spills at 12 warps for a
+  // 35-dof humanoid), no tiles, 14 and 16 warps per SM: see GenSet.
+  std::vector<int> nts;
+  bool direct = algo == BRBD_GEN_ABA, slots = algo == BRBD_GEN_ABA || (flags & BRBD_GEN_EXPLICIT_SLOTS);
+  if (const char * e = std::getenv("BRBD_GEN_SLOTS")) slots = std::atoi(e) != 0;
+  if (const char * e = std::getenv("BRBD_GEN_DIRECT")) direct = std::atoi(e) != 0;
+  if (const char * e = std::getenv("BRBD_GEN_NT")) nts.push_back(std::max(32, std::min(1024, std::atoi(e) / 32 * 32)));
+  else if (direct) nts = {448, 512, 256};
+  else
+  {
+    const size_t tile_bytes = (size_t)32 * ((p->model.pd.nq | 1) + 2 * (p->model.pd.nv | 1)) * (fp32 ? 4 : 8);
+    nts = {32 * (int)std::max<size_t>(1, std::min<size_t>(8, ((size_t)p->devs[0].max_smem_optin - 2048) / tile_bytes))};
+  }
+  for (int nt : nts)
+  {
+    if (g.nvar >= 2 && nt == 256) break; // 8 warps only when the larger variants do not fit
+    GenKernel k;
+    brbd_status st = build_variant(p, algo, fp32, nt, direct, slots, k);
+    if (st != BRBD_OK) return st;
+    if (k.kernel) g.var[g.nvar++] = k;
+  }
+  if (g.nvar == 0) return fail(BRBD_EINVAL, "specialisation: the model's long-lived state does not fit the SM; the generic kernels remain in use");
+  return BRBD_OK;
+}
+
+// one generated kernel: q, v, x (tau or a) -> out
+template<class T>
+brbd_status launch_generated(brbd_pool * p, DeviceCtx & d, int algo, const T * q, int64_t ldq, const T * v, int64_t ldv, const T * x,
+                             int64_t ldx, T * out, int64_t ldo, int64_t B)
+{
+  const GenSet & g = p->gen[algo][sizeof(T) == 4 ? 1 : 0];
+  // cheapest rounds * (c0 + warps); c0 = 9 measured on the 35-dof humanoid ABA (one pass: 0.124 ms at 8 warps, 0.178 at 16)
+  int best = 0;
+  int64_t best_cost = -1;
+  for (int k = 0; k < g.nvar; ++k)
+  {
+    const int64_t per_round = (int64_t)d.sm_count * g.var[k].nt;
+    const int64_t cost = ((B + per_round - 1) / per_round) * (9 + g.var[k].nt / 32);
+    if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = k; }
+  }
+  const GenKernel & k = g.var[best];
+  const int64_t ctas_needed = (B + k.nt - 1) / k.nt;
+  const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(ctas_needed, (int64_t)d.sm_count));
+  brbd_status st = ensure_work(d, std::max<size_t>(8, (size_t)k.nrec * grid * k.nt * sizeof(T)));
+  if (st != BRBD_OK) return st;
+  long long ldq_ = ldq, ldv_ = ldv, ldx_ = ldx, ldo_ = ldo, B_ = B;
+  T * rec = (T *)d.work;
+  void * args[] = {(void *)&q, &ldq_, (void *)&v, &ldv_, (void *)&x, &ldx_, (void *)&out, &ldo_, (void *)&rec, &B_};
+  CUDA_TRY(cudaLaunchKernel((const void *)k.kernel, dim3(grid), dim3(k.nt), args, k.smem_bytes, d.s()));
+  p->launches += 1;
+  return BRBD_OK;
+}
+template brbd_status launch_generated<double>(brbd_pool *, DeviceCtx &, int, const double *, int64_t, const double *, int64_t, const double *,
+                                              int64_t, double *, int64_t, int64_t);
+template brbd_status launch_generated<float>(brbd_pool *, DeviceCtx &, int, const float *, int64_t, const float *, int64_t, const float *,
+                                             int64_t, float *, int64_t, int64_t);
+} // namespace brbd

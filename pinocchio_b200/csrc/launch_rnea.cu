@@ -10,6 +10,8 @@ brbd_status launch_rnea(brbd_pool * p, DeviceCtx & d, const T * q, int64_t ldq, 
 {
   const TreePOD<T> & t = tree_of<T>(p);
   if (forced_path("BRBD_RNEA_V", "v1")) return launch_rnea_v1<T>(p, d, q, ldq, v, ldv, a, lda, tau, ldtau, B);
+  if (!std::getenv("BRBD_RNEA_V") && use_generated<T>(p, BRBD_GEN_RNEA, B))
+    return launch_generated<T>(p, d, BRBD_GEN_RNEA, q, ldq, v, ldv, a, lda, tau, ldtau, B);
   if (B <= coop_max_batch(false, p->model.pd.nv))
   {
     const ModelPOD<double> & M = p->model.pd;

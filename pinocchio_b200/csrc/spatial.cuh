@@ -19,6 +19,10 @@ namespace brbd
 #define BRBD_SYNCWARP() __syncwarp()
 #endif
 
+// max(a, b) as the reference's math::max; an overload for the code generator's recording scalar lives in codegen/sym.hpp
+BRBD_DI double max_t(double a, double b) { return a > b ? a : b; }
+BRBD_DI float max_t(float a, float b) { return a > b ? a : b; }
+
 template<class T> struct Vec3
 {
   T x, y, z;
@@ -194,7 +198,7 @@ template<class T> struct Inertia
   {
     const T mab = m + b.m;
     const T eps = sizeof(T) == 8 ? T(2.220446049250313e-16) : T(1.1920929e-07);
-    const T mab_inv = T(1) / (mab > eps ? mab : eps);
+    const T mab_inv = T(1) / max_t(mab, eps);
     const Vec3<T> AB = c - b.c;
     const T k = m * b.m * mab_inv;
     c = (m * mab_inv) * c + (b.m * mab_inv) * b.c;

@@ -112,6 +112,26 @@ class ModelPool:
             _raise(e)
         self._stream_pinned, self._stream_handle = False, None
 
+    def specialize(self, algos=("rnea", "aba"), fp32: bool = False, min_batch: Optional[int] = None):
+        """Generate, compile (NVRTC) and load kernels specialised for this pool's model (brbd_pool_specialize): the tree
+        unrolled, joint types resolved, the model's constants folded in.  Large batches of the listed algorithms then run
+        them; results agree with the generic kernels to rounding."""
+        from .codegen import ALGOS
+        mask = 0
+        for a in algos:
+            mask |= 1 << ALGOS[a]
+        try:
+            _capi.check(_capi.lib().brbd_pool_specialize(self._h_pool, mask, 4 if fp32 else 0))
+            if min_batch is not None:
+                _capi.check(_capi.lib().brbd_pool_set_specialized_min_batch(self._h_pool, int(min_batch)))
+        except EngineError as e:
+            _raise(e)
+
+    def specialized(self):
+        from .codegen import ALGOS
+        mask = int(_capi.lib().brbd_pool_specialized(self._h_pool))
+        return [a for a, k in ALGOS.items() if mask & (1 << k)]
+
     def flat_model(self):
         """The model as the engine holds it (brbd_model_get_flat), as a dict of numpy arrays."""
         fm = _capi.FlatModel()

@@ -111,6 +111,26 @@ def make_extra_models():
     return out
 
 
+def structural_mask(model, lower=False):
+    """(nv*nv,) bool, col-major: True where the tree sparsity allows a non-zero.
+    Upper part: joint(row) is an ancestor-or-self of joint(col) (crba.hxx:94-95); with lower=True also the
+    transposed entries (rnea-derivatives.hxx:433-438)."""
+    nv = model.nv
+    dof_joint = np.zeros(nv, dtype=int)
+    for j in range(1, model.njoints):
+        dof_joint[model.idx_vs[j]:model.idx_vs[j] + model.nvs[j]] = j
+    anc = np.zeros((model.njoints, model.njoints), dtype=bool)  # anc[a, j]: a ancestor-or-self of j
+    for j in range(1, model.njoints):
+        a = j
+        while a > 0:
+            anc[a, j] = True
+            a = model.parents[a]
+    mask = anc[np.ix_(dof_joint, dof_joint)]
+    if lower:
+        mask = mask | mask.T
+    return mask.reshape(-1, order="F")
+
+
 def random_inputs(model, B, seed):
     """(q, v, a) with the reference benchmark's distributions (benchmark/timings-parallel.cpp:48-60)."""
     from pinocchio_b200.joint_configuration import batched_random_configuration, batched_random_tangent

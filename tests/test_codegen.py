@@ -1,0 +1,86 @@
+"""CPU tests of the per-model code generator (pinocchio_b200/csrc/codegen*): the generated straight-line program, emitted in
+its host-callable variant and compiled with g++, against the oracle.  The device variant of the same text is what
+brbd_pool_specialize compiles with NVRTC (GPU parity: tests/test_gpu_large.py::test_specialized_kernels).  The host variant
+exists for these tests only; nothing in the product executes it.
+Reference being mirrored: the code-generation unit tests, unittest/cppadcg-algo.cpp (generated code == algorithm)."""
+import ctypes
+import os
+import subprocess
+import tempfile
+
+import numpy as np
+import pytest
+
+from conftest import MODEL_NAMES, load_model, make_extra_models, random_inputs
+
+ALL = MODEL_NAMES + ["mixed", "double_ff", "unaligned", "humanoid_hands"]
+EXTRA = make_extra_models()
+
+
+def build_host(model, algo, explicit_slots, tmp):
+    from pinocchio_b200.codegen import codegen_source
+    src, info = codegen_source(model, algo, explicit_slots=explicit_slots, host=True)
+    cpp = os.path.join(tmp, f"gen_{algo}_{int(explicit_slots)}.cpp")
+    with open(cpp, "w") as fh:
+        fh.write(src)
+    so = cpp[:-4] + ".so"
+    cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+    subprocess.check_call([cxx, "-O1", "-shared", "-fPIC", "-ffp-contract=off", "-o", so, cpp, "-lm"])
+    return getattr(ctypes.CDLL(so), f"brbd_gen_{algo}_host"), info
+
+
+def run_host(fn, info, model, q, v, x):
+    B = q.shape[1]
+    out = np.zeros((model.nv, B), order="F")
+    rec, park = np.full(max(1, info["record_slots"]), np.nan), np.full(max(1, info["park_slots"]), np.nan)
+    P = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    for i in range(B):
+        qi, vi, xi = (np.ascontiguousarray(a[:, i]) for a in (q, v, x))
+        oi = np.zeros(model.nv)
+        rec[:] = np.nan  # a read of a slot nobody wrote would poison the result
+        park[:] = np.nan
+        fn(P(qi), P(vi), P(xi), P(oi), P(rec), P(park))
+        out[:, i] = oi
+    return out
+
+
+@pytest.mark.parametrize("name", ALL)
+@pytest.mark.parametrize("explicit_slots", [False, True])
+def test_generated_program_matches_the_oracle(oracle_cls, name, explicit_slots):
+    model = EXTRA[name] if name in EXTRA else load_model(name)
+    orc = oracle_cls(model)
+    q, v, x = random_inputs(model, 6, 11)
+    with tempfile.TemporaryDirectory() as tmp:
+        for algo, ref in (("rnea", orc.rnea(q, v, x)), ("aba", orc.aba(q, v, x))):
+            fn, info = build_host(model, algo, explicit_slots, tmp)
+            got = run_host(fn, info, model, q, v, x)
+            assert np.isfinite(got).all(), (name, algo)
+            assert np.abs(got - ref).max() <= 1e-11 * max(1.0, np.abs(ref).max()), (name, algo, np.abs(got - ref).max())
+            if explicit_slots and algo == "aba" and model.njoints > 3:
+                assert info["park_slots"] > 0
+
+
+def test_constant_folding_shrinks_the_program(oracle_cls):
+    """simple_humanoid's placements are identity rotations: the generated ABA executes far fewer operations than the
+    algorithm's count on a general model (26 103, the oracle's counting scalar), and the model's constants never appear as loads."""
+    from pinocchio_b200.codegen import codegen_source
+    model = load_model("simple_humanoid_ff")
+    _, info = codegen_source(model, "aba")
+    orc = oracle_cls(model)
+    q, v, x = random_inputs(model, 1, 3)
+    counted = orc.count_flops("aba", q[:, 0], v[:, 0], x[:, 0])["flops"]
+    assert info["adds"] + info["muls"] < 0.75 * counted
+    assert info["sincos"] == 29 and info["record_slots"] > 0
+    src, _ = codegen_source(model, "aba", explicit_slots=True, nt=448)
+    assert "tcgen05.st" in src and "brbd_gen_aba_0" in src
+
+
+def test_codegen_rejects_unknown_algorithm():
+    from pinocchio_b200 import _capi
+    from pinocchio_b200.codegen import codegen_source, ALGOS
+    ALGOS["bogus"] = 7
+    try:
+        with pytest.raises(_capi.EngineError):
+            codegen_source(load_model("manipulator"), "bogus")
+    finally:
+        del ALGOS["bogus"]

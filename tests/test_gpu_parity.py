@@ -7,11 +7,11 @@ and extends it to crba / computeRNEADerivatives / computeABADerivatives.
 import numpy as np
 import pytest
 
-from conftest import MODEL_NAMES, assert_close, load_model, make_extra_models, random_inputs
+from conftest import MODEL_NAMES, assert_close, load_model, make_extra_models, random_inputs, structural_mask
 
 pytestmark = pytest.mark.gpu
 
-ALL_MODELS = MODEL_NAMES + ["mixed", "double_ff", "unaligned"]
+ALL_MODELS = MODEL_NAMES + ["mixed", "double_ff", "unaligned", "humanoid_hands"]
 
 
 @pytest.fixture(scope="module")
@@ -28,26 +28,6 @@ def ctx(oracle_cls):
     yield get
     for _, pool, _ in cache.values():
         pool.close()
-
-
-def structural_mask(model, lower=False):
-    """(nv*nv,) bool, col-major: True where the tree sparsity allows a non-zero.
-    Upper part: joint(row) is an ancestor-or-self of joint(col) (crba.hxx:94-95); with lower=True also the
-    transposed entries (rnea-derivatives.hxx:433-438)."""
-    nv = model.nv
-    dof_joint = np.zeros(nv, dtype=int)
-    for j in range(1, model.njoints):
-        dof_joint[model.idx_vs[j]:model.idx_vs[j] + model.nvs[j]] = j
-    anc = np.zeros((model.njoints, model.njoints), dtype=bool)  # anc[a, j]: a ancestor-or-self of j
-    for j in range(1, model.njoints):
-        a = j
-        while a > 0:
-            anc[a, j] = True
-            a = model.parents[a]
-    mask = anc[np.ix_(dof_joint, dof_joint)]
-    if lower:
-        mask = mask | mask.T
-    return mask.reshape(-1, order="F")
 
 
 @pytest.mark.parametrize("name", ALL_MODELS)
