@@ -689,7 +689,8 @@ BRBD_DI void coop_dblock_product_dispatch(int nv, const T * Minv, int mld, const
     case 1: case 2: case 3: coop_dblock_product<T, G, 3>(nv, Minv, mld, Dblk, c0, gq, gv, gl, active); break;
     case 4: coop_dblock_product<T, G, 4>(nv, Minv, mld, Dblk, c0, gq, gv, gl, active); break;
     case 5: coop_dblock_product<T, G, 5>(nv, Minv, mld, Dblk, c0, gq, gv, gl, active); break;
-    default: coop_dblock_product<T, G, 6>(nv, Minv, mld, Dblk, c0, gq, gv, gl, active); break;
+    case 6: coop_dblock_product<T, G, 6>(nv, Minv, mld, Dblk, c0, gq, gv, gl, active); break;
+    default: coop_dblock_product<T, G, 8>(nv, Minv, mld, Dblk, c0, gq, gv, gl, active); break; // nv <= 64 = MAXNV
     }
   }
   else if (G == 16)

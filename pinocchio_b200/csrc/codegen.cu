@@ -93,7 +93,7 @@ void emit_park_helpers(std::ostringstream & os, int n, int space, bool fp32, int
 // overwrites the x row and leaves through the same tile with coalesced stores.  (First version: one strided LDG per element and
 // lane, 32 sectors per instruction — the generated RNEA was bound by exactly that.)
 std::string wrap_device(const std::string & body, const char * name, bool fp32, int nrec, const cg::EmitStats & st, int nt, int minb,
-                        int tmem_cols, int nq, int nv, int copies, bool direct_io)
+                        int tmem_cols, int nq, int nv, int copies, bool direct_io, const std::string & ktable)
 {
   std::ostringstream os;
   // direct_io: no shared-memory tiles, every lane reads / writes its own column in global memory (strided, through L1); leaves
@@ -101,7 +101,7 @@ std::string wrap_device(const std::string & body, const char * name, bool fp32, 
   const int qp = nq | 1, vp = nv | 1, tile = direct_io ? 0 : 32 * (qp + 2 * vp), warps = nt / 32;
   os << "// generated by pinocchio_b200 codegen: " << name << (fp32 ? " (FP32)" : " (FP64)") << ", " << nrec << " record slots, "
      << st.tmem_slots << " tensor-memory + " << st.smem_slots << " shared-memory park slots per configuration\n";
-  os << math_macros(fp32);
+  os << math_macros(fp32) << ktable;
   os << (fp32 ? "__device__ __forceinline__ real ld_rec(const real * p) { real v; asm volatile(\"ld.global.cg.f32 %0, [%1];\" : \"=f\"(v) : \"l\"(p) : \"memory\"); return v; }\n"
               : "__device__ __forceinline__ real ld_rec(const real * p) { real v; asm volatile(\"ld.global.cg.f64 %0, [%1];\" : \"=d\"(v) : \"l\"(p) : \"memory\"); return v; }\n");
   // warp-cooperative tile copies: `rows` elements per configuration, configurations `ld` apart in global memory, `pitch` apart
@@ -214,11 +214,11 @@ std::string wrap_device(const std::string & body, const char * name, bool fp32, 
   return os.str();
 }
 
-std::string wrap_host(const std::string & body, const char * name, bool fp32, const cg::EmitStats & st)
+std::string wrap_host(const std::string & body, const char * name, bool fp32, const cg::EmitStats & st, const std::string & ktable)
 {
   std::ostringstream os;
   os << "// generated by pinocchio_b200 codegen (host variant, C++, tests only): " << name << "\n#include <math.h>\n";
-  os << math_macros(fp32);
+  os << math_macros(fp32) << ktable;
   os << "#define BRBD_IN0(k) qc[(k)]\n#define BRBD_IN1(k) vc[(k)]\n#define BRBD_IN2(k) xc[(k)]\n";
   os << "#define BRBD_REC_ST(k, val) rec[(k)] = (val)\n#define BRBD_REC_LD(k) rec[(k)]\n#define BRBD_OUT0(row, val) oc[(row)] = (val)\n";
   for (const auto & sh : st.park_shapes)
@@ -271,15 +271,17 @@ brbd_status brbd_codegen_source(const brbd_model * m, int algo, int flags, char 
   int sync_every = 0;
   if (const char * e = std::getenv("BRBD_GEN_SYNC")) sync_every = std::atoi(e);
   if (flags & BRBD_GEN_HOST) sync_every = 0;
-  const std::string body = cg::emit_body(T.g, st, tmem_capacity, sync_every);
+  cg::ConstTable K;
+  const std::string body = cg::emit_body(T.g, st, K, tmem_capacity, sync_every);
   if (st.tmem_slots > 0)
   { // allocate no more columns than the kernel uses
     int need = 32;
     while (need < st.tmem_slots * wpv * ranges) need *= 2;
     tmem_cols = need;
   }
-  const std::string src = (flags & BRBD_GEN_HOST) ? wrap_host(body, algo_name(algo), fp32, st)
-                                                  : wrap_device(body, algo_name(algo), fp32, T.nrec, st, nt, minb, tmem_cols, m->pd.nq, m->pd.nv, copies, direct_io);
+  const std::string src = (flags & BRBD_GEN_HOST) ? wrap_host(body, algo_name(algo), fp32, st, K.definition("static const"))
+                                                  : wrap_device(body, algo_name(algo), fp32, T.nrec, st, nt, minb, tmem_cols, m->pd.nq, m->pd.nv, copies,
+                                                                direct_io, K.definition("__constant__"));
   char * buf = (char *)std::malloc(src.size() + 1);
   if (!buf) return fail(BRBD_ENOMEM, "out of memory");
   std::memcpy(buf, src.c_str(), src.size() + 1);

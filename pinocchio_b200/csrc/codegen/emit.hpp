@@ -28,14 +28,44 @@ struct EmitStats
   std::set<std::pair<int, int>> park_shapes; // (number of values, space: 0 tensor memory, 1 shared memory) of the park groups
 };
 
-inline std::string lit(double v)
+inline std::string lit_text(double v)
 {
   char buf[64];
   std::snprintf(buf, sizeof buf, "%.17g", v);
   std::string s(buf);
   if (s.find_first_of(".eEn") == std::string::npos) s += ".0";
-  return "BRBD_C(" + s + ")";
+  return s;
 }
+// Constants.  A double whose low 32 bits are zero (0.5, 2, -1, ...) is an immediate operand of DFMA / DMUL / DADD; any other
+// one costs two UMOV to materialise when written as a literal (970 of the 16 k instructions of the humanoid ABA).  Those go
+// to a __constant__ table instead and are read as c[bank][offset] operands: no instruction at all.
+struct ConstTable
+{
+  std::vector<double> vals;
+  std::map<uint64_t, int> index;
+  std::string ref(double v)
+  {
+    uint64_t bits;
+    std::memcpy(&bits, &v, 8);
+    if ((bits & 0xffffffffull) == 0) return "BRBD_C(" + lit_text(v) + ")";
+    auto it = index.find(bits);
+    if (it == index.end())
+    {
+      it = index.emplace(bits, (int)vals.size()).first;
+      vals.push_back(v);
+    }
+    return "BRBD_K[" + std::to_string(it->second) + "]";
+  }
+  std::string definition(const char * qualifier) const
+  {
+    std::ostringstream os;
+    os << qualifier << " real BRBD_K[" << (vals.empty() ? 1 : vals.size()) << "] = {";
+    for (size_t k = 0; k < vals.size(); ++k) os << (k ? ", " : "") << "BRBD_C(" << lit_text(vals[k]) << ")";
+    if (vals.empty()) os << "BRBD_C(0.0)";
+    os << "};\n";
+    return os.str();
+  }
+};
 
 // Emits the body.  `slots_out`: number of explicit park slots the body needs (0 when the tracer did not park explicitly).
 // `tmem_capacity`: values per configuration that fit in the warp's tensor-memory slice; park groups beyond it go to shared memory
@@ -43,7 +73,7 @@ inline std::string lit(double v)
 // hundreds of KB of straight-line code, far beyond the instruction caches (L0 ~6 KB per scheduler, L1.5 32 KB per SM): warps
 // that drift apart each stream it from L2 on their own and starve (ncu: 66 % of the stall samples `no_instruction`); kept within
 // one cache window of each other they share ONE sequential, prefetchable stream.
-inline std::string emit_body(const Graph & g, EmitStats & st, int tmem_capacity = 0, int sync_every = 0)
+inline std::string emit_body(const Graph & g, EmitStats & st, ConstTable & K, int tmem_capacity = 0, int sync_every = 0)
 {
   const int N = (int)g.nodes.size();
   // ---- liveness: outputs and record stores are roots; a live FETCH keeps its parked value alive -------------------
@@ -136,7 +166,7 @@ inline std::string emit_body(const Graph & g, EmitStats & st, int tmem_capacity 
   std::vector<char> emitted(N, 0);
   auto name = [&](int id) -> std::string {
     const Node & n = g.nodes[id];
-    if (n.op == OP_CONST) return lit(n.val);
+    if (n.op == OP_CONST) return K.ref(n.val);
     return "t" + std::to_string(id);
   };
   // sin / cos of the same argument leave as one sincos
