@@ -282,7 +282,7 @@ def main():
         c0, c1 = column_range(Btot, world, rank)
         B = c1 - c0
     pool = pb.ModelPool(model, [local_rank])
-    spec = [] if args.generic else [k for k in algos if k in ("rnea", "aba")]
+    spec = [] if args.generic else [k for k in algos if k in ("rnea", "aba", "crba")]
     if spec:
         pool.specialize(spec)  # kernels generated for this model (codegen + NVRTC), outside the timed region like the pool itself
     stream = torch.cuda.current_stream()

@@ -214,9 +214,102 @@ std::string wrap_device(const std::string & body, const char * name, bool fp32, 
   return os.str();
 }
 
-std::string wrap_host(const std::string & body, const char * name, bool fp32, const cg::EmitStats & st, const std::string & ktable)
+// Device wrappers of the generated CRBA.  Every lane computes the entries of one column of ITS configuration's matrix into
+// its row of the warp's staging tile; the tile then leaves as column `col` of 32 consecutive configurations:
+//   brbd_gen_crba_0   : the warp writes the 32 segments of nv elements with coalesced stores (any layout); the flush is a small
+//                       rolled loop that stays in the instruction cache, only the arithmetic is straight-line;
+//   brbd_gen_crba_tma : ONE cp.async.bulk.tensor.2d store per column and warp (two with an odd leading dimension), issued
+//                       by one lane and asynchronous — the scheme of crba_tma_kernel (crba_dfs.cuh), including its shifted boxes
+//                       for odd nv: same tensor maps (crba_tma_setup), same CrbaTmaGeom.
+// q is read directly (nq strided loads per lane).
+std::string wrap_device_crba(const std::string & body, bool fp32, const cg::EmitStats & st, int nt, int nq, int nv, const std::string & ktable, int nbuf)
 {
   std::ostringstream os;
+  const int pitch = nv | 1;       // LSU variant: odd pitch, conflict-free rows
+  const int epad = nv + (nv & 1); // TMA variant: the box's inner extent (even: rows stay 16-byte aligned)
+  os << "// generated by pinocchio_b200 codegen: crba" << (fp32 ? " (FP32)" : " (FP64)") << "\n";
+  os << math_macros(fp32) << ktable;
+  os << (fp32 ? "__device__ __forceinline__ real ld_in(const real * p) { real v; asm volatile(\"ld.global.nc.f32 %0, [%1];\" : \"=f\"(v) : \"l\"(p)); return v; }\n"
+              : "__device__ __forceinline__ real ld_in(const real * p) { real v; asm volatile(\"ld.global.nc.f64 %0, [%1];\" : \"=d\"(v) : \"l\"(p)); return v; }\n");
+  os << "#define BRBD_IN0(k) ld_in(tq + (k))\n#define BRBD_SYNC()\n";
+  os << "struct __align__(64) TensorMap { unsigned long long opaque[16]; };\n";
+  // column `col` of the warp's configurations: element k = c * nv + r of the staging buffer goes to gM[c * ldM + r]
+  os << "__device__ __noinline__ void flush_col(real * colbuf, real * __restrict__ g, long long ldM, int nvalid, int lane)\n{\n"
+        "  __syncwarp();\n  int c = 0, r = lane;\n  while (r >= " << nv << ") { r -= " << nv << "; ++c; }\n"
+        "  const int total = nvalid * " << nv << ";\n"
+        "#pragma unroll 4\n  for (int k = lane; k < total; k += 32)\n  {\n    g[c * ldM + r] = colbuf[c * " << pitch << " + r];\n    r += 32;\n"
+        "    while (r >= " << nv << ") { r -= " << nv << "; ++c; }\n  }\n  __syncwarp();\n}\n";
+  os << "__device__ __forceinline__ void tma_store_2d(const void * tmap, const void * ssrc, int x, int y)\n{\n"
+        "  asm volatile(\"cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];\" ::\"l\"(tmap),\n"
+        "               \"r\"((unsigned)__cvta_generic_to_shared(ssrc)), \"r\"(x), \"r\"(y) : \"memory\");\n}\n";
+  // ---- LSU variant ----
+  os << "#define BRBD_OUT0(row, val) cb[(row)] = (val)\n#define BRBD_COLBEGIN(col)\n#define BRBD_CLEAR(row) cb[(row)] = BRBD_C(0.0)\n";
+  os << "#define BRBD_FLUSH(col) do { flush_col(colbuf + buf * " << 32 * pitch << ", gM + (col) * " << nv << ", ldM, nvalid, lane); buf = buf + 1 == " << nbuf
+     << " ? 0 : buf + 1; cb = colbuf + buf * " << 32 * pitch << " + lane * " << pitch << "; } while (0)\n";
+  os << "extern \"C\" __global__ void __launch_bounds__(" << nt << ", 1)\nbrbd_gen_crba_0"
+     << "(const real * __restrict__ q, long long ldq, const real * __restrict__ v, long long ldv, const real * __restrict__ x, long long ldx,\n"
+        "     real * __restrict__ out, long long ldM, real * __restrict__ recbase, long long B)\n{\n";
+  os << "  extern __shared__ __align__(128) unsigned char smem_raw[];\n  real * smem = reinterpret_cast<real *>(smem_raw);\n";
+  os << "  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;\n";
+  os << "  real * colbuf = smem + warp * " << nbuf * 32 * pitch << ";\n  real * cb = colbuf + lane * " << pitch << ";\n  int buf = 0;\n";
+  os << "  for (int k = lane; k < " << nbuf * 32 * pitch << "; k += 32) colbuf[k] = BRBD_C(0.0);\n  __syncwarp();\n";
+  os << "  const long long nthreads = (long long)gridDim.x * " << nt << ";\n";
+  os << "  const long long rounds = (B + nthreads - 1) / nthreads;\n";
+  os << "  for (long long rd = 0; rd < rounds; ++rd)\n  {\n";
+  os << "    const long long cfg0 = rd * nthreads + (long long)blockIdx.x * " << nt << " + warp * 32;\n";
+  os << "    if (cfg0 >= B) continue; // warp-uniform\n";
+  os << "    const int nvalid = (int)(B - cfg0 < 32 ? B - cfg0 : 32);\n";
+  os << "    const long long cfg = cfg0 + (lane < nvalid ? lane : nvalid - 1);\n";
+  os << "    const real * __restrict__ tq = q + cfg * ldq;\n    real * __restrict__ gM = out + cfg0 * ldM;\n";
+  os << "    {\n" << body << "    }\n  }\n}\n";
+  // ---- TMA variant ----
+  os << "#undef BRBD_OUT0\n#undef BRBD_COLBEGIN\n#undef BRBD_CLEAR\n#undef BRBD_FLUSH\n";
+  os << "#define BRBD_OUT0(row, val) myrow[cs + (row)] = (val)\n#define BRBD_CLEAR(row) myrow[ps[buf] + (row)] = BRBD_C(0.0)\n";
+  // the tile is free again once the engine has read the previous column block out of it; then this column's shift: one
+  // element early where the segment starts at an odd element, two where it starts at an even one, none for the plain columns
+  os << "#define BRBD_COLBEGIN(col) do { if (lane == 0) asm volatile(\"cp.async.bulk.wait_group.read " << nbuf - 1 << ";\" ::: \"memory\"); __syncwarp(); \\\n"
+        "    if (odd) { const int a_ = (half + (col)) & 1; plain = (col) == 0 || ((col) == " << nv - 1 << " && a_ == 0); cs = plain ? 0 : (a_ ? 1 : 2); } } while (0)\n";
+  os << "#define BRBD_FLUSH(col) do { asm volatile(\"fence.proxy.async.shared::cta;\" ::: \"memory\"); __syncwarp(); \\\n"
+        "    if (odd) { \\\n"
+        "      const int a0_ = (col) & 1, a1_ = ((col) + 1) & 1; \\\n"
+        "      const bool plain0_ = (col) == 0 || ((col) == " << nv - 1 << " && a0_ == 0), plain1_ = (col) == 0 || ((col) == " << nv - 1 << " && a1_ == 0); \\\n"
+        "      if (lane == 0) { \\\n"
+        "        if (pairs) { const int y_ = (int)(cfg0 >> 1); \\\n"
+        "          if (!plain0_) tma_store_2d(&map0, emb, (col) * " << nv << " - (a0_ ? 1 : 2), y_); \\\n"
+        "          if (!plain1_ && cfg0 + 1 < B) tma_store_2d(&map1, emb + " << 16 * epad << ", (col) * " << nv << " - (a1_ ? 1 : 2) + 1, y_); } \\\n"
+        "        else if (!plain0_) tma_store_2d(&map0, emb, (col) * " << nv << " - (a0_ ? 1 : 2), (int)cfg0); \\\n"
+        "        asm volatile(\"cp.async.bulk.commit_group;\" ::: \"memory\"); } \\\n"
+        "      if (plain && live) { real * __restrict__ g_ = out + cfg * ldM + (long long)(col) * " << nv << "; for (int e_ = 0; e_ < " << nv << "; ++e_) g_[e_] = myrow[e_]; } \\\n"
+        "    } else { \\\n"
+        "      if (lane == 0) { tma_store_2d(&map0, emb, (col) * " << nv << ", (int)cfg0); asm volatile(\"cp.async.bulk.commit_group;\" ::: \"memory\"); } } \\\n"
+        "    ps[buf] = cs; buf = buf + 1 == " << nbuf << " ? 0 : buf + 1; emb = em + buf * " << 32 * epad << "; myrow = emb + rowoff; } while (0)\n";
+  os << "extern \"C\" __global__ void __launch_bounds__(" << nt << ", 1)\nbrbd_gen_crba_tma"
+     << "(const real * __restrict__ q, long long ldq, real * __restrict__ out, long long ldM, long long B, int odd, int pairs,\n"
+        "     const __grid_constant__ TensorMap map0, const __grid_constant__ TensorMap map1)\n{\n";
+  os << "  extern __shared__ __align__(128) unsigned char smem_raw[];\n  real * smem = reinterpret_cast<real *>(smem_raw);\n";
+  os << "  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;\n";
+  os << "  real * em = smem + warp * " << nbuf * 32 * epad << ";\n  real * emb = em;\n";
+  os << "  const int half = (odd && pairs) ? (lane & 1) : 0;\n";
+  os << "  const int rowoff = ((odd && pairs) ? (lane >> 1) + 16 * half : lane) * " << epad << ";\n  real * myrow = em + rowoff;\n";
+  os << "  for (int b = 0; b < " << nbuf << "; ++b) for (int k = 0; k < " << epad << "; ++k) em[b * " << 32 * epad << " + rowoff + k] = BRBD_C(0.0);\n  __syncwarp();\n";
+  os << "  int ps[" << nbuf << "] = {0}, cs = 0, buf = 0;\n  bool plain = false;\n";
+  os << "  const long long nthreads = (long long)gridDim.x * " << nt << ";\n";
+  os << "  const long long rounds = (B + nthreads - 1) / nthreads;\n";
+  os << "  for (long long rd = 0; rd < rounds; ++rd)\n  {\n";
+  os << "    const long long cfg0 = rd * nthreads + (long long)blockIdx.x * " << nt << " + warp * 32;\n";
+  os << "    if (cfg0 >= B) continue; // warp-uniform\n";
+  os << "    const bool live = cfg0 + lane < B;\n    const long long cfg = live ? cfg0 + lane : B - 1;\n";
+  os << "    const real * __restrict__ tq = q + cfg * ldq;\n";
+  os << "    {\n" << body << "    }\n  }\n";
+  os << "  if (lane == 0) asm volatile(\"cp.async.bulk.wait_group 0;\" ::: \"memory\");\n  __syncwarp();\n}\n";
+  (void)st; (void)nq;
+  return os.str();
+}
+
+std::string wrap_host(const std::string & body, const char * name, bool fp32, const cg::EmitStats & st, const std::string & ktable, int nv)
+{
+  std::ostringstream os;
+  os << "#define BRBD_NV " << nv << "\n";
   os << "// generated by pinocchio_b200 codegen (host variant, C++, tests only): " << name << "\n#include <math.h>\n";
   os << math_macros(fp32) << ktable;
   os << "#define BRBD_IN0(k) qc[(k)]\n#define BRBD_IN1(k) vc[(k)]\n#define BRBD_IN2(k) xc[(k)]\n";
@@ -237,6 +330,15 @@ std::string wrap_host(const std::string & body, const char * name, bool fp32, co
     os << "#define BRBD_PARK_ST" << sp << sh.first << "(s, ...) park_st" << sp << sh.first << "(park + " << off << " + (s), __VA_ARGS__)\n";
     os << "#define BRBD_PARK_LD" << sp << sh.first << "(s, ...) park_ld" << sp << sh.first << "(park + " << off << " + (s), __VA_ARGS__)\n";
   }
+  if (std::string(name) == "crba")
+  { // matrix output: BRBD_OUT0 fills the staging row of the current column, BRBD_FLUSH copies it into column `col` of oc
+    os << "#undef BRBD_OUT0\n#define BRBD_OUT0(row, val) colbuf[(row)] = (val)\n#define BRBD_COLBEGIN(col)\n#define BRBD_CLEAR(row) colbuf[(row)] = BRBD_C(0.0)\n"
+          "#define BRBD_FLUSH(col) for (int r_ = 0; r_ < BRBD_NV; ++r_) oc[(col) * BRBD_NV + r_] = colbuf[r_]\n";
+    os << "extern \"C\" void brbd_gen_crba_host(const real * qc, const real * vc, const real * xc, real * oc, real * rec, real * park)\n{\n"
+          "  real colbuf[BRBD_NV];\n  for (int r_ = 0; r_ < BRBD_NV; ++r_) colbuf[r_] = BRBD_C(0.0);\n";
+    os << body << "}\n";
+    return os.str();
+  }
   os << "extern \"C\" void brbd_gen_" << name << "_host(const real * qc, const real * vc, const real * xc, real * oc, real * rec, real * park)\n{\n";
   os << body << "}\n";
   return os.str();
@@ -249,9 +351,16 @@ brbd_status brbd_codegen_source(const brbd_model * m, int algo, int flags, char 
 {
   if (!m || !source) return fail(BRBD_EINVAL, "null argument");
   *source = nullptr;
-  if (algo != BRBD_GEN_RNEA && algo != BRBD_GEN_ABA) return fail(BRBD_EINVAL, "code generation: unknown algorithm");
+  if (algo != BRBD_GEN_RNEA && algo != BRBD_GEN_ABA && algo != BRBD_GEN_CRBA) return fail(BRBD_EINVAL, "code generation: unknown algorithm");
+  // CRBA: staging tiles per warp.  Rotating over 2 or 3 (so that a tensor store drains while the next column is assembled)
+  // was measured and does not pay — 65 536 x simple_humanoid: 0.233 ms with one tile and 16 warps, 0.287 with two and 12
+  // (profiles/r2_gen_crba_experiments.txt): the store path, not the wait for the tile, bounds the kernel
+  int crba_nbuf = 1;
+  if (const char * e = std::getenv("BRBD_GEN_CRBA_NBUF")) crba_nbuf = std::max(1, std::min(4, std::atoi(e)));
+  if (flags & BRBD_GEN_HOST) crba_nbuf = 1;
   cg::Tracer T(m->pd, (flags & BRBD_GEN_EXPLICIT_SLOTS) != 0);
   if (algo == BRBD_GEN_ABA) cg::trace_aba(T);
+  else if (algo == BRBD_GEN_CRBA) cg::trace_crba(T, crba_nbuf);
   else cg::trace_rnea(T);
   cg::EmitStats st;
   const int nt = (flags >> 8) & 0xfff ? (flags >> 8) & 0xfff : 128;
@@ -279,7 +388,9 @@ brbd_status brbd_codegen_source(const brbd_model * m, int algo, int flags, char 
     while (need < st.tmem_slots * wpv * ranges) need *= 2;
     tmem_cols = need;
   }
-  const std::string src = (flags & BRBD_GEN_HOST) ? wrap_host(body, algo_name(algo), fp32, st, K.definition("static const"))
+  const std::string src = (algo == BRBD_GEN_CRBA && !(flags & BRBD_GEN_HOST))
+                            ? wrap_device_crba(body, fp32, st, nt, m->pd.nq, m->pd.nv, K.definition("__constant__"), crba_nbuf)
+                            : (flags & BRBD_GEN_HOST) ? wrap_host(body, algo_name(algo), fp32, st, K.definition("static const"), m->pd.nv)
                                                   : wrap_device(body, algo_name(algo), fp32, T.nrec, st, nt, minb, tmem_cols, m->pd.nq, m->pd.nv, copies,
                                                                 direct_io, K.definition("__constant__"));
   char * buf = (char *)std::malloc(src.size() + 1);
@@ -293,7 +404,8 @@ brbd_status brbd_codegen_source(const brbd_model * m, int algo, int flags, char 
     info->loads = st.inputs + st.rec_ld + st.park_ld; info->stores = st.rec_st + st.park_st + st.outputs;
     info->threads_per_block = nt;
     info->copies = copies;
-    info->dynamic_smem_bytes = (int32_t)(((direct_io ? 0 : (size_t)(nt / 32) * 32 * ((m->pd.nq | 1) + 2 * (m->pd.nv | 1))) + (size_t)st.smem_slots * nt) * (fp32 ? 4 : 8));
+    if (algo == BRBD_GEN_CRBA) info->dynamic_smem_bytes = (int32_t)((size_t)crba_nbuf * (nt / 32) * 32 * (m->pd.nv + 2) * (fp32 ? 4 : 8));
+    else info->dynamic_smem_bytes = (int32_t)(((direct_io ? 0 : (size_t)(nt / 32) * 32 * ((m->pd.nq | 1) + 2 * (m->pd.nv | 1))) + (size_t)st.smem_slots * nt) * (fp32 ? 4 : 8));
   }
   return BRBD_OK;
 }

@@ -272,6 +272,9 @@ inline std::string emit_body(const Graph & g, EmitStats & st, ConstTable & K, in
         break;
       }
       case Effect::RELEASE: break;
+      case Effect::FLUSH:
+        os << (e.handle == 0 ? "  BRBD_COLBEGIN(" : (e.handle == 1 ? "  BRBD_FLUSH(" : "  BRBD_CLEAR(")) << e.index << ");\n";
+        break;
       case Effect::COMMENT: os << "  // " << e.text << "\n"; break;
       }
     }

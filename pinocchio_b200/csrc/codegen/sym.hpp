@@ -49,7 +49,7 @@ struct Node
 // side effects, in program order, interleaved with the pure nodes by `at` (= number of nodes when issued)
 struct Effect
 {
-  enum Kind : uint8_t { OUTPUT, PARK, RELEASE, RECORD_ST, COMMENT } kind;
+  enum Kind : uint8_t { OUTPUT, PARK, RELEASE, RECORD_ST, COMMENT, FLUSH } kind;
   int at;                 // issued after node id at-1 was created
   int handle;             // PARK / RELEASE / RECORD_ST: slot-group handle; OUTPUT: output array
   int index;              // OUTPUT: row; RECORD_ST: first record slot

@@ -103,6 +103,17 @@ struct Tracer
     e.kind = Effect::OUTPUT; e.at = (int)g.nodes.size(); e.handle = array; e.index = row; e.vals.push_back(v.id);
     g.effects.push_back(e);
   }
+  // matrix output through the wrapper's staging row (CRBA): colbegin(col), clear(row) for what the previous column left,
+  // output(row, value) for this column's entries, flush(col)
+  void col_effect(int what, int index)
+  {
+    Effect e;
+    e.kind = Effect::FLUSH; e.at = (int)g.nodes.size(); e.handle = what; e.index = index;
+    g.effects.push_back(e);
+  }
+  void colbegin(int col) { col_effect(0, col); }
+  void clear(int row) { col_effect(2, row); }
+  void flush(int col) { col_effect(1, col); }
   void comment(const std::string & s)
   {
     Effect e;
@@ -621,6 +632,88 @@ inline void trace_rnea(Tracer & T)
         }
         else
           fc = fp;
+      }
+    }
+  }
+}
+
+// ======================================================================================================================
+// CRBA — column by column in joint-local frames.
+// The reference's default convention is LOCAL (crba.hpp:51; crbaLocalConvention, crba.hxx:454-491 with the steps :234-309):
+// Ycrb[parent] += liMi.act(Ycrb[i]), F[:, i] = Ycrb[i] S_i, M[i, subtree(i)] = S_i^T F[:, subtree(i)] after carrying the
+// subtree's force columns into frame i.  Carrying ALL subtree columns up level by level needs 6 nvSubtree live values; here
+// each column is finished at once instead: when joint j's composite inertia is complete, F = Ycrb_j S_j is walked up the root
+// path (f <- liMi.act(f) per level) and leaves one entry per ancestor dof — the same products in another order, and the only
+// long-lived state is (sin q, cos q) per tree depth plus one composite inertia per open branching joint.
+// Output: row r of the current column through Tracer::output (the wrapper's staging row of this configuration), then
+// Tracer::flush(column); rows outside the tree sparsity are zeros (a fresh Data, data.hxx:43).
+// ======================================================================================================================
+inline void trace_crba(Tracer & T, int nbuf = 1)
+{
+  const ModelPOD<double> & M = T.M;
+  const int nj = M.njoints;
+  const JointTopo topo(M);
+  struct SC { Sym s, c; std::vector<Sym> q; };
+  std::vector<SC> sc(nj);
+  std::vector<Inertia<Sym>> Yacc(nj);
+  std::vector<char> has_acc(nj, 0);
+  // the wrapper may rotate over `nbuf` staging rows: the one a column is assembled in still holds the column of nbuf flushes ago
+  std::vector<std::vector<char>> prev_rows(nbuf, std::vector<char>(M.nv, 0));
+  int ncol = 0;
+  auto liMi_of = [&](int a) { return sym_liMi(M, a, sc[a].s, sc[a].c, sc[a].q); };
+  auto S_col = [&](int type, int k) { return joint_S_col<Sym>(type, k); };
+  for (int i = 1; i < nj; ++i)
+  {
+    T.comment("joint " + std::to_string(i));
+    {
+      const int type = M.type[i];
+      const int nqj = (i + 1 < nj ? M.idx_q[i + 1] : M.nq) - M.idx_q[i];
+      sc[i].q.clear();
+      for (int k = 0; k < nqj; ++k) sc[i].q.push_back(T.in(IN_Q, M.idx_q[i] + k));
+      sc[i].s = Sym(0.0); sc[i].c = Sym(0.0);
+      if (type <= J_RZ) sincos_t(sc[i].q[0], &sc[i].s, &sc[i].c);
+      else if (type <= J_PZ) sc[i].s = sc[i].q[0];
+    }
+    const int stop = topo.stop[i];
+    for (int j = i; j != stop; j = M.parent[j])
+    {
+      const int tj = M.type[j], pj = M.parent[j], nvj = M.nvj[j], iv = M.idx_v[j];
+      Inertia<Sym> Y = sym_inertia(M, j);
+      if (has_acc[j]) Y += Yacc[j];
+      for (int k = 0; k < nvj; ++k)
+      {
+        const int col = iv + k;
+        std::vector<char> rows(M.nv, 0);
+        T.colbegin(col);
+        for (int r = 0; r < M.nv; ++r)
+          if (prev_rows[ncol % nbuf][r]) T.clear(r);
+        Force<Sym> f = Y * S_col(tj, k);
+        for (int kk = 0; kk < nvj; ++kk)
+        { // the joint's own diagonal block (full, as M.block(idx_v, idx_v, nv, nvSubtree) = S^T F writes it)
+          Sym val = dot6(S_col(tj, kk), f);
+          if (kk == k) val += Sym(M.armature[col]);
+          T.output(OUT_MAIN, iv + kk, val);
+          rows[iv + kk] = 1;
+        }
+        for (int a = j; M.parent[a] > 0; a = M.parent[a])
+        {
+          const int pa = M.parent[a];
+          f = liMi_of(a).act(f); // into the parent's frame
+          for (int kk = 0; kk < M.nvj[pa]; ++kk)
+          {
+            T.output(OUT_MAIN, M.idx_v[pa] + kk, dot6(S_col(M.type[pa], kk), f));
+            rows[M.idx_v[pa] + kk] = 1;
+          }
+        }
+        T.flush(col);
+        prev_rows[ncol % nbuf] = rows;
+        ++ncol;
+      }
+      if (pj > 0)
+      {
+        const Inertia<Sym> Yp = act(liMi_of(j), Y);
+        if (has_acc[pj]) Yacc[pj] += Yp;
+        else { Yacc[pj] = Yp; has_acc[pj] = 1; }
       }
     }
   }

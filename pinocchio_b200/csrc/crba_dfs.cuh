@@ -327,12 +327,7 @@ crba_tmem_kernel(const __grid_constant__ TreePOD<T> m, const CrbaTmemLayout L, c
 // The emitter tile is rewritten only after cp.async.bulk.wait_group.read, lazily — just before the next column is
 // assembled — so the wait hides behind the forward step / the Y J product in between.
 // ------------------------------------------------------------------------------------------------------
-struct CrbaTmaGeom
-{
-  int bx;    // box inner extent = emitter row length (elements): nv, or nv + 1 for odd nv
-  int odd;   // odd nv (FP64): shifted boxes, see above
-  int pairs; // odd nv and odd ldM: even / odd configurations over two maps
-};
+// struct CrbaTmaGeom {bx, odd, pairs}: tree.cuh (shared with the generated CRBA kernel, codegen.cu)
 BRBD_DI void tma_store_2d(const void * tmap, const void * ssrc, int x, int y)
 {
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(tmap),

@@ -85,6 +85,7 @@ struct GenKernel
 {
   void * lib = nullptr;    // cudaLibrary_t
   void * kernel = nullptr; // cudaKernel_t
+  void * kernel_tma = nullptr; // CRBA: the variant whose column blocks leave through TMA tensor stores
   int nt = 0, nrec = 0;
   size_t smem_bytes = 0;
 };
@@ -291,6 +292,54 @@ inline int64_t coop_max_batch(bool aba, int nv)
   if (nv <= 8) return 4096; // 4 configurations per warp
   return aba ? 2048 : 4096;
 }
+
+// ---- TMA tensor maps over the caller's (nv*nv x B, leading dimension ldM) matrix block: see crba_tma_kernel ----------
+typedef CUresult (*brbd_encode_tiled_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                         const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                         CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+inline brbd_encode_tiled_fn encode_tiled_fn()
+{
+  static brbd_encode_tiled_fn fn = [] {
+    void * p = nullptr;
+    cudaDriverEntryPointQueryResult qr;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qr) != cudaSuccess || qr != cudaDriverEntryPointSuccess)
+      p = nullptr;
+    return (brbd_encode_tiled_fn)p;
+  }();
+  return fn;
+}
+template<class T>
+bool crba_tma_setup(T * Mout, int64_t ldM, int64_t B, int nv, CrbaTmaGeom & G, CUtensorMap & map0, CUtensorMap & map1)
+{
+  const brbd_encode_tiled_fn enc = encode_tiled_fn();
+  constexpr int E = (int)sizeof(T), K = 16 / E;
+  if (!enc || (reinterpret_cast<uintptr_t>(Mout) & 15) || nv > 255 || ldM < (int64_t)nv * nv) return false;
+  const bool even = (nv % K) == 0 && (ldM % K) == 0;
+  const bool odd = E == 8 && (nv & 1) && nv >= 3;
+  if (!even && !odd) return false;
+  G.odd = even ? 0 : 1;
+  G.pairs = (!even && (ldM & 1)) ? 1 : 0;
+  G.bx = even ? nv : nv + 1;
+  const CUtensorMapDataType dt = E == 8 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+  const cuuint32_t es[2] = {1, 1};
+  auto make = [&](CUtensorMap & mp, T * base, cuuint64_t inner, cuuint64_t outer, cuuint64_t stride_elems, cuuint32_t rows) {
+    const cuuint64_t gd[2] = {inner, outer > 0 ? outer : 1};
+    const cuuint64_t gs[1] = {stride_elems * (cuuint64_t)E};
+    const cuuint32_t bd[2] = {(cuuint32_t)G.bx, rows};
+    return enc(&mp, dt, 2, (void *)base, gd, gs, bd, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+               CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+  };
+  if (!G.pairs)
+  {
+    if (!make(map0, Mout, (cuuint64_t)ldM, (cuuint64_t)B, (cuuint64_t)ldM, 32)) return false;
+    map1 = map0;
+    return true;
+  }
+  if (!make(map0, Mout, (cuuint64_t)ldM, (cuuint64_t)((B + 1) / 2), (cuuint64_t)(2 * ldM), 16)) return false;
+  if (B < 2) { map1 = map0; return true; } // the kernel issues no odd-half store for a single configuration
+  return make(map1, Mout + (ldM - 1), (cuuint64_t)(ldM + 1), (cuuint64_t)(B / 2), (cuuint64_t)(2 * ldM), 16);
+}
+
 
 // ---- one launch function per algorithm, each instantiated for double and float in its own translation unit ----------
 template<class T>

@@ -4,53 +4,6 @@
 
 namespace brbd
 {
-// ---- TMA tensor maps over the caller's (nv*nv x B, leading dimension ldM) matrix block: see crba_tma_kernel ----------
-typedef CUresult (*brbd_encode_tiled_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
-                                         const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                         CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-static brbd_encode_tiled_fn encode_tiled_fn()
-{
-  static brbd_encode_tiled_fn fn = [] {
-    void * p = nullptr;
-    cudaDriverEntryPointQueryResult qr;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qr) != cudaSuccess || qr != cudaDriverEntryPointSuccess)
-      p = nullptr;
-    return (brbd_encode_tiled_fn)p;
-  }();
-  return fn;
-}
-template<class T>
-bool crba_tma_setup(T * Mout, int64_t ldM, int64_t B, int nv, CrbaTmaGeom & G, CUtensorMap & map0, CUtensorMap & map1)
-{
-  const brbd_encode_tiled_fn enc = encode_tiled_fn();
-  constexpr int E = (int)sizeof(T), K = 16 / E;
-  if (!enc || (reinterpret_cast<uintptr_t>(Mout) & 15) || nv > 255 || ldM < (int64_t)nv * nv) return false;
-  const bool even = (nv % K) == 0 && (ldM % K) == 0;
-  const bool odd = E == 8 && (nv & 1) && nv >= 3;
-  if (!even && !odd) return false;
-  G.odd = even ? 0 : 1;
-  G.pairs = (!even && (ldM & 1)) ? 1 : 0;
-  G.bx = even ? nv : nv + 1;
-  const CUtensorMapDataType dt = E == 8 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
-  const cuuint32_t es[2] = {1, 1};
-  auto make = [&](CUtensorMap & mp, T * base, cuuint64_t inner, cuuint64_t outer, cuuint64_t stride_elems, cuuint32_t rows) {
-    const cuuint64_t gd[2] = {inner, outer > 0 ? outer : 1};
-    const cuuint64_t gs[1] = {stride_elems * (cuuint64_t)E};
-    const cuuint32_t bd[2] = {(cuuint32_t)G.bx, rows};
-    return enc(&mp, dt, 2, (void *)base, gd, gs, bd, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
-               CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
-  };
-  if (!G.pairs)
-  {
-    if (!make(map0, Mout, (cuuint64_t)ldM, (cuuint64_t)B, (cuuint64_t)ldM, 32)) return false;
-    map1 = map0;
-    return true;
-  }
-  if (!make(map0, Mout, (cuuint64_t)ldM, (cuuint64_t)((B + 1) / 2), (cuuint64_t)(2 * ldM), 16)) return false;
-  if (B < 2) { map1 = map0; return true; } // the kernel issues no odd-half store for a single configuration
-  return make(map1, Mout + (ldM - 1), (cuuint64_t)(ldM + 1), (cuuint64_t)(B / 2), (cuuint64_t)(2 * ldM), 16);
-}
-
 template<class T>
 brbd_status launch_crba(brbd_pool * p, DeviceCtx & d, const T * q, int64_t ldq, T * Mout, int64_t ldM, int64_t B)
 {
@@ -59,6 +12,10 @@ brbd_status launch_crba(brbd_pool * p, DeviceCtx & d, const T * q, int64_t ldq, 
   brbd_status st = BRBD_OK;
   const char * ver = std::getenv("BRBD_CRBA_V"); // "tmem" (LSU emitter), "dfs" (crba_dfs_kernel), "v1" (crba_kernel)
   if (ver && std::strcmp(ver, "v1") == 0) return launch_crba_v1<T>(p, d, q, ldq, Mout, ldM, B);
+  // the generated CRBA wins where the arithmetic matters (6-dof manipulator: 0.034 -> 0.016 ms at 65 536 configurations);
+  // from ~25 dofs on the column stores bound both kernels alike and the hand-written one is kept (BRBD_CRBA_V=gen forces it)
+  if ((!ver && use_generated<T>(p, BRBD_GEN_CRBA, B) && t.nv <= 24) || (ver && std::strncmp(ver, "gen", 3) == 0 && p->gen[BRBD_GEN_CRBA][sizeof(T) == 4 ? 1 : 0].nvar > 0))
+    return launch_generated<T>(p, d, BRBD_GEN_CRBA, q, ldq, (const T *)nullptr, 0, (const T *)nullptr, 0, Mout, ldM, B);
   // preferred: oYcrb / oMi stacks in tensor memory (<= 8 warps per CTA, one CTA per SM)
   if (!(ver && std::strcmp(ver, "dfs") == 0))
   {

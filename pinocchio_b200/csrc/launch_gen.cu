@@ -114,9 +114,15 @@ brbd_status build_variant(brbd_pool * p, int algo, bool fp32, int nt, bool direc
     return fail(BRBD_ECUDA, std::string("cudaLibraryGetKernel: ") + cudaGetErrorString(e));
   }
   k.smem_bytes = (size_t)info.dynamic_smem_bytes;
+  cudaKernel_t kern_tma = nullptr;
+  if (algo == BRBD_GEN_CRBA && cudaLibraryGetKernel(&kern_tma, lib, "brbd_gen_crba_tma") != cudaSuccess) kern_tma = nullptr;
   if (k.smem_bytes > 48 * 1024)
     for (const DeviceCtx & d : p->devs)
+    {
       CUDA_TRY(cudaKernelSetAttributeForDevice(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k.smem_bytes, d.dev));
+      if (kern_tma) CUDA_TRY(cudaKernelSetAttributeForDevice(kern_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k.smem_bytes, d.dev));
+    }
+  k.kernel_tma = kern_tma;
   k.lib = lib; k.kernel = kern; k.nt = nt; k.nrec = info.record_slots;
   return BRBD_OK;
 }
@@ -134,6 +140,7 @@ brbd_status specialize_one(brbd_pool * p, int algo, bool fp32, int flags)
   if (const char * e = std::getenv("BRBD_GEN_SLOTS")) slots = std::atoi(e) != 0;
   if (const char * e = std::getenv("BRBD_GEN_DIRECT")) direct = std::atoi(e) != 0;
   if (const char * e = std::getenv("BRBD_GEN_NT")) nts.push_back(std::max(32, std::min(1024, std::atoi(e) / 32 * 32)));
+  else if (algo == BRBD_GEN_CRBA) nts = {512, 384, 256}; // small state (128 registers at 16 warps, no spills): one staging row per lane
   else if (direct) nts = {448, 512, 256};
   else
   {
@@ -143,6 +150,7 @@ brbd_status specialize_one(brbd_pool * p, int algo, bool fp32, int flags)
   for (int nt : nts)
   {
     if (g.nvar >= 2 && nt == 256) break; // 8 warps only when the larger variants do not fit
+    if (algo == BRBD_GEN_CRBA && g.nvar >= 1) break;
     GenKernel k;
     brbd_status st = build_variant(p, algo, fp32, nt, direct, slots, k);
     if (st != BRBD_OK) return st;
@@ -170,6 +178,20 @@ brbd_status launch_generated(brbd_pool * p, DeviceCtx & d, int algo, const T * q
   const GenKernel & k = g.var[best];
   const int64_t ctas_needed = (B + k.nt - 1) / k.nt;
   const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(ctas_needed, (int64_t)d.sm_count));
+  if (algo == BRBD_GEN_CRBA && k.kernel_tma && !forced_path("BRBD_CRBA_V", "gen-lsu"))
+  { // the caller's layout allows tensor maps: column blocks leave through TMA tensor stores (as crba_tma_kernel)
+    CrbaTmaGeom G{0, 0, 0};
+    CUtensorMap map0, map1;
+    if (crba_tma_setup<T>(out, ldo, B, p->model.pd.nv, G, map0, map1))
+    {
+      long long ldq_ = ldq, ldo_ = ldo, B_ = B;
+      int odd = G.odd, pairs = G.pairs;
+      void * args[] = {(void *)&q, &ldq_, (void *)&out, &ldo_, &B_, &odd, &pairs, &map0, &map1};
+      CUDA_TRY(cudaLaunchKernel((const void *)k.kernel_tma, dim3(grid), dim3(k.nt), args, k.smem_bytes, d.s()));
+      p->launches += 1;
+      return BRBD_OK;
+    }
+  }
   brbd_status st = ensure_work(d, std::max<size_t>(8, (size_t)k.nrec * grid * k.nt * sizeof(T)));
   if (st != BRBD_OK) return st;
   long long ldq_ = ldq, ldv_ = ldv, ldx_ = ldx, ldo_ = ldo, B_ = B;

@@ -104,6 +104,14 @@ template<class T> inline void build_tree(const ModelPOD<double> & M, TreePOD<T> 
   for (int k = 0; k < 3; ++k) P.gravity[k] = (T)M.gravity[k];
 }
 
+// geometry of the TMA tensor stores of a (nv*nv x B) matrix block, see crba_dfs.cuh (crba_tma_kernel)
+struct CrbaTmaGeom
+{
+  int bx;    // box inner extent = emitter row length (elements): nv, or nv + 1 for odd nv
+  int odd;   // odd nv (FP64): shifted boxes
+  int pairs; // odd nv and odd ldM: even / odd configurations over two maps
+};
+
 // ---- per-thread view of the slot-major shared state ------------------------------------------------
 // NT = threads per CTA is a template parameter so that slot offsets fold into the LDS/STS immediates.
 template<class T, int NT> struct Slots

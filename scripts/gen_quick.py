@@ -24,12 +24,14 @@ for name in args.models:
     for mode in ("generic", "generated"):
         pool = pb.ModelPool(model, [0])
         if mode == "generated":
-            t0 = time.time(); pool.specialize(["rnea", "aba"]); print(f"{name}: specialize {time.time()-t0:.1f}s", flush=True)
+            t0 = time.time(); pool.specialize(["rnea", "aba", "crba"]); print(f"{name}: specialize {time.time()-t0:.1f}s", flush=True)
         pool.set_stream(torch.cuda.current_stream().cuda_stream)
-        for algo, fn in (("rnea", pb.rneaInParallel), ("aba", pb.abaInParallel)):
+        crba_fn = lambda n, pl, a, b, c, out=None, async_=False: pb.crbaInParallel(n, pl, a, out, async_=async_)
+        for algo, fn in (("rnea", pb.rneaInParallel), ("aba", pb.abaInParallel), ("crba", crba_fn)):
             out = fn(1, pool, tq, tv, tx)
             torch.cuda.synchronize()
-            ref = orc.rnea(q[:, :4096], v[:, :4096], x[:, :4096]) if algo == "rnea" else orc.aba(q[:, :4096], v[:, :4096], x[:, :4096])
+            ref = (orc.rnea(q[:, :4096], v[:, :4096], x[:, :4096]) if algo == "rnea" else
+                   orc.aba(q[:, :4096], v[:, :4096], x[:, :4096]) if algo == "aba" else orc.crba(q[:, :4096], world=True))
             got = out[:4096].cpu().numpy().T
             err = np.abs(got - ref).max() / np.abs(ref).max()
             last = out[-1].cpu().numpy()

@@ -29,14 +29,15 @@ def build_host(model, algo, explicit_slots, tmp):
     return getattr(ctypes.CDLL(so), f"brbd_gen_{algo}_host"), info
 
 
-def run_host(fn, info, model, q, v, x):
+def run_host(fn, info, model, q, v, x, nout=None):
     B = q.shape[1]
-    out = np.zeros((model.nv, B), order="F")
+    nout = model.nv if nout is None else nout
+    out = np.zeros((nout, B), order="F")
     rec, park = np.full(max(1, info["record_slots"]), np.nan), np.full(max(1, info["park_slots"]), np.nan)
     P = lambda a: a.ctypes.data_as(ctypes.c_void_p)
     for i in range(B):
         qi, vi, xi = (np.ascontiguousarray(a[:, i]) for a in (q, v, x))
-        oi = np.zeros(model.nv)
+        oi = np.full(nout, np.nan)
         rec[:] = np.nan  # a read of a slot nobody wrote would poison the result
         park[:] = np.nan
         fn(P(qi), P(vi), P(xi), P(oi), P(rec), P(park))
@@ -58,6 +59,13 @@ def test_generated_program_matches_the_oracle(oracle_cls, name, explicit_slots):
             assert np.abs(got - ref).max() <= 1e-11 * max(1.0, np.abs(ref).max()), (name, algo, np.abs(got - ref).max())
             if explicit_slots and algo == "aba" and model.njoints > 3:
                 assert info["park_slots"] > 0
+        if not explicit_slots:
+            fn, info = build_host(model, "crba", False, tmp)
+            got = run_host(fn, info, model, q, v, x, nout=model.nv * model.nv)
+            ref = orc.crba(q, world=True)
+            assert np.isfinite(got).all(), (name, "crba")  # every entry written, zeros outside the tree sparsity
+            assert np.abs(got - ref).max() <= 1e-12 * max(1.0, np.abs(ref).max()), (name, "crba")
+            assert not got[ref == 0].any() or np.abs(got[ref == 0]).max() < 1e-13
 
 
 def test_constant_folding_shrinks_the_program(oracle_cls):

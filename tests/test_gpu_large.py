@@ -329,15 +329,16 @@ SPEC_MODELS = ["manipulator", "humanoid", "humanoid_random", "simple_humanoid_ff
 
 
 @pytest.mark.parametrize("name", SPEC_MODELS)
-def test_specialized_kernels(ctx, name):
+def test_specialized_kernels(ctx, name, monkeypatch):
     """pool.specialize(): kernels generated for the model (codegen: the tree unrolled, constants folded), compiled with NVRTC.
     Same parity bar as the generic kernels, every column compared, ragged batch over several rounds of the grid; the generic
     path must still be what small batches take."""
     import pinocchio_b200 as pb
     model, _, orc = ctx(name)
     pool = pb.ModelPool(model, [0])
-    pool.specialize(["rnea", "aba"], min_batch=1)
-    assert set(pool.specialized()) == {"rnea", "aba"}
+    pool.specialize(["rnea", "aba", "crba"], min_batch=1)
+    assert set(pool.specialized()) == {"rnea", "aba", "crba"}
+    monkeypatch.setenv("BRBD_CRBA_V", "gen")  # the launch keeps the hand-written CRBA above 24 dofs: force the generated one
     for B in (1, 257, 148 * 256 + 4321):
         q, v, a = random_inputs(model, B, 77)
         tq, tv, ta = to_dev(q, v, a)
@@ -348,6 +349,18 @@ def test_specialized_kernels(ctx, name):
         ref = orc.aba(q, v, a)
         assert_close(ddq, ref, rtol=1e-10, atol=1e-12 + 1e-10 * np.abs(ref).max(axis=0, keepdims=True), what=f"aba[generated] {name} B={B}")
         assert pool.launch_count() == n0 + 2
+        if B <= 257 or model.nv <= 40:
+            import torch
+            nn = model.nv * model.nv
+            big = torch.full((B + 1, nn + 3), -7.0, dtype=torch.float64, device="cuda")  # padded leading dimension + canary
+            pb.crbaInParallel(1, pool, tq, big[:B, :nn])
+            torch.cuda.synchronize()
+            got = big.cpu().numpy()
+            refM = orc.crba(q, world=True)
+            assert_close(got[:B, :nn].T, refM, rtol=1e-10, atol=1e-12 + 1e-12 * np.abs(refM).max(axis=0, keepdims=True),
+                         what=f"crba[generated] {name} B={B}")
+            assert not got[:B, :nn].T[~structural_mask(model)].any(), "entries outside the tree sparsity must be exact zeros"
+            assert (got[:B, nn:] == -7.0).all() and (got[B] == -7.0).all(), "wrote outside the caller's block"
     # host pointers, nle / gravity / Euler step ride on the same kernels
     q, v, a = random_inputs(model, 300, 78)
     assert_close(pb.nonLinearEffectsInParallel(1, pool, q, v), orc.nle(q, v), atol=1e-12 * max(1.0, np.abs(orc.nle(q, v)).max()),
