@@ -48,6 +48,10 @@ typedef enum brbd_joint_type {
   BRBD_JOINT_PLANAR = 8,                                     /* joint-planar.hpp     (nq 4, nv 3) */
   BRBD_JOINT_REVOLUTE_UNALIGNED = 9,                         /* joint-revolute-unaligned.hpp: axis in brbd_flat_model::axis */
   BRBD_JOINT_PRISMATIC_UNALIGNED = 10,                       /* joint-prismatic-unaligned.hpp */
+  /* joint-revolute-unbounded.hpp:121-235 (URDF "continuous" joints, parsers/urdf/model.hxx:269-273): revolute joints whose
+     configuration is (cos q, sin q) — nq 2, nv 1 */
+  BRBD_JOINT_RUBX = 11, BRBD_JOINT_RUBY = 12, BRBD_JOINT_RUBZ = 13,
+  BRBD_JOINT_REVOLUTE_UNBOUNDED_UNALIGNED = 14,              /* joint-revolute-unbounded-unaligned.hpp: axis in brbd_flat_model::axis */
   BRBD_JOINT_UNIVERSE = -1                                   /* slot 0 only */
 } brbd_joint_type;
 

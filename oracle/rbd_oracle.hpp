@@ -483,9 +483,19 @@ template<class S> inline Force<S> mul6(const Mat6<S> & A, const Motion<S> & v)
 // ---------------------------------------------------------------------------------------------
 // Model (constants in Scalar) and Data (workspaces): multibody/model.hpp:97-205, data.hxx:30-315
 // ---------------------------------------------------------------------------------------------
-inline bool joint_unaligned(int t) { return t == BRBD_JOINT_REVOLUTE_UNALIGNED || t == BRBD_JOINT_PRISMATIC_UNALIGNED; }
-inline int joint_nq(int t) { return (t <= BRBD_JOINT_PZ || joint_unaligned(t)) ? 1 : (t == BRBD_JOINT_FREEFLYER ? 7 : 4); }
-inline int joint_nv(int t) { return (t <= BRBD_JOINT_PZ || joint_unaligned(t)) ? 1 : (t == BRBD_JOINT_FREEFLYER ? 6 : 3); }
+// unbounded revolute joints (URDF "continuous"): joint-revolute-unbounded.hpp:121-235, joint-revolute-unbounded-unaligned.hpp:133-260;
+// configuration (cos q, sin q), nq = 2, nv = 1
+inline bool joint_unbounded(int t) { return t >= BRBD_JOINT_RUBX && t <= BRBD_JOINT_REVOLUTE_UNBOUNDED_UNALIGNED; }
+inline bool joint_unaligned(int t)
+{
+  return t == BRBD_JOINT_REVOLUTE_UNALIGNED || t == BRBD_JOINT_PRISMATIC_UNALIGNED || t == BRBD_JOINT_REVOLUTE_UNBOUNDED_UNALIGNED;
+}
+inline int joint_nq(int t)
+{
+  if (joint_unbounded(t)) return 2;
+  return (t <= BRBD_JOINT_PZ || joint_unaligned(t)) ? 1 : (t == BRBD_JOINT_FREEFLYER ? 7 : 4);
+}
+inline int joint_nv(int t) { return (t <= BRBD_JOINT_PZ || joint_unaligned(t) || joint_unbounded(t)) ? 1 : (t == BRBD_JOINT_FREEFLYER ? 6 : 3); }
 
 template<class S> struct Model
 {
@@ -624,15 +634,18 @@ inline void jointCalc(const Model<S> & model, int i, const S * q, const S * vq, 
   jd.v = Motion<S>();
   const S * qj = q + model.idx_q[i];
   const S * vj = vq ? vq + model.idx_v[i] : nullptr;
-  if (t <= BRBD_JOINT_RZ)
+  if (t <= BRBD_JOINT_RZ || (t >= BRBD_JOINT_RUBX && t <= BRBD_JOINT_RUBZ))
   {
     // data.M.setValues(sa, ca); jointPlacements[i] * jdata.M() converts the TransformRevolute to a
     // plain SE3 (operator PlainType, joint-revolute.hpp:112-122, _setRotation 199-232) and uses the
     // generic SE3 product (se3-base.hpp:138-141, se3-tpl.hpp:314-317). The se3action shortcut at
     // joint-revolute.hpp:123-156 has no caller.
-    const int axis = t - BRBD_JOINT_RX;
+    // JointModelRevoluteUnbounded::calc (joint-revolute-unbounded.hpp:154-162): ca = q[0], sa = q[1], no sincos
+    const bool unbounded = t >= BRBD_JOINT_RUBX;
+    const int axis = unbounded ? t - BRBD_JOINT_RUBX : t - BRBD_JOINT_RX;
     S sa, ca;
-    sincos_s(qj[0], sa, ca);
+    if (unbounded) { ca = qj[0]; sa = qj[1]; }
+    else sincos_s(qj[0], sa, ca);
     jd.M = SE3<S>::Identity();
     if (axis == 0) { jd.M.R(1, 1) = ca; jd.M.R(1, 2) = -sa; jd.M.R(2, 1) = sa; jd.M.R(2, 2) = ca; }
     else if (axis == 1) { jd.M.R(0, 0) = ca; jd.M.R(0, 2) = sa; jd.M.R(2, 0) = -sa; jd.M.R(2, 2) = ca; }
@@ -649,13 +662,15 @@ inline void jointCalc(const Model<S> & model, int i, const S * q, const S * vq, 
     jd.Sm[LINEAR + axis][0] = structural_one<S>();
     if (vj) jd.v.lin[axis] = vj[0];
   }
-  else if (t == BRBD_JOINT_REVOLUTE_UNALIGNED)
+  else if (t == BRBD_JOINT_REVOLUTE_UNALIGNED || t == BRBD_JOINT_REVOLUTE_UNBOUNDED_UNALIGNED)
   {
     // JointModelRevoluteUnalignedTpl::calc, joint-revolute-unaligned.hpp:668-672: toRotationMatrix(axis, cos, sin) of
     // math/rotation.hpp:26-55 (Eigen's AngleAxis formula); S = (0, axis), v = axis qdot (:84-103)
+    // (unbounded: ca = q[0], sa = q[1], joint-revolute-unbounded-unaligned.hpp:192-200)
     const V3<S> & ax = model.axis[i];
     S sa, ca;
-    sincos_s(qj[0], sa, ca);
+    if (t == BRBD_JOINT_REVOLUTE_UNBOUNDED_UNALIGNED) { ca = qj[0]; sa = qj[1]; }
+    else sincos_s(qj[0], sa, ca);
     const V3<S> sin_axis = sa * ax, cos1_axis = (S(1) - ca) * ax;
     jd.M = SE3<S>::Identity();
     S tmp = cos1_axis[0] * ax[1];
@@ -1409,7 +1424,19 @@ template<class S> void integrate(const Model<S> & model, const S * q, const S * 
     const S * vj = v + model.idx_v[i];
     S * o = qout + model.idx_q[i];
     const int t = model.type[i];
-    if (t <= BRBD_JOINT_PZ || joint_unaligned(t))
+    if (joint_unbounded(t))
+    { // SpecialOrthogonalOperationTpl<2>::integrate_impl, liegroup/special-orthogonal.hpp:164-185
+      const S ca = qj[0], sa = qj[1];
+      S so, co;
+      sincos_s(vj[0], so, co);
+      o[0] = co * ca - so * sa;
+      o[1] = so * ca + co * sa;
+      const S norm2 = o[0] * o[0] + o[1] * o[1];
+      const S k = (S(3) - norm2) / S(2);
+      o[0] = o[0] * k;
+      o[1] = o[1] * k;
+    }
+    else if (t <= BRBD_JOINT_PZ || joint_unaligned(t))
       o[0] = qj[0] + vj[0]; // VectorSpaceOperation::integrate_impl, liegroup/vector-space.hpp:142-150
     else if (t == BRBD_JOINT_FREEFLYER)
     {

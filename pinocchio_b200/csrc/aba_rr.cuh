@@ -202,7 +202,7 @@ aba_rr_kernel(const __grid_constant__ TreePOD<T> m, const AbaRRLayout L, const T
           async_fetch(&st[L.oP + 1], vc + m.j[i + 1].idx_v);
         }
         async_fetch(&st[L.oP + 2], tc + r.idx_v); // tau of this joint, for its backward step (a leaf's follows at once)
-        tree_sc(r.type, q0, &si, &ci);
+        tree_sc_joint(m, i, r.type, qc + r.idx_q, q0, &si, &ci);
         const SE3<T> Xl = tree_liMi_sc(m, i, r.type, qc + r.idx_q, si, ci);
         if (r.parent > 0)
         {

@@ -253,7 +253,8 @@ inline void trace_aba(Tracer & T)
     // ---- pass 1, joint i: kinematics only (aba.hxx:101-131) ----
     Sym si(0.0), ci(0.0);
     std::vector<Sym> qj = qseg(i, 0), vj = vseg(i, 0);
-    if (type <= J_RZ) sincos_t(qj[0], &si, &ci);
+    if (type <= J_RZ && M.unb[i]) { ci = qj[0]; si = qj[1]; }
+    else if (type <= J_RZ) sincos_t(qj[0], &si, &ci);
     else if (type <= J_PZ) si = qj[0];
     const SE3<Sym> Xl = sym_liMi(M, i, si, ci, qj);
     if (parent > 0)
@@ -543,7 +544,8 @@ inline void trace_rnea(Tracer & T)
     for (int k = 0; k < nvj; ++k) vj.push_back(T.in(IN_V, iv + k));
     for (int k = 0; k < nvj; ++k) aj.push_back(T.in(IN_X, iv + k));
     Sym si(0.0), ci(0.0);
-    if (type <= J_RZ) sincos_t(qj[0], &si, &ci);
+    if (type <= J_RZ && M.unb[i]) { ci = qj[0]; si = qj[1]; }
+    else if (type <= J_RZ) sincos_t(qj[0], &si, &ci);
     else if (type <= J_PZ) si = qj[0];
     const SE3<Sym> Xl = sym_liMi(M, i, si, ci, qj);
     liMi[i] = Xl;
@@ -671,7 +673,8 @@ inline void trace_crba(Tracer & T, int nbuf = 1)
       sc[i].q.clear();
       for (int k = 0; k < nqj; ++k) sc[i].q.push_back(T.in(IN_Q, M.idx_q[i] + k));
       sc[i].s = Sym(0.0); sc[i].c = Sym(0.0);
-      if (type <= J_RZ) sincos_t(sc[i].q[0], &sc[i].s, &sc[i].c);
+      if (type <= J_RZ && M.unb[i]) { sc[i].c = sc[i].q[0]; sc[i].s = sc[i].q[1]; }
+      else if (type <= J_RZ) sincos_t(sc[i].q[0], &sc[i].s, &sc[i].c);
       else if (type <= J_PZ) sc[i].s = sc[i].q[0];
     }
     const int stop = topo.stop[i];

@@ -29,6 +29,7 @@ template<class T> struct ModelPOD
   int parent[MAXJ], type[MAXJ], idx_q[MAXJ], idx_v[MAXJ], nvj[MAXJ];
   int nvsub[MAXJ];       // nvSubtree (data.hxx:197-242)
   int depth[MAXJ];       // universe = 0
+  int unb[MAXJ];         // 1: revolute joint with an unbounded configuration, q = (cos, sin) (joint-revolute-unbounded.hpp:154-179)
   int dof_joint[MAXNV];  // joint owning each tangent row
   int parent_row[MAXNV]; // parents_fromRow (data.hxx:246-315)
   T placement[MAXJ][12]; // R by columns (c0, c1, c2) then p
@@ -95,7 +96,8 @@ template<class T> BRBD_DI SE3<T> joint_liMi(const ModelPOD<T> & m, int i, int ty
   {
   case J_RX: case J_RY: case J_RZ: {
     T s, c;
-    sincos_t(qj[0], &s, &c);
+    if (m.unb[i]) { c = qj[0]; s = qj[1]; } // JointModelRevoluteUnbounded::calc: data.M.setValues(sa, ca) from q = (ca, sa)
+    else sincos_t(qj[0], &s, &c);
     X.p = P.p;
     if (type == J_RX) { X.R.c0 = P.R.c0; X.R.c1 = c * P.R.c1 + s * P.R.c2; X.R.c2 = c * P.R.c2 - s * P.R.c1; }
     else if (type == J_RY) { X.R.c1 = P.R.c1; X.R.c2 = c * P.R.c2 + s * P.R.c0; X.R.c0 = c * P.R.c0 - s * P.R.c2; }

@@ -170,8 +170,19 @@ integrate_kernel(const ModelPOD<T> * __restrict__ gmod, const T * __restrict__ q
         T o[7];
         const int type = m.type[i];
         T * qj = ql + m.idx_q[i];
-        integrate_joint(type, qj, vl + m.idx_v[i], EULER ? dt : T(1), o);
-        const int nqj = type <= J_PZ ? 1 : (type == J_FF ? 7 : 4);
+        if (m.unb[i])
+        { // SpecialOrthogonalOperationTpl<2>::integrate_impl (special-orthogonal.hpp:164-185): q = (cos, sin) turned by v,
+          // then the first-order normalisation of the unit complex
+          const T om = (EULER ? dt : T(1)) * vl[m.idx_v[i]];
+          T so, co;
+          sincos_t(om, &so, &co);
+          const T c1 = co * qj[0] - so * qj[1], s1 = so * qj[0] + co * qj[1];
+          const T n = (T(3) - (c1 * c1 + s1 * s1)) / T(2);
+          o[0] = c1 * n; o[1] = s1 * n;
+        }
+        else
+          integrate_joint(type, qj, vl + m.idx_v[i], EULER ? dt : T(1), o);
+        const int nqj = m.unb[i] ? 2 : (type <= J_PZ ? 1 : (type == J_FF ? 7 : 4));
 #pragma unroll
         for (int k = 0; k < 7; ++k)
           if (k < nqj) qj[k] = o[k];

@@ -15,9 +15,17 @@
 
 namespace brbd
 {
-inline bool joint_is_unaligned(int t) { return t == BRBD_JOINT_REVOLUTE_UNALIGNED || t == BRBD_JOINT_PRISMATIC_UNALIGNED; }
-inline int joint_nq_of(int t) { return (t <= BRBD_JOINT_PZ || joint_is_unaligned(t)) ? 1 : (t == BRBD_JOINT_FREEFLYER ? 7 : 4); }
-inline int joint_nv_of(int t) { return (t <= BRBD_JOINT_PZ || joint_is_unaligned(t)) ? 1 : (t == BRBD_JOINT_FREEFLYER ? 6 : 3); }
+inline bool joint_is_unbounded(int t) { return t >= BRBD_JOINT_RUBX && t <= BRBD_JOINT_REVOLUTE_UNBOUNDED_UNALIGNED; }
+inline bool joint_is_unaligned(int t)
+{
+  return t == BRBD_JOINT_REVOLUTE_UNALIGNED || t == BRBD_JOINT_PRISMATIC_UNALIGNED || t == BRBD_JOINT_REVOLUTE_UNBOUNDED_UNALIGNED;
+}
+inline int joint_nq_of(int t)
+{
+  if (joint_is_unbounded(t)) return 2;
+  return (t <= BRBD_JOINT_PZ || joint_is_unaligned(t)) ? 1 : (t == BRBD_JOINT_FREEFLYER ? 7 : 4);
+}
+inline int joint_nv_of(int t) { return (t <= BRBD_JOINT_PZ || joint_is_unaligned(t) || joint_is_unbounded(t)) ? 1 : (t == BRBD_JOINT_FREEFLYER ? 6 : 3); }
 
 template<class T> inline void fill_pod(ModelPOD<T> & P, const ModelPOD<double> & D)
 {
@@ -26,7 +34,7 @@ template<class T> inline void fill_pod(ModelPOD<T> & P, const ModelPOD<double> &
   for (int i = 0; i < MAXJ; ++i)
   {
     P.parent[i] = D.parent[i]; P.type[i] = D.type[i]; P.idx_q[i] = D.idx_q[i]; P.idx_v[i] = D.idx_v[i];
-    P.nvj[i] = D.nvj[i]; P.nvsub[i] = D.nvsub[i]; P.depth[i] = D.depth[i];
+    P.nvj[i] = D.nvj[i]; P.nvsub[i] = D.nvsub[i]; P.depth[i] = D.depth[i]; P.unb[i] = D.unb[i];
     for (int k = 0; k < 12; ++k) P.placement[i][k] = (T)D.placement[i][k];
     for (int k = 0; k < 10; ++k) P.inertia[i][k] = (T)D.inertia[i][k];
   }
@@ -56,7 +64,7 @@ inline brbd_status build_model_pod(const brbd_flat_model * f, ModelPOD<double> &
       P.nvj[i] = 0; P.depth[i] = 0;
       continue;
     }
-    if (P.type[i] < BRBD_JOINT_RX || P.type[i] > BRBD_JOINT_PRISMATIC_UNALIGNED)
+    if (P.type[i] < BRBD_JOINT_RX || P.type[i] > BRBD_JOINT_REVOLUTE_UNBOUNDED_UNALIGNED)
     { err = "joint " + std::to_string(i) + " has unsupported type tag " + std::to_string(f->joint_type[i]); return BRBD_EUNSUPPORTED_JOINT; }
     if (P.parent[i] < 0 || P.parent[i] >= i)
     { err = "parents[" + std::to_string(i) + "] must be < " + std::to_string(i); return BRBD_ETOPOLOGY; }
@@ -160,8 +168,17 @@ inline brbd_status build_model_pod(const brbd_flat_model * f, ModelPOD<double> &
         const double pp[3] = {plc[12 * k + 9], plc[12 * k + 10], plc[12 * k + 11]};
         for (int r = 0; r < 3; ++r) plc[12 * k + 9 + r] = RaT[3 * r] * pp[0] + RaT[3 * r + 1] * pp[1] + RaT[3 * r + 2] * pp[2];
       }
-    P.type[i] = P.type[i] == BRBD_JOINT_REVOLUTE_UNALIGNED ? BRBD_JOINT_RZ : BRBD_JOINT_PZ;
+    if (P.type[i] == BRBD_JOINT_REVOLUTE_UNBOUNDED_UNALIGNED) { P.type[i] = BRBD_JOINT_RZ; P.unb[i] = 1; }
+    else P.type[i] = P.type[i] == BRBD_JOINT_REVOLUTE_UNALIGNED ? BRBD_JOINT_RZ : BRBD_JOINT_PZ;
   }
+  // RUBX / RUBY / RUBZ: the revolute joint of the same axis whose configuration is (cos q, sin q); the kernels read the pair
+  // where they would call sincos (JointModelRevoluteUnbounded::calc, joint-revolute-unbounded.hpp:154-162)
+  for (int i = 1; i < f->njoints; ++i)
+    if (P.type[i] >= BRBD_JOINT_RUBX && P.type[i] <= BRBD_JOINT_RUBZ)
+    {
+      P.type[i] = BRBD_JOINT_RX + (P.type[i] - BRBD_JOINT_RUBX);
+      P.unb[i] = 1;
+    }
   for (int i = 0; i < f->njoints; ++i)
   {
     const double * S = &plc[12 * i];         // R row-major, p

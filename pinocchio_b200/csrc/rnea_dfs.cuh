@@ -64,7 +64,7 @@ rnea_dfs_kernel(const __grid_constant__ TreePOD<T> m, const RneaLayout L, const 
           an = __ldg(ac + m.j[i + 1].idx_v);
         }
         T sj, cj;
-        tree_sc(r.type, q0, &sj, &cj);
+        tree_sc_joint(m, i, r.type, qc + r.idx_q, q0, &sj, &cj);
         const SE3<T> X = tree_liMi_sc(m, i, r.type, qc + r.idx_q, sj, cj);
         Motion<T> vp = vi, ap = ai;
         if (r.parent == 0)

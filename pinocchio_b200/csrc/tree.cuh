@@ -34,7 +34,7 @@ struct JointRec
   short stop;    // parent[i + 1] (0 for the last joint): the unwind after fwd(i) stops there
   short nchild;
   short poff;    // offset of this joint in the per-configuration persistent store (ABA)
-  short pad_;
+  short unb;     // 1: unbounded revolute joint, q = (cos, sin)
 };
 
 template<class T> struct TreePOD
@@ -68,7 +68,7 @@ template<class T> inline void build_tree(const ModelPOD<double> & M, TreePOD<T> 
     const int p = M.parent[i];
     JointRec & r = P.j[i];
     r.type = (short)M.type[i]; r.parent = (short)p; r.idx_q = (short)M.idx_q[i]; r.idx_v = (short)M.idx_v[i];
-    r.nvj = (short)M.nvj[i]; r.depth = (short)M.depth[i];
+    r.nvj = (short)M.nvj[i]; r.depth = (short)M.depth[i]; r.unb = (short)M.unb[i];
     pdof[i] = p > 0 ? pdof[p] + M.nvj[p] : 0;
     r.pdof = (short)pdof[i];
     bdepth[i] = p > 0 ? bdepth[p] + (nchild[p] >= 2 ? 1 : 0) : 0;
@@ -231,10 +231,16 @@ template<class T> BRBD_DI void tree_sc(int type, T q0, T * s, T * c)
   if (type <= J_RZ) sincos_t(q0, s, c);
   else { *s = q0; *c = T(0); }
 }
+// (s, c) of joint i, also for the unbounded revolute joints whose configuration IS (cos, sin)
+template<class T> BRBD_DI void tree_sc_joint(const TreePOD<T> & m, int i, int type, const T * __restrict__ qj, T q0, T * s, T * c)
+{
+  if (m.j[i].unb) { *c = q0; *s = __ldg(qj + 1); }
+  else tree_sc(type, q0, s, c);
+}
 template<class T> BRBD_DI SE3<T> tree_liMi(const TreePOD<T> & m, int i, int type, const T * __restrict__ qj, T q0)
 {
   T s, c;
-  tree_sc(type, q0, &s, &c);
+  tree_sc_joint(m, i, type, qj, q0, &s, &c);
   return tree_liMi_sc(m, i, type, qj, s, c);
 }
 template<class T> BRBD_DI SE3<T> tree_liMi(const TreePOD<T> & m, int i, int type, const T * __restrict__ qj)

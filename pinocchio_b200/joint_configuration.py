@@ -24,7 +24,7 @@ from typing import Optional
 
 import numpy as np
 
-from .model import (JOINT_FREEFLYER, JOINT_PLANAR, JOINT_PZ, JOINT_REVOLUTE_UNALIGNED, JOINT_SPHERICAL, Model)
+from .model import (JOINT_FREEFLYER, JOINT_PLANAR, JOINT_PZ, JOINT_REVOLUTE_UNALIGNED, JOINT_SPHERICAL, Model, joint_is_unbounded)
 
 RAND_MAX = 2147483647
 
@@ -71,7 +71,11 @@ def randomConfiguration(model: Model, lo=None, hi=None, rng: Optional[LibcRand] 
 
     for j in range(1, model.njoints):
         t, iq = model.joint_types[j], model.idx_qs[j]
-        if t <= JOINT_PZ or t >= JOINT_REVOLUTE_UNALIGNED:
+        if joint_is_unbounded(t):
+            # SpecialOrthogonalOperationTpl<2>::random_impl (special-orthogonal.hpp): angle in [-pi, pi] -> (cos, sin)
+            ang = -math.pi + 2.0 * math.pi * rng.unit()
+            q[iq], q[iq + 1] = math.cos(ang), math.sin(ang)
+        elif t <= JOINT_PZ or t >= JOINT_REVOLUTE_UNALIGNED:
             vec(iq, 1)
         elif t == JOINT_FREEFLYER:
             vec(iq, 3)
@@ -96,7 +100,10 @@ def batched_random_configuration(model: Model, batch: int, seed: int, lo: float 
     q = np.empty((batch, model.nq), dtype=np.float64)
     for j in range(1, model.njoints):
         t, iq = model.joint_types[j], model.idx_qs[j]
-        if t <= JOINT_PZ or t >= JOINT_REVOLUTE_UNALIGNED:
+        if joint_is_unbounded(t):
+            ang = g.uniform(-math.pi, math.pi, batch)
+            q[:, iq], q[:, iq + 1] = np.cos(ang), np.sin(ang)
+        elif t <= JOINT_PZ or t >= JOINT_REVOLUTE_UNALIGNED:
             q[:, iq] = g.uniform(lo, hi, batch)
         elif t == JOINT_FREEFLYER:
             q[:, iq:iq + 3] = g.uniform(lo, hi, (batch, 3))
@@ -130,6 +137,8 @@ def neutral(model: Model) -> np.ndarray:
             q[iq + 3] = 1.0
         elif t == JOINT_PLANAR:
             q[iq + 2] = 1.0
+        elif joint_is_unbounded(t):
+            q[iq] = 1.0  # (cos, sin) of a zero angle
     return q
 
 
@@ -192,7 +201,13 @@ def integrate(model: Model, q: np.ndarray, v: np.ndarray) -> np.ndarray:
     out = np.array(q, dtype=np.float64, copy=True)
     for j in range(1, model.njoints):
         t, iq, iv = model.joint_types[j], model.idx_qs[j], model.idx_vs[j]
-        if t <= JOINT_PZ or t >= JOINT_REVOLUTE_UNALIGNED:
+        if joint_is_unbounded(t):  # SO(2), special-orthogonal.hpp:164-185
+            ca, sa = q[iq], q[iq + 1]
+            co, so = math.cos(v[iv]), math.sin(v[iv])
+            c1, s1 = co * ca - so * sa, so * ca + co * sa
+            n = (3.0 - (c1 * c1 + s1 * s1)) / 2.0
+            out[iq], out[iq + 1] = c1 * n, s1 * n
+        elif t <= JOINT_PZ or t >= JOINT_REVOLUTE_UNALIGNED:
             out[iq] = q[iq] + v[iv]
         elif t == JOINT_FREEFLYER:  # special-euclidean.hpp:660-698
             quat = q[iq + 3:iq + 7]

@@ -29,6 +29,8 @@ JOINT_RX, JOINT_RY, JOINT_RZ = 0, 1, 2
 JOINT_PX, JOINT_PY, JOINT_PZ = 3, 4, 5
 JOINT_FREEFLYER, JOINT_SPHERICAL, JOINT_PLANAR = 6, 7, 8
 JOINT_REVOLUTE_UNALIGNED, JOINT_PRISMATIC_UNALIGNED = 9, 10  # axis given per joint (joint-{revolute,prismatic}-unaligned.hpp)
+# unbounded revolute joints, q = (cos, sin): joint-revolute-unbounded.hpp:121-235 (URDF "continuous", parsers/urdf/model.hxx:269-273)
+JOINT_RUBX, JOINT_RUBY, JOINT_RUBZ, JOINT_REVOLUTE_UNBOUNDED_UNALIGNED = 11, 12, 13, 14
 JOINT_UNIVERSE = -1
 
 _JOINT_NAMES = {
@@ -37,10 +39,22 @@ _JOINT_NAMES = {
     JOINT_FREEFLYER: "JointModelFreeFlyer", JOINT_SPHERICAL: "JointModelSpherical",
     JOINT_PLANAR: "JointModelPlanar", JOINT_UNIVERSE: "universe",
     JOINT_REVOLUTE_UNALIGNED: "JointModelRevoluteUnaligned", JOINT_PRISMATIC_UNALIGNED: "JointModelPrismaticUnaligned",
+    JOINT_RUBX: "JointModelRUBX", JOINT_RUBY: "JointModelRUBY", JOINT_RUBZ: "JointModelRUBZ",
+    JOINT_REVOLUTE_UNBOUNDED_UNALIGNED: "JointModelRevoluteUnboundedUnaligned",
 }
 
 
+def joint_is_unbounded(t: int) -> bool:
+    return JOINT_RUBX <= t <= JOINT_REVOLUTE_UNBOUNDED_UNALIGNED
+
+
+def joint_has_axis(t: int) -> bool:
+    return t in (JOINT_REVOLUTE_UNALIGNED, JOINT_PRISMATIC_UNALIGNED, JOINT_REVOLUTE_UNBOUNDED_UNALIGNED)
+
+
 def joint_nq(t: int) -> int:
+    if joint_is_unbounded(t):
+        return 2
     return 1 if (0 <= t <= JOINT_PZ or t >= JOINT_REVOLUTE_UNALIGNED) else (7 if t == JOINT_FREEFLYER else 4)
 
 
@@ -241,7 +255,7 @@ class Model:
         self.nqs.append(nqj)
         self.nvs.append(nvj)
         self.jointPlacements.append(placement.copy())
-        if joint_type >= JOINT_REVOLUTE_UNALIGNED:
+        if joint_has_axis(joint_type):
             ax = np.asarray(axis, dtype=np.float64)
             if ax.shape != (3,) or not np.linalg.norm(ax) > 0:
                 raise ValueError("an unaligned joint needs a non-zero axis")
@@ -606,7 +620,8 @@ def buildModelFromUrdf(path_or_xml: str, root_joint: Optional[int] = None,
     merge their body into the parent joint; axis-aligned revolute / continuous / prismatic axes
     map to RX/RY/RZ / PX/PY/PZ, any other axis to RevoluteUnaligned / PrismaticUnaligned (which the engine re-frames
     into RZ / PZ at brbd_model_create, model_build.hpp).
-    ``continuous`` joints would be RUB* (nq=2) in the reference and are rejected here.
+    ``continuous`` joints become RUBX / RUBY / RUBZ / RevoluteUnboundedUnaligned (nq = 2, q = (cos, sin)) as in
+    parsers/urdf/model.hxx:269-273; mimic joints are rejected with the reference's wording.
     """
     text = path_or_xml
     if not path_or_xml.lstrip().startswith("<"):
@@ -666,6 +681,16 @@ def buildModelFromUrdf(path_or_xml: str, root_joint: Optional[int] = None,
                 lo = [float(lim.get("lower", "0"))] if lim is not None else None
                 hi = [float(lim.get("upper", "0"))] if lim is not None else None
                 jid = model.addJoint(frame.parentJoint, tag, frame.placement * placement, jname, lo, hi,
+                                     axis=axis if k is None else None)
+                jf = model.addJointFrame(jid, parent_fid)
+                body_frame[child] = _urdf_append_body(model, jf, Y, SE3.Identity(), child)
+            elif jtype == "continuous":
+                if j.find("mimic") is not None:
+                    raise ValueError("Cannot mimic this type. Only revolute, prismatic and helicoidal can be mimicked")
+                k = _axis_tag(axis)
+                tag = JOINT_REVOLUTE_UNBOUNDED_UNALIGNED if k is None else JOINT_RUBX + k
+                # an unbounded joint has no position limits; (cos, sin) is sampled on the circle whatever the bounds
+                jid = model.addJoint(frame.parentJoint, tag, frame.placement * placement, jname, [-1.01, -1.01], [1.01, 1.01],
                                      axis=axis if k is None else None)
                 jf = model.addJointFrame(jid, parent_fid)
                 body_frame[child] = _urdf_append_body(model, jf, Y, SE3.Identity(), child)

@@ -21,7 +21,7 @@ import numpy as np
 LD = np.longdouble
 
 # joint type tags as in include/pinocchio_b200.h (duplicated on purpose: no import from the package's algorithms)
-RX, RY, RZ, PX, PY, PZ, FF, SPH, PLANAR, RU, PU = range(11)
+RX, RY, RZ, PX, PY, PZ, FF, SPH, PLANAR, RU, PU, RUBX, RUBY, RUBZ, RUBU = range(15)
 
 
 def _quat_R(x, y, z, w):
@@ -31,11 +31,12 @@ def _quat_R(x, y, z, w):
     return (w * w - v @ v) * np.eye(3, dtype=LD) + 2 * np.outer(v, v) + 2 * w * K
 
 
-def _axis_R(axis, angle):
-    """Rodrigues."""
+def _axis_R(axis, angle, cs=None):
+    """Rodrigues; `cs` = (cos, sin) given directly (unbounded joints)."""
     a = np.asarray(axis, dtype=LD)
     K = np.array([[0, -a[2], a[1]], [a[2], 0, -a[0]], [-a[1], a[0], 0]], dtype=LD)
-    return np.eye(3, dtype=LD) + np.sin(angle) * K + (1 - np.cos(angle)) * (K @ K)
+    c, s_ = (np.cos(angle), np.sin(angle)) if cs is None else cs
+    return np.eye(3, dtype=LD) + s_ * K + (1 - c) * (K @ K)
 
 
 class BruteForce:
@@ -69,6 +70,11 @@ class BruteForce:
             elif t == PU:
                 a = np.asarray(m.axes[j], dtype=LD)
                 Rj, pj, ax = E, qj[0] * a, [("l", a)]
+            elif t in (RUBX, RUBY, RUBZ):
+                Rj, pj, ax = _axis_R(E[t - RUBX], None, (qj[0], qj[1])), np.zeros(3, dtype=LD), [("a", E[t - RUBX])]
+            elif t == RUBU:
+                a = np.asarray(m.axes[j], dtype=LD)
+                Rj, pj, ax = _axis_R(a, None, (qj[0], qj[1])), np.zeros(3, dtype=LD), [("a", a)]
             elif t == FF:
                 Rj, pj = _quat_R(qj[3], qj[4], qj[5], qj[6]), qj[:3].copy()
                 ax = [("l", E[0]), ("l", E[1]), ("l", E[2]), ("a", E[0]), ("a", E[1]), ("a", E[2])]

@@ -108,6 +108,24 @@ def make_extra_models():
             for k in range(4):
                 pf = addh(rev[(k + f) % 3] if k else M.JOINT_RZ, pf, f"finger_{side}{f}{k}")
     out["humanoid_hands"] = m4
+    # unbounded revolute joints (URDF "continuous": RUBX / RUBY / RUBZ / RevoluteUnboundedUnaligned, q = (cos, sin)): a wheeled
+    # base — planar joint, two wheels, a turret on a continuous joint about an oblique axis carrying a 2-dof arm
+    m5 = M.Model()
+    m5.name = "wheeled"
+
+    def addw(jt, parent, name, axis=None):
+        nqj = M.joint_nq(jt)
+        idx = m5.addJoint(parent, jt, rng.se3(), name, np.full(nqj, -1.0), np.full(nqj, 1.0), axis=axis)
+        m5.appendBodyToJoint(idx, rng.inertia(), M.SE3.Identity())
+        return idx
+    base = addw(M.JOINT_PLANAR, 0, "base")
+    addw(M.JOINT_RUBY, base, "wheel_l")
+    addw(M.JOINT_RUBX, base, "wheel_r")
+    tur = addw(M.JOINT_REVOLUTE_UNBOUNDED_UNALIGNED, base, "turret", [0.2, -0.3, 0.9])
+    sh = addw(M.JOINT_RUBZ, tur, "shoulder")
+    addw(M.JOINT_RY, sh, "elbow")
+    m5.armature = np.abs(rng.sym(m5.nv)) * 0.05
+    out["wheeled"] = m5
     return out
 
 

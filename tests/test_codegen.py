@@ -13,7 +13,7 @@ import pytest
 
 from conftest import MODEL_NAMES, load_model, make_extra_models, random_inputs
 
-ALL = MODEL_NAMES + ["mixed", "double_ff", "unaligned", "humanoid_hands"]
+ALL = MODEL_NAMES + ["mixed", "double_ff", "unaligned", "humanoid_hands", "wheeled"]
 EXTRA = make_extra_models()
 
 

@@ -34,7 +34,7 @@ def emu():
 
 def _models():
     extra = make_extra_models()
-    names = ["manipulator", "humanoid", "simple_humanoid_ff", "talos_reduced_ff", "mixed", "double_ff", "unaligned", "humanoid_hands"]
+    names = ["manipulator", "humanoid", "simple_humanoid_ff", "talos_reduced_ff", "mixed", "double_ff", "unaligned", "humanoid_hands", "wheeled"]
     return names, extra
 
 

@@ -325,7 +325,7 @@ def test_multi_device_pool(ctx):
 
 
 SPEC_MODELS = ["manipulator", "humanoid", "humanoid_random", "simple_humanoid_ff", "talos_reduced_ff", "mixed", "double_ff", "unaligned",
-               "humanoid_hands"]
+               "humanoid_hands", "wheeled"]
 
 
 @pytest.mark.parametrize("name", SPEC_MODELS)

@@ -11,7 +11,7 @@ from conftest import MODEL_NAMES, assert_close, load_model, make_extra_models, r
 
 pytestmark = pytest.mark.gpu
 
-ALL_MODELS = MODEL_NAMES + ["mixed", "double_ff", "unaligned", "humanoid_hands"]
+ALL_MODELS = MODEL_NAMES + ["mixed", "double_ff", "unaligned", "humanoid_hands", "wheeled"]
 
 
 @pytest.fixture(scope="module")

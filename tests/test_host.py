@@ -172,3 +172,59 @@ def test_pool_argument_marshalling_without_gpu():
     assert _describe(c, 3, "x").ld == 3
     with pytest.raises(ValueError):
         _describe(c, 3, "x", out=True)
+
+
+WHEELED_URDF = """<?xml version="1.0"?>
+<robot name="cart">
+  <link name="base"><inertial><origin xyz="0 0 0.1"/><mass value="5"/><inertia ixx="0.1" ixy="0" ixz="0" iyy="0.2" iyz="0" izz="0.3"/></inertial></link>
+  <link name="wheel_l"><inertial><mass value="1"/><inertia ixx="0.01" ixy="0" ixz="0" iyy="0.02" iyz="0" izz="0.01"/></inertial></link>
+  <link name="wheel_r"><inertial><mass value="1"/><inertia ixx="0.01" ixy="0" ixz="0" iyy="0.02" iyz="0" izz="0.01"/></inertial></link>
+  <link name="turret"><inertial><origin xyz="0.05 0 0.2"/><mass value="2"/><inertia ixx="0.05" ixy="0.001" ixz="0" iyy="0.05" iyz="0" izz="0.02"/></inertial></link>
+  <joint name="jl" type="continuous"><parent link="base"/><child link="wheel_l"/><origin xyz="0 0.3 0" rpy="0 0 0"/><axis xyz="0 1 0"/></joint>
+  <joint name="jr" type="continuous"><parent link="base"/><child link="wheel_r"/><origin xyz="0 -0.3 0"/><axis xyz="0 1 0"/></joint>
+  <joint name="jt" type="continuous"><parent link="base"/><child link="turret"/><origin xyz="0.1 0 0.2"/><axis xyz="0.1 0.2 1"/></joint>
+</robot>
+"""
+
+
+def test_urdf_continuous_joints_are_unbounded_revolute(oracle_cls):
+    """parsers/urdf/model.hxx:269-273: CONTINUOUS -> JointModelRUBX / RUBY / RUBZ / RevoluteUnboundedUnaligned (nq = 2, q = (cos, sin),
+    joint-revolute-unbounded.hpp:154-162).  Dynamics equal those of the bounded revolute joint at the same angle."""
+    from pinocchio_b200 import model as M
+    from pinocchio_b200.joint_configuration import neutral, randomConfiguration
+    m = M.buildModelFromUrdf(WHEELED_URDF, root_joint=M.JOINT_FREEFLYER)
+    assert [m.joint_types[m.getJointId(n)] for n in ("jl", "jr", "jt")] == [M.JOINT_RUBY, M.JOINT_RUBY, M.JOINT_REVOLUTE_UNBOUNDED_UNALIGNED]
+    assert (m.nq, m.nv) == (7 + 2 * 3, 6 + 3)
+    q0 = neutral(m)
+    assert np.allclose(q0[7:], [1, 0, 1, 0, 1, 0])
+    # the same robot with `revolute` joints: identical results at q_bounded = angle, q_unbounded = (cos, sin)(angle)
+    mb = M.buildModelFromUrdf(WHEELED_URDF.replace('type="continuous"', 'type="revolute"'), root_joint=M.JOINT_FREEFLYER)
+    rng = np.random.default_rng(3)
+    qb = np.concatenate([rng.uniform(-1, 1, 3), [0.1, -0.2, 0.3, 0.0], rng.uniform(-3, 3, 3)])
+    qb[3:7] /= np.linalg.norm(qb[3:7]) if np.linalg.norm(qb[3:7]) > 0 else 1.0
+    qb[6] = np.sqrt(max(0.0, 1.0 - qb[3] ** 2 - qb[4] ** 2 - qb[5] ** 2))
+    qu = np.concatenate([qb[:7], np.column_stack([np.cos(qb[7:]), np.sin(qb[7:])]).ravel()])
+    v, a = rng.uniform(-1, 1, m.nv), rng.uniform(-1, 1, m.nv)
+    ou, ob = oracle_cls(m), oracle_cls(mb)
+    assert np.allclose(ou.rnea(qu, v, a), ob.rnea(qb, v, a), rtol=1e-12, atol=1e-12)
+    assert np.allclose(ou.aba(qu, v, a), ob.aba(qb, v, a), rtol=1e-10, atol=1e-12)
+    assert np.allclose(ou.crba(qu, world=True), ob.crba(qb, world=True), rtol=1e-12, atol=1e-12)
+    q = randomConfiguration(m, np.full(m.nq, -1.0), np.full(m.nq, 1.0))
+    assert np.allclose(q[7::2] ** 2 + q[8::2] ** 2, 1.0)
+    with pytest.raises(ValueError, match="mimic"):
+        M.buildModelFromUrdf(WHEELED_URDF.replace('<axis xyz="0 1 0"/></joint>', '<axis xyz="0 1 0"/><mimic joint="jt"/></joint>', 1))
+
+
+def test_c_abi_accepts_unbounded_joint_tags():
+    """brbd_model_create: tags 11..14, nq = 2 per joint; a wrong nq is refused."""
+    from pinocchio_b200 import _capi
+    import ctypes
+    m = make_extra_models()["wheeled"]
+    fm, keep = _capi.make_flat(m.flat())
+    h = ctypes.c_void_p()
+    L = _capi.lib()
+    assert L.brbd_model_create(ctypes.byref(fm), ctypes.byref(h)) == _capi.BRBD_OK
+    assert (L.brbd_model_nq(h), L.brbd_model_nv(h)) == (m.nq, m.nv) == (4 + 2 * 4 + 1, 3 + 5)
+    L.brbd_model_destroy(h)
+    fm.nq = m.nq - 1
+    assert L.brbd_model_create(ctypes.byref(fm), ctypes.byref(h)) == _capi.BRBD_EINVAL
