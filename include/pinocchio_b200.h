@@ -94,6 +94,12 @@ int brbd_device_count(void);
 
 brbd_status brbd_model_create(const brbd_flat_model * flat, brbd_model ** out);
 void brbd_model_destroy(brbd_model * m);
+/* URDF -> model on the host C++ side (src/parsers/urdf/model.cpp:67-294, include/pinocchio/parsers/urdf/model.hxx:205-372:
+ * name-sorted depth-first visit, fixed joints merged into the parent body, axis-aligned / unaligned / continuous joints).
+ * `path_or_xml`: a file name, or the XML text itself when it starts with '<'.  `root_joint_type`: BRBD_JOINT_UNIVERSE for a
+ * fixed base, else BRBD_JOINT_FREEFLYER / PLANAR / SPHERICAL (pinocchio::urdf::buildModel(file, root_joint, model)).
+ * Mimic joints are refused (BRBD_EUNSUPPORTED_JOINT). */
+brbd_status brbd_model_from_urdf(const char * path_or_xml, int root_joint_type, brbd_model ** out);
 int brbd_model_nq(const brbd_model * m);
 int brbd_model_nv(const brbd_model * m);
 int brbd_model_njoints(const brbd_model * m);

@@ -27,7 +27,7 @@ SYMBOLS = [
     "brbd_host_register", "brbd_host_unregister", "brbd_nle_batch", "brbd_gravity_batch", "brbd_minverse_batch",
     "brbd_integrate_batch", "brbd_aba_euler_step_batch", "brbd_model_get_flat", "brbd_pool_resize", "brbd_pool_model",
     "brbd_pool_device_id", "brbd_pool_workspace_bytes", "brbd_codegen_source", "brbd_codegen_free", "brbd_pool_specialize",
-    "brbd_pool_specialized", "brbd_pool_set_specialized_min_batch",
+    "brbd_pool_specialized", "brbd_pool_set_specialized_min_batch", "brbd_model_from_urdf",
 ]
 
 
@@ -66,6 +66,7 @@ def lib():
     L.brbd_version.restype = ctypes.c_char_p
     L.brbd_device_count.restype = ci
     L.brbd_model_create.argtypes = [ctypes.POINTER(FlatModel), ctypes.POINTER(vp)]
+    L.brbd_model_from_urdf.argtypes = [ctypes.c_char_p, ci, ctypes.POINTER(vp)]
     L.brbd_model_destroy.argtypes = [vp]
     L.brbd_model_destroy.restype = None
     for f in ("brbd_model_nq", "brbd_model_nv", "brbd_model_njoints"):

@@ -667,6 +667,9 @@ def buildModelFromUrdf(path_or_xml: str, root_joint: Optional[int] = None,
             ax_el = j.find("axis")
             axis = np.array([float(t) for t in ax_el.get("xyz").split()]) if ax_el is not None else np.array([1.0, 0, 0])
             lim = j.find("limit")
+            if jtype != "fixed" and j.find("mimic") is not None:
+                # mimic joints (parsers/urdf/model.hxx:298-319) are not supported by the batched engine
+                raise ValueError(f"Cannot mimic this type. Only revolute, prismatic and helicoidal can be mimicked (joint {jname})")
             if jtype == "fixed":
                 # addFixedJointAndBody — parsers/urdf/model.hxx:347-361
                 M = frame.placement * placement
@@ -685,8 +688,6 @@ def buildModelFromUrdf(path_or_xml: str, root_joint: Optional[int] = None,
                 jf = model.addJointFrame(jid, parent_fid)
                 body_frame[child] = _urdf_append_body(model, jf, Y, SE3.Identity(), child)
             elif jtype == "continuous":
-                if j.find("mimic") is not None:
-                    raise ValueError("Cannot mimic this type. Only revolute, prismatic and helicoidal can be mimicked")
                 k = _axis_tag(axis)
                 tag = JOINT_REVOLUTE_UNBOUNDED_UNALIGNED if k is None else JOINT_RUBX + k
                 # an unbounded joint has no position limits; (cos, sin) is sampled on the circle whatever the bounds

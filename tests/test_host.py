@@ -228,3 +228,56 @@ def test_c_abi_accepts_unbounded_joint_tags():
     L.brbd_model_destroy(h)
     fm.nq = m.nq - 1
     assert L.brbd_model_create(ctypes.byref(fm), ctypes.byref(h)) == _capi.BRBD_EINVAL
+
+
+def _flat_from_c_urdf(text_or_path, root):
+    """brbd_model_from_urdf + brbd_model_get_flat -> dict of numpy arrays."""
+    import ctypes
+    from pinocchio_b200 import _capi
+    L = _capi.lib()
+    h = ctypes.c_void_p()
+    _capi.check(L.brbd_model_from_urdf(text_or_path.encode(), root, ctypes.byref(h)))
+    fm = _capi.FlatModel()
+    _capi.check(L.brbd_model_get_flat(h, ctypes.byref(fm)))
+    n, nv = fm.njoints, fm.nv
+    a = lambda ptr, k, dt: np.ctypeslib.as_array(ptr, shape=(k,)).astype(dt).copy()
+    out = {"njoints": n, "nq": fm.nq, "nv": nv, "parents": a(fm.parents, n, np.int32), "joint_type": a(fm.joint_type, n, np.int32),
+           "idx_q": a(fm.idx_q, n, np.int32), "idx_v": a(fm.idx_v, n, np.int32), "placement": a(fm.placement, 12 * n, np.float64).reshape(n, 12),
+           "inertia": a(fm.inertia, 10 * n, np.float64).reshape(n, 10), "axis": a(fm.axis, 3 * n, np.float64).reshape(n, 3)}
+    L.brbd_model_destroy(h)
+    return out
+
+
+def test_cpp_urdf_loader_matches_the_python_one():
+    """brbd_model_from_urdf (urdf_loader.cpp) against pinocchio_b200.model.buildModelFromUrdf: same joints in the same order,
+    same placements and merged inertias — on the wheeled cart (continuous + unaligned joints), on the reference's two robot
+    files when they are present (models/simple_humanoid.urdf, talos_reduced.urdf: unittest/urdf.cpp:85,252), fixed base and
+    free-flyer root."""
+    from pinocchio_b200 import model as M
+    from pinocchio_b200 import _capi
+    cases = [(WHEELED_URDF, M.JOINT_FREEFLYER), (WHEELED_URDF, None)]
+    for f in ("/root/reference/models/simple_humanoid.urdf",
+              "/root/reference/models/example-robot-data/robots/talos_data/robots/talos_reduced.urdf"):
+        if os.path.exists(f):
+            cases.append((f, M.JOINT_FREEFLYER))
+    for src, root in cases:
+        py = M.buildModelFromUrdf(src, root_joint=root).flat()
+        c = _flat_from_c_urdf(src, -1 if root is None else root)
+        assert (c["njoints"], c["nq"], c["nv"]) == (py["njoints"], py["nq"], py["nv"]), src[:60]
+        for k in ("parents", "joint_type", "idx_q", "idx_v"):
+            assert np.array_equal(c[k], py[k]), (src[:60], k)
+        assert np.allclose(c["placement"], py["placement"], rtol=0, atol=1e-15)
+        # joint 0 (the universe) carries the fixed-base root link in the Python mirror only; it never enters an algorithm
+        assert np.allclose(c["inertia"][1:], py["inertia"][1:], rtol=1e-14, atol=1e-15)
+        assert np.allclose(c["axis"], py["axis"].reshape(-1, 3), atol=1e-15)
+    if any(s.startswith("/root/reference/models/simple") for s, _ in cases):
+        c = _flat_from_c_urdf("/root/reference/models/simple_humanoid.urdf", M.JOINT_FREEFLYER)
+        assert (c["nq"], c["njoints"]) == (36, 31)  # unittest/urdf.cpp:85,252
+    import ctypes
+    h = ctypes.c_void_p()
+    L = _capi.lib()
+    assert L.brbd_model_from_urdf(b"<robot><link name='a'/><link name='b'/></robot>", -1, ctypes.byref(h)) == _capi.BRBD_EINVAL  # two roots
+    bad = WHEELED_URDF.replace('<axis xyz="0 1 0"/></joint>', '<axis xyz="0 1 0"/><mimic joint="jt"/></joint>', 1)
+    assert L.brbd_model_from_urdf(bad.encode(), -1, ctypes.byref(h)) == _capi.BRBD_EUNSUPPORTED_JOINT
+    assert b"mimic" in L.brbd_last_error_string()
+    assert L.brbd_model_from_urdf(b"/no/such/file.urdf", -1, ctypes.byref(h)) == _capi.BRBD_EINVAL
