@@ -20,6 +20,7 @@
 
 #include <cstddef>
 #include <cstdint>
+#include <memory>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -64,6 +65,18 @@ public:
   // flat: the fields of ModelTpl the algorithms read (see brbd_flat_model); devices: CUDA ordinals,
   // empty = device 0.  (With Pinocchio available, flatten a pinocchio::Model with
   // INTEGRATION.md's `flatten(const pinocchio::Model &)`.)
+  // from a URDF file / text (pinocchio::urdf::buildModel + ModelPool in one step); root_joint_type: BRBD_JOINT_UNIVERSE = fixed base
+  static DeviceModelPool * fromUrdf(const std::string & path_or_xml, int root_joint_type = BRBD_JOINT_UNIVERSE, const std::vector<int> & devices = {})
+  {
+    brbd_model * m = nullptr;
+    check_status(brbd_model_from_urdf(path_or_xml.c_str(), root_joint_type, &m));
+    brbd_flat_model f;
+    check_status(brbd_model_get_flat(m, &f));
+    DeviceModelPool * p = nullptr;
+    try { p = new DeviceModelPool(f, devices); } catch (...) { brbd_model_destroy(m); throw; }
+    brbd_model_destroy(m);
+    return p;
+  }
   explicit DeviceModelPool(const brbd_flat_model & flat, const std::vector<int> & devices = {})
   {
     check_status(brbd_model_create(&flat, &model_));
@@ -99,9 +112,43 @@ public:
       brbd_model_destroy(m);
     check_status(st);
   }
+  // ModelPoolTpl::getModel / getModels (pool/model.hpp:60-89): every replica holds the same model; what comes back is the
+  // flattened view of it (pointers owned by the pool, valid until the next update() / destruction)
+  brbd_flat_model getModel(size_t index = 0) const
+  {
+    // wording of pool/model.hpp:63-65
+    if (index >= size()) throw std::invalid_argument("Index greater than the size of the model vector.");
+    brbd_flat_model f;
+    check_status(brbd_model_get_flat(model_, &f));
+    return f;
+  }
+  std::vector<brbd_flat_model> getModels() const { return std::vector<brbd_flat_model>(size(), getModel(0)); }
+  // ModelPoolTpl::getData / getDatas (pool/model.hpp:91-...): a device replica has no per-thread Data; it owns a CUDA device and
+  // its grow-only arenas
+  struct DeviceData { int device; uint64_t workspace_bytes; };
+  DeviceData getData(size_t index) const
+  {
+    if (index >= size()) throw std::invalid_argument("Index greater than the size of the data vector.");
+    return DeviceData{brbd_pool_device_id(pool_, (int)index), brbd_pool_workspace_bytes(pool_, (int)index)};
+  }
+  std::vector<DeviceData> getDatas() const
+  {
+    std::vector<DeviceData> v;
+    for (size_t i = 0; i < size(); ++i) v.push_back(getData(i));
+    return v;
+  }
+  // ModelPoolTpl::resize (pool/model.hpp:110-131): the replicas of a device pool are devices
+  void resize(const std::vector<int> & devices) { check_status(brbd_pool_resize(pool_, devices.empty() ? nullptr : devices.data(), (int)devices.size())); }
+  // kernels generated for this model (the batched analogue of pinocchio's code generation, codegen/code-generator-algo.hpp)
+  void specialize(bool rnea = true, bool aba = true, bool crba = true)
+  {
+    check_status(brbd_pool_specialize(pool_, (rnea ? 1 << BRBD_GEN_RNEA : 0) | (aba ? 1 << BRBD_GEN_ABA : 0) | (crba ? 1 << BRBD_GEN_CRBA : 0), 0));
+  }
   int nq() const { return brbd_model_nq(model_); }
   int nv() const { return brbd_model_nv(model_); }
   brbd_pool * handle() { return pool_; }
+  // Unlike the reference (parallel/rnea.hpp:53 "The pool is too small"), num_threads is NOT checked against size(): the GPU
+  // path has no per-thread replicas, any num_threads is accepted.
 
 private:
   brbd_model * model_ = nullptr;
@@ -305,6 +352,52 @@ template<class Q, class M1>
 void crbaInParallel(const size_t num_threads, DeviceModelPool & pool, const Eigen::MatrixBase<Q> & q, const Eigen::MatrixBase<M1> & M)
 {
   crbaInParallel(num_threads, pool, detail::cview(q), detail::mview(M));
+}
+// argument order of computeRNEADerivatives(model, data, q, v, a, rnea_partial_dq, rnea_partial_dv, rnea_partial_da), rnea-derivatives.hpp:110-128
+template<class Q, class V1, class V2, class M1, class M2, class M3>
+void computeRNEADerivativesInParallel(const size_t num_threads, DeviceModelPool & pool, const Eigen::MatrixBase<Q> & q,
+                                      const Eigen::MatrixBase<V1> & v, const Eigen::MatrixBase<V2> & a, const Eigen::MatrixBase<M1> & rnea_partial_dq,
+                                      const Eigen::MatrixBase<M2> & rnea_partial_dv, const Eigen::MatrixBase<M3> & rnea_partial_da)
+{
+  computeRNEADerivativesInParallel(num_threads, pool, detail::cview(q), detail::cview(v), detail::cview(a), detail::mview(rnea_partial_dq),
+                                   detail::mview(rnea_partial_dv), detail::mview(rnea_partial_da));
+}
+// computeABADerivatives(model, data, q, v, tau, aba_partial_dq, aba_partial_dv, aba_partial_dtau), aba-derivatives.hpp:52-66
+template<class Q, class V1, class V2, class M1, class M2, class M3>
+void computeABADerivativesInParallel(const size_t num_threads, DeviceModelPool & pool, const Eigen::MatrixBase<Q> & q,
+                                     const Eigen::MatrixBase<V1> & v, const Eigen::MatrixBase<V2> & tau, const Eigen::MatrixBase<M1> & aba_partial_dq,
+                                     const Eigen::MatrixBase<M2> & aba_partial_dv, const Eigen::MatrixBase<M3> & aba_partial_dtau)
+{
+  computeABADerivativesInParallel(num_threads, pool, detail::cview(q), detail::cview(v), detail::cview(tau), detail::mview(aba_partial_dq),
+                                  detail::mview(aba_partial_dv), detail::mview(aba_partial_dtau));
+}
+template<class Q, class V1, class V2>
+void nonLinearEffectsInParallel(const size_t num_threads, DeviceModelPool & pool, const Eigen::MatrixBase<Q> & q, const Eigen::MatrixBase<V1> & v,
+                                const Eigen::MatrixBase<V2> & nle)
+{
+  nonLinearEffectsInParallel(num_threads, pool, detail::cview(q), detail::cview(v), detail::mview(nle));
+}
+template<class Q, class V1>
+void computeGeneralizedGravityInParallel(const size_t num_threads, DeviceModelPool & pool, const Eigen::MatrixBase<Q> & q, const Eigen::MatrixBase<V1> & g)
+{
+  computeGeneralizedGravityInParallel(num_threads, pool, detail::cview(q), detail::mview(g));
+}
+template<class Q, class M1>
+void computeMinverseInParallel(const size_t num_threads, DeviceModelPool & pool, const Eigen::MatrixBase<Q> & q, const Eigen::MatrixBase<M1> & Minv)
+{
+  computeMinverseInParallel(num_threads, pool, detail::cview(q), detail::mview(Minv));
+}
+template<class Q, class V1, class Q2>
+void integrateInParallel(const size_t num_threads, DeviceModelPool & pool, const Eigen::MatrixBase<Q> & q, const Eigen::MatrixBase<V1> & v,
+                         const Eigen::MatrixBase<Q2> & qout)
+{
+  integrateInParallel(num_threads, pool, detail::cview(q), detail::cview(v), detail::mview(qout));
+}
+template<class Q, class V1, class V2, class Q2, class V3>
+void abaEulerStepInParallel(const size_t num_threads, DeviceModelPool & pool, const Eigen::MatrixBase<Q> & q, const Eigen::MatrixBase<V1> & v,
+                            const Eigen::MatrixBase<V2> & tau, double dt, const Eigen::MatrixBase<Q2> & q_next, const Eigen::MatrixBase<V3> & v_next)
+{
+  abaEulerStepInParallel(num_threads, pool, detail::cview(q), detail::cview(v), detail::cview(tau), dt, detail::mview(q_next), detail::mview(v_next));
 }
 #endif // PINOCCHIO_B200_WITH_EIGEN
 
