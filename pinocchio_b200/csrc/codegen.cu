@@ -92,6 +92,33 @@ void emit_park_helpers(std::ostringstream & os, int n, int space, bool fp32, int
 // shared memory, row per configuration with an odd pitch, so that each lane then walks its own row conflict-free; the result
 // overwrites the x row and leaves through the same tile with coalesced stores.  (First version: one strided LDG per element and
 // lane, 32 sectors per instruction — the generated RNEA was bound by exactly that.)
+// sincos of the generated FP64 device code.  CUDA's sincos costs ~100 instructions per call site in straight-line code (a
+// third of them UMOV pairs materialising its polynomial coefficients, plus the out-of-line slow path of the Payne-Hanek
+// reduction), i.e. 2.9 k of the 7.7 k instructions of the humanoid RNEA — and the generated kernels run at the rate their
+// instructions can be FETCHED.  Same method, leaner: Cody-Waite reduction by pi/2 in three FMA steps, the fdlibm kernels
+// (__kernel_sin / __kernel_cos minimax polynomials on [-pi/4, pi/4], error < 1 ulp), coefficients as constant-bank operands;
+// No Payne-Hanek path: with FMA the three-step reduction keeps its absolute error near 1e-16 while n = rint(2 x / pi) is exact,
+// i.e. far beyond any joint angle; the quadrant is taken from a 64-bit n.  (A shared out-of-line slow path was tried: the call
+// sites' ABI spills cost more than the whole saving.)
+const char * device_sincos(bool fp32)
+{
+  if (fp32) return "#define BRBD_SINCOS(x, s, c) sincosf((x), (s), (c))\n";
+  return "__constant__ double BRBD_SC[16] = {6.36619772367581382433e-01, 1.57079632679489655800e+00, 6.12323399573676603587e-17, 8.47842766036889956997e-32,\n"
+         "  -1.66666666666666324348e-01, 8.33333333332248946124e-03, -1.98412698298579493134e-04, 2.75573137070700676789e-06, -2.50507602534068634195e-08, 1.58969099521155010221e-10,\n"
+         "  4.16666666666666019037e-02, -1.38888888888741095749e-03, 2.48015872894767294178e-05, -2.75573143513906633035e-07, 2.08757232129817482790e-09, -1.13596475577881948265e-11};\n"
+         "__device__ __forceinline__ void brbd_sincos(double x, double * s, double * c)\n{\n"
+         "  const double n = rint(x * BRBD_SC[0]);\n  const int i = (int)(__double2ll_rn(n) & 3ll);\n"
+         "  double r = fma(-n, BRBD_SC[1], x);\n  r = fma(-n, BRBD_SC[2], r);\n  r = fma(-n, BRBD_SC[3], r);\n"
+         "  const double z = r * r;\n"
+         "  double ps = fma(z, BRBD_SC[9], BRBD_SC[8]);\n  ps = fma(z, ps, BRBD_SC[7]);\n  ps = fma(z, ps, BRBD_SC[6]);\n  ps = fma(z, ps, BRBD_SC[5]);\n  ps = fma(z, ps, BRBD_SC[4]);\n"
+         "  const double sr = fma(z * r, ps, r);\n"
+         "  double pc = fma(z, BRBD_SC[15], BRBD_SC[14]);\n  pc = fma(z, pc, BRBD_SC[13]);\n  pc = fma(z, pc, BRBD_SC[12]);\n  pc = fma(z, pc, BRBD_SC[11]);\n  pc = fma(z, pc, BRBD_SC[10]);\n"
+         "  const double cr = fma(z * z, pc, fma(z, -0.5, 1.0));\n"
+         "  const double s0 = (i & 1) ? cr : sr, c0 = (i & 1) ? sr : cr;\n"
+         "  *s = (i & 2) ? -s0 : s0;\n  *c = ((i + 1) & 2) ? -c0 : c0;\n}\n"
+         "#define BRBD_SINCOS(x, s, c) brbd_sincos((x), (s), (c))\n";
+}
+
 std::string wrap_device(const std::string & body, const char * name, bool fp32, int nrec, const cg::EmitStats & st, int nt, int minb,
                         int tmem_cols, int nq, int nv, int copies, bool direct_io, const std::string & ktable)
 {
@@ -101,7 +128,7 @@ std::string wrap_device(const std::string & body, const char * name, bool fp32, 
   const int qp = nq | 1, vp = nv | 1, tile = direct_io ? 0 : 32 * (qp + 2 * vp), warps = nt / 32;
   os << "// generated by pinocchio_b200 codegen: " << name << (fp32 ? " (FP32)" : " (FP64)") << ", " << nrec << " record slots, "
      << st.tmem_slots << " tensor-memory + " << st.smem_slots << " shared-memory park slots per configuration\n";
-  os << math_macros(fp32) << ktable;
+  os << math_macros(fp32) << "#undef BRBD_SINCOS\n" << device_sincos(fp32) << ktable;
   os << (fp32 ? "__device__ __forceinline__ real ld_rec(const real * p) { real v; asm volatile(\"ld.global.cg.f32 %0, [%1];\" : \"=f\"(v) : \"l\"(p) : \"memory\"); return v; }\n"
               : "__device__ __forceinline__ real ld_rec(const real * p) { real v; asm volatile(\"ld.global.cg.f64 %0, [%1];\" : \"=d\"(v) : \"l\"(p) : \"memory\"); return v; }\n");
   // warp-cooperative tile copies: `rows` elements per configuration, configurations `ld` apart in global memory, `pitch` apart
@@ -228,7 +255,7 @@ std::string wrap_device_crba(const std::string & body, bool fp32, const cg::Emit
   const int pitch = nv | 1;       // LSU variant: odd pitch, conflict-free rows
   const int epad = nv + (nv & 1); // TMA variant: the box's inner extent (even: rows stay 16-byte aligned)
   os << "// generated by pinocchio_b200 codegen: crba" << (fp32 ? " (FP32)" : " (FP64)") << "\n";
-  os << math_macros(fp32) << ktable;
+  os << math_macros(fp32) << "#undef BRBD_SINCOS\n" << device_sincos(fp32) << ktable;
   os << (fp32 ? "__device__ __forceinline__ real ld_in(const real * p) { real v; asm volatile(\"ld.global.nc.f32 %0, [%1];\" : \"=f\"(v) : \"l\"(p)); return v; }\n"
               : "__device__ __forceinline__ real ld_in(const real * p) { real v; asm volatile(\"ld.global.nc.f64 %0, [%1];\" : \"=d\"(v) : \"l\"(p)); return v; }\n");
   os << "#define BRBD_IN0(k) ld_in(tq + (k))\n#define BRBD_SYNC()\n";
