@@ -282,7 +282,7 @@ def main():
         c0, c1 = column_range(Btot, world, rank)
         B = c1 - c0
     pool = pb.ModelPool(model, [local_rank])
-    spec = [] if args.generic else [k for k in algos if k in ("rnea", "aba", "crba")]
+    spec = [] if args.generic else [k for k in algos if k in ("rnea", "aba", "crba") or (k.endswith("derivatives") and model.nv <= 16)]
     if spec:
         pool.specialize(spec)  # kernels generated for this model (codegen + NVRTC), outside the timed region like the pool itself
     stream = torch.cuda.current_stream()
@@ -426,7 +426,7 @@ def main():
         gbs = alg[name]["bytes"] * B / (ms * 1e-3) / 1e9
         tfl = alg[name]["flops"] * B / (ms * 1e-3) / 1e12
         hbm_frac, fp64_frac = gbs / hbm_peak, tfl / (fp64_peak / 1e12)
-        kern[name] = {"kernel": (f"brbd_gen_{name} (generated for the model, NVRTC)" if name in spec else KERNEL_NAME[name]), "ms_per_launch": ms, "share_of_step": ms / step_sum, "configs_per_s": B / (ms * 1e-3),
+        kern[name] = {"kernel": (f"brbd_gen_{name} (generated for the model, NVRTC)" if name in spec and not (name == "crba" and nv > 24) else KERNEL_NAME[name]), "ms_per_launch": ms, "share_of_step": ms / step_sum, "configs_per_s": B / (ms * 1e-3),
                       "algorithmic_bytes_per_config": alg[name]["bytes"], "algorithmic_flops_per_config": alg[name]["flops"],
                       "sincos_per_config": alg[name]["sincos"], "achieved_GBs": gbs, "hbm_frac": hbm_frac,
                       "achieved_fp64_TFLOPs": tfl, "fp64_frac_of_measured_dfma_peak": fp64_frac,

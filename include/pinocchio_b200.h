@@ -188,7 +188,8 @@ brbd_status brbd_aba_euler_step_batch(brbd_pool * p, const void * q, int64_t ldq
  * for THIS model: the tree unrolled, joint types resolved, placements / inertias folded in as constants.  *source is
  * malloc'ed; release it with brbd_codegen_free.  brbd_pool_specialize compiles it (NVRTC) and makes the pool's
  * brbd_rnea_batch / brbd_aba_batch use it for large batches. */
-enum { BRBD_GEN_RNEA = 0, BRBD_GEN_ABA = 1, BRBD_GEN_CRBA = 2 };
+enum { BRBD_GEN_RNEA = 0, BRBD_GEN_ABA = 1, BRBD_GEN_CRBA = 2,
+       BRBD_GEN_RNEA_DERIVATIVES = 3, BRBD_GEN_ABA_DERIVATIVES = 4 /* small models only: every result stays alive to the end */ };
 enum {
   BRBD_GEN_EXPLICIT_SLOTS = 1, /* long-lived values in explicit on-chip slots instead of compiler-managed local memory */
   BRBD_GEN_HOST = 2,           /* emit the host-callable variant (tests of the generator only)                          */

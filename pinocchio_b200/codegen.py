@@ -7,7 +7,7 @@ import ctypes
 
 from . import _capi
 
-ALGOS = {"rnea": 0, "aba": 1, "crba": 2}
+ALGOS = {"rnea": 0, "aba": 1, "crba": 2, "rnea_derivatives": 3, "aba_derivatives": 4}
 
 
 class CodegenInfo(ctypes.Structure):

@@ -423,7 +423,7 @@ brbd_status brbd_pool_specialize(brbd_pool * p, int algo_mask, int flags)
   brbd_status st = brbd_pool_synchronize(p);
   if (st != BRBD_OK) return st;
   if (!p->devs.empty()) CUDA_TRY(cudaSetDevice(p->devs[0].dev));
-  for (int algo = 0; algo < 3; ++algo)
+  for (int algo = 0; algo < 5; ++algo)
     if (algo_mask & (1 << algo))
     {
       st = specialize_one(p, algo, (flags & BRBD_GEN_FP32) != 0, flags);
@@ -435,7 +435,7 @@ int brbd_pool_specialized(const brbd_pool * p)
 {
   int mask = 0;
   if (p)
-    for (int algo = 0; algo < 3; ++algo)
+    for (int algo = 0; algo < 5; ++algo)
       if (p->gen[algo][0].nvar || p->gen[algo][1].nvar) mask |= 1 << algo;
   return mask;
 }

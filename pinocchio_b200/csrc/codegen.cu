@@ -8,6 +8,7 @@
 #include "codegen/sym.hpp"
 #include "host_ctx.hpp"
 #include "codegen/trace.hpp"
+#include "codegen/trace_derivs.hpp"
 #include "codegen/emit.hpp"
 
 #include <sstream>
@@ -16,7 +17,11 @@ using namespace brbd;
 
 namespace
 {
-const char * algo_name(int algo) { return algo == BRBD_GEN_RNEA ? "rnea" : (algo == BRBD_GEN_ABA ? "aba" : "crba"); }
+const char * algo_name(int algo)
+{
+  const char * names[] = {"rnea", "aba", "crba", "rnea_derivatives", "aba_derivatives"};
+  return names[algo];
+}
 
 const char * math_macros(bool fp32)
 {
@@ -333,6 +338,62 @@ std::string wrap_device_crba(const std::string & body, bool fp32, const cg::Emit
   return os.str();
 }
 
+// Device wrapper of the generated derivative kernels (small models): every lane reads its own q / v / x column.  Results:
+// `staged` — each lane fills its row of three per-warp tiles (32 x nv^2, odd pitch) in shared memory and the warp writes them
+// out with coalesced stores (906 MB per algorithm at 2^20 x manipulator: strided 8-byte stores were the whole run time);
+// otherwise every lane stores its own results directly.
+std::string wrap_device_derivs(const std::string & body, const char * name, bool fp32, int nt, const std::string & ktable, int nv, bool staged)
+{
+  std::ostringstream os;
+  const int nn = nv * nv, pitch = nn | 1, vp = nv | 1, tile = 32 * (3 * pitch + vp);
+  os << "// generated by pinocchio_b200 codegen: " << name << (fp32 ? " (FP32)" : " (FP64)") << "\n";
+  os << math_macros(fp32) << "#undef BRBD_SINCOS\n" << device_sincos(fp32) << ktable;
+  os << (fp32 ? "__device__ __forceinline__ real ld_in(const real * p) { real v; asm volatile(\"ld.global.nc.f32 %0, [%1];\" : \"=f\"(v) : \"l\"(p)); return v; }\n"
+              : "__device__ __forceinline__ real ld_in(const real * p) { real v; asm volatile(\"ld.global.nc.f64 %0, [%1];\" : \"=d\"(v) : \"l\"(p)); return v; }\n");
+  os << "#define BRBD_IN0(k) ld_in(tq + (k))\n#define BRBD_IN1(k) ld_in(tv + (k))\n#define BRBD_IN2(k) ld_in(tx + (k))\n#define BRBD_SYNC()\n";
+  if (staged)
+  {
+    os << "__device__ __noinline__ void tile_out(real * __restrict__ g, long long ld, const real * t, int pitch, int rows, int nvalid, int lane)\n{\n"
+          "  if (ld == rows && nvalid == 32)\n  {\n    int c = 0, r = lane;\n    while (r >= rows) { r -= rows; ++c; }\n"
+          "#pragma unroll 4\n    for (int k = lane; k < 32 * rows; k += 32)\n    {\n      g[k] = t[c * pitch + r];\n      r += 32;\n"
+          "      while (r >= rows) { r -= rows; ++c; }\n    }\n  }\n  else\n"
+          "    for (int c = 0; c < nvalid; ++c)\n      for (int r = lane; r < rows; r += 32) g[c * ld + r] = t[c * pitch + r];\n}\n";
+    for (int k = 0; k < 4; ++k) os << "#define BRBD_OUT" << k << "(i, val) s" << k << "[(i)] = (val)\n";
+  }
+  else
+    for (int k = 0; k < 4; ++k) os << "#define BRBD_OUT" << k << "(i, val) do { if (live" << (k == 3 ? " && o3" : "") << ") p" << k << "[(i)] = (val); } while (0)\n";
+  os << "extern \"C\" __global__ void __launch_bounds__(" << nt << ", 1)\nbrbd_gen_" << name << "_0"
+     << "(const real * __restrict__ q, long long ldq, const real * __restrict__ v, long long ldv, const real * __restrict__ x, long long ldx,\n"
+        "     real * __restrict__ o0, long long ld0, real * __restrict__ o1, long long ld1, real * __restrict__ o2, long long ld2, real * __restrict__ o3, long long ld3, long long B)\n{\n";
+  os << "  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;\n";
+  if (staged)
+  {
+    os << "  extern __shared__ __align__(16) unsigned char smem_raw[];\n  real * tile = reinterpret_cast<real *>(smem_raw) + warp * " << tile << ";\n";
+    os << "  real * s0 = tile + lane * " << pitch << ";\n  real * s1 = s0 + " << 32 * pitch << ";\n  real * s2 = s1 + " << 32 * pitch << ";\n"
+          "  real * s3 = tile + " << 3 * 32 * pitch << " + lane * " << vp << ";\n";
+  }
+  os << "  const long long nthreads = (long long)gridDim.x * " << nt << ";\n";
+  os << "  for (long long cfg0 = (long long)blockIdx.x * " << nt << " + warp * 32; cfg0 < B; cfg0 += nthreads)\n  {\n";
+  os << "    const long long cfg_raw = cfg0 + lane;\n    const bool live = cfg_raw < B;\n    const long long cfg = live ? cfg_raw : B - 1;\n";
+  os << "    const int nvalid = (int)(B - cfg0 < 32 ? B - cfg0 : 32);\n";
+  os << "    const real * __restrict__ tq = q + cfg * ldq;\n    const real * __restrict__ tv = v + cfg * ldv;\n    const real * __restrict__ tx = x + cfg * ldx;\n";
+  if (!staged)
+    os << "    real * __restrict__ p0 = o0 + cfg * ld0;\n    real * __restrict__ p1 = o1 + cfg * ld1;\n    real * __restrict__ p2 = o2 + cfg * ld2;\n"
+          "    real * __restrict__ p3 = o3 ? o3 + cfg * ld3 : o3;\n";
+  os << "    {\n" << body << "    }\n";
+  if (staged)
+  {
+    os << "    __syncwarp();\n";
+    os << "    tile_out(o0 + cfg0 * ld0, ld0, tile, " << pitch << ", " << nn << ", nvalid, lane);\n";
+    os << "    tile_out(o1 + cfg0 * ld1, ld1, tile + " << 32 * pitch << ", " << pitch << ", " << nn << ", nvalid, lane);\n";
+    os << "    tile_out(o2 + cfg0 * ld2, ld2, tile + " << 2 * 32 * pitch << ", " << pitch << ", " << nn << ", nvalid, lane);\n";
+    os << "    if (o3) tile_out(o3 + cfg0 * ld3, ld3, tile + " << 3 * 32 * pitch << ", " << vp << ", " << nv << ", nvalid, lane);\n";
+    os << "    __syncwarp();\n";
+  }
+  os << "    (void)live; (void)nvalid;\n  }\n}\n";
+  return os.str();
+}
+
 std::string wrap_host(const std::string & body, const char * name, bool fp32, const cg::EmitStats & st, const std::string & ktable, int nv)
 {
   std::ostringstream os;
@@ -357,6 +418,14 @@ std::string wrap_host(const std::string & body, const char * name, bool fp32, co
     os << "#define BRBD_PARK_ST" << sp << sh.first << "(s, ...) park_st" << sp << sh.first << "(park + " << off << " + (s), __VA_ARGS__)\n";
     os << "#define BRBD_PARK_LD" << sp << sh.first << "(s, ...) park_ld" << sp << sh.first << "(park + " << off << " + (s), __VA_ARGS__)\n";
   }
+  if (std::string(name).find("derivatives") != std::string::npos)
+  { // oc = [block 0 | block 1 | block 2 | vector]
+    os << "#undef BRBD_OUT0\n#define BRBD_OUT0(i, val) oc[(i)] = (val)\n#define BRBD_OUT1(i, val) oc[BRBD_NV * BRBD_NV + (i)] = (val)\n"
+          "#define BRBD_OUT2(i, val) oc[2 * BRBD_NV * BRBD_NV + (i)] = (val)\n#define BRBD_OUT3(i, val) oc[3 * BRBD_NV * BRBD_NV + (i)] = (val)\n";
+    os << "extern \"C\" void brbd_gen_" << name << "_host(const real * qc, const real * vc, const real * xc, real * oc, real * rec, real * park)\n{\n";
+    os << body << "}\n";
+    return os.str();
+  }
   if (std::string(name) == "crba")
   { // matrix output: BRBD_OUT0 fills the staging row of the current column, BRBD_FLUSH copies it into column `col` of oc
     os << "#undef BRBD_OUT0\n#define BRBD_OUT0(row, val) colbuf[(row)] = (val)\n#define BRBD_COLBEGIN(col)\n#define BRBD_CLEAR(row) colbuf[(row)] = BRBD_C(0.0)\n"
@@ -378,7 +447,9 @@ brbd_status brbd_codegen_source(const brbd_model * m, int algo, int flags, char 
 {
   if (!m || !source) return fail(BRBD_EINVAL, "null argument");
   *source = nullptr;
-  if (algo != BRBD_GEN_RNEA && algo != BRBD_GEN_ABA && algo != BRBD_GEN_CRBA) return fail(BRBD_EINVAL, "code generation: unknown algorithm");
+  if (algo < BRBD_GEN_RNEA || algo > BRBD_GEN_ABA_DERIVATIVES) return fail(BRBD_EINVAL, "code generation: unknown algorithm");
+  if (algo >= BRBD_GEN_RNEA_DERIVATIVES && m->pd.nv > 16)
+    return fail(BRBD_EINVAL, "code generation: the derivative programs keep all 3 nv^2 results alive and are limited to nv <= 16");
   // CRBA: staging tiles per warp.  Rotating over 2 or 3 (so that a tensor store drains while the next column is assembled)
   // was measured and does not pay — 65 536 x simple_humanoid: 0.233 ms with one tile and 16 warps, 0.287 with two and 12
   // (profiles/r2_gen_crba_experiments.txt): the store path, not the wait for the tile, bounds the kernel
@@ -388,8 +459,13 @@ brbd_status brbd_codegen_source(const brbd_model * m, int algo, int flags, char 
   cg::Tracer T(m->pd, (flags & BRBD_GEN_EXPLICIT_SLOTS) != 0);
   if (algo == BRBD_GEN_ABA) cg::trace_aba(T);
   else if (algo == BRBD_GEN_CRBA) cg::trace_crba(T, crba_nbuf);
+  else if (algo == BRBD_GEN_RNEA_DERIVATIVES) cg::trace_rnea_derivatives(T);
+  else if (algo == BRBD_GEN_ABA_DERIVATIVES) cg::trace_aba_derivatives(T);
   else cg::trace_rnea(T);
   cg::EmitStats st;
+  // derivative programs: results through per-warp tiles when a warp's three nv^2 blocks fit beside those of its CTA's other warps
+  const size_t derivs_tile_bytes = (size_t)32 * (3 * ((m->pd.nv * m->pd.nv) | 1) + (m->pd.nv | 1)) * ((flags & BRBD_GEN_FP32) ? 4 : 8);
+  const bool derivs_staged = derivs_tile_bytes * ((((flags >> 8) & 0xfff) ? ((flags >> 8) & 0xfff) : 128) / 32) <= 220 * 1024;
   const int nt = (flags >> 8) & 0xfff ? (flags >> 8) & 0xfff : 128;
   const int minb = (flags >> 20) & 0xf ? (flags >> 20) & 0xf : 1;
   const bool fp32 = (flags & BRBD_GEN_FP32) != 0;
@@ -415,7 +491,9 @@ brbd_status brbd_codegen_source(const brbd_model * m, int algo, int flags, char 
     while (need < st.tmem_slots * wpv * ranges) need *= 2;
     tmem_cols = need;
   }
-  const std::string src = (algo == BRBD_GEN_CRBA && !(flags & BRBD_GEN_HOST))
+  const std::string src = (algo >= BRBD_GEN_RNEA_DERIVATIVES && !(flags & BRBD_GEN_HOST))
+                            ? wrap_device_derivs(body, algo_name(algo), fp32, nt, K.definition("__constant__"), m->pd.nv, derivs_staged)
+                            : (algo == BRBD_GEN_CRBA && !(flags & BRBD_GEN_HOST))
                             ? wrap_device_crba(body, fp32, st, nt, m->pd.nq, m->pd.nv, K.definition("__constant__"), crba_nbuf)
                             : (flags & BRBD_GEN_HOST) ? wrap_host(body, algo_name(algo), fp32, st, K.definition("static const"), m->pd.nv)
                                                   : wrap_device(body, algo_name(algo), fp32, T.nrec, st, nt, minb, tmem_cols, m->pd.nq, m->pd.nv, copies,
@@ -431,7 +509,8 @@ brbd_status brbd_codegen_source(const brbd_model * m, int algo, int flags, char 
     info->loads = st.inputs + st.rec_ld + st.park_ld; info->stores = st.rec_st + st.park_st + st.outputs;
     info->threads_per_block = nt;
     info->copies = copies;
-    if (algo == BRBD_GEN_CRBA) info->dynamic_smem_bytes = (int32_t)((size_t)crba_nbuf * (nt / 32) * 32 * (m->pd.nv + 2) * (fp32 ? 4 : 8));
+    if (algo >= BRBD_GEN_RNEA_DERIVATIVES) info->dynamic_smem_bytes = derivs_staged ? (int32_t)(derivs_tile_bytes * (nt / 32)) : 0;
+    else if (algo == BRBD_GEN_CRBA) info->dynamic_smem_bytes = (int32_t)((size_t)crba_nbuf * (nt / 32) * 32 * (m->pd.nv + 2) * (fp32 ? 4 : 8));
     else info->dynamic_smem_bytes = (int32_t)(((direct_io ? 0 : (size_t)(nt / 32) * 32 * ((m->pd.nq | 1) + 2 * (m->pd.nv | 1))) + (size_t)st.smem_slots * nt) * (fp32 ? 4 : 8));
   }
   return BRBD_OK;

@@ -246,13 +246,25 @@ inline void trace_aba(Tracer & T)
     return joint_velocity(M.type[i], tmp.data());
   };
 
+  // Loads are volatile and stay where the trace issues them, so they are issued AHEAD of their use: q / v of joint i + 1 while
+  // joint i is computed, tau of the next joint of an unwind one step early, the pass-3 records two joints ahead (first version:
+  // each load sat right in front of its consumer and `long_scoreboard` was 48 % of the stall samples of the kernel).
+  std::vector<std::vector<Sym>> q_pf(nj + 1), v_pf(nj + 1), tau_pf(nj + 1);
+  auto tauseg = [&](int j) {
+    std::vector<Sym> t;
+    for (int k = 0; k < M.nvj[j]; ++k) t.push_back(T.in(IN_X, M.idx_v[j] + k, 0));
+    return t;
+  };
+  if (nj > 1) { q_pf[1] = qseg(1, 0); v_pf[1] = vseg(1, 0); }
   for (int i = 1; i < nj; ++i)
   {
     const int type = M.type[i], parent = M.parent[i], nvj = M.nvj[i];
     T.comment("pass 1, joint " + std::to_string(i));
     // ---- pass 1, joint i: kinematics only (aba.hxx:101-131) ----
     Sym si(0.0), ci(0.0);
-    std::vector<Sym> qj = qseg(i, 0), vj = vseg(i, 0);
+    std::vector<Sym> qj = q_pf[i], vj = v_pf[i];
+    if (i + 1 < nj) { q_pf[i + 1] = qseg(i + 1, 0); v_pf[i + 1] = vseg(i + 1, 0); }
+    if (topo.stop[i] != i) tau_pf[i] = tauseg(i); // a leaf: its backward step follows at once
     if (type <= J_RZ && M.unb[i]) { ci = qj[0]; si = qj[1]; }
     else if (type <= J_RZ) sincos_t(qj[0], &si, &ci);
     else if (type <= J_PZ) si = qj[0];
@@ -292,6 +304,7 @@ inline void trace_aba(Tracer & T)
     {
       T.comment("pass 2, joint " + std::to_string(j));
       const int tj = M.type[j], pj = M.parent[j], nv_j = M.nvj[j], iv = M.idx_v[j];
+      if (pj != stop && pj > 0) tau_pf[pj] = tauseg(pj); // the unwind goes on with the parent
       Sym sj = si, cj = ci;
       std::vector<Sym> vjj = vj;
       std::vector<Sym> qjj = qj;
@@ -348,7 +361,7 @@ inline void trace_aba(Tracer & T)
       Sym U[6][6], StU[6][6], Di[6][6], UD[6][6], uj[6];
       for (int k = 0; k < nv_j; ++k)
       {
-        uj[k] = T.in(IN_X, iv + k, 0) - dot6(Jc[k], fi);
+        uj[k] = tau_pf[j][k] - dot6(Jc[k], fi);
         Sym Jv[6], Uk[6];
         m2a(Jc[k], Jv);
         sym6_mul(A, Jv, Uk);
@@ -450,17 +463,26 @@ inline void trace_aba(Tracer & T)
   // ---- pass 3 (aba.hxx:206-226) with the forward kinematics rebuilt from the recorded (sin, cos) -------------------
   std::vector<Tracer::Parked> bstate(nj);   // (oMi, ov, oa_gf) of a branching joint for its later children
   Motion<Sym> ag = mzero<Sym>();
+  struct P3 { std::vector<Sym> R, qj, vj; };
+  std::vector<P3> p3(nj + 1);
+  auto p3_load = [&](int i) {
+    p3[i].R = T.record_load(rec[i].first, rec[i].n);
+    if (M.nvj[i] > 1) p3[i].qj = qseg(i, 2);
+    p3[i].vj = vseg(i, 2);
+  };
+  constexpr int P3_AHEAD = 2;
+  for (int i = 1; i < nj && i <= P3_AHEAD; ++i) p3_load(i);
   for (int i = 1; i < nj; ++i)
   {
     T.comment("pass 3, joint " + std::to_string(i));
     const int type = M.type[i], parent = M.parent[i], nvj = M.nvj[i], iv = M.idx_v[i];
-    std::vector<Sym> R = T.record_load(rec[i].first, rec[i].n);
+    if (i + P3_AHEAD < nj) p3_load(i + P3_AHEAD);
+    const std::vector<Sym> R = p3[i].R;
     int o = 0;
     Sym si(0.0), ci(0.0);
-    std::vector<Sym> qj;
+    const std::vector<Sym> qj = p3[i].qj;
     if (nvj == 1) { si = R[0]; ci = R[1]; o = 2; }
-    else qj = qseg(i, 2);
-    std::vector<Sym> vj = vseg(i, 2);
+    const std::vector<Sym> vj = p3[i].vj;
     Motion<Sym> ovp = mzero<Sym>(), agp = mzero<Sym>();
     if (parent == 0)
       agp.lin = Vec3<Sym>(Sym(-M.gravity[0]), Sym(-M.gravity[1]), Sym(-M.gravity[2])); // data.oa_gf[0] = -gravity (aba.hxx:260)

@@ -102,7 +102,7 @@ struct GenSet
 
 struct brbd_pool
 {
-  brbd::GenSet gen[3][2]; // [BRBD_GEN_*][fp64, fp32]
+  brbd::GenSet gen[5][2]; // [BRBD_GEN_*][fp64, fp32]
   int64_t gen_min_batch = 8192; // batches at least this large use a specialised kernel when there is one
   brbd_model model;
   std::vector<brbd::DeviceCtx> devs;
@@ -386,6 +386,10 @@ void release_generated(brbd_pool * p);
 template<class T>
 brbd_status launch_generated(brbd_pool * p, DeviceCtx & d, int algo, const T * q, int64_t ldq, const T * v, int64_t ldv, const T * x,
                              int64_t ldx, T * out, int64_t ldo, int64_t B);
+// generated computeRNEADerivatives / computeABADerivatives (small models): q, v, x -> three nv*nv blocks + an nv block
+template<class T>
+brbd_status launch_generated_derivs(brbd_pool * p, DeviceCtx & d, int algo, const T * q, int64_t ldq, const T * v, int64_t ldv, const T * x,
+                                    int64_t ldx, T * o0, int64_t ld0, T * o1, int64_t ld1, T * o2, int64_t ld2, T * o3, int64_t ld3, int64_t B);
 template<class T> inline bool use_generated(const brbd_pool * p, int algo, int64_t B)
 {
   return p->gen[algo][sizeof(T) == 4 ? 1 : 0].nvar > 0 && B >= p->gen_min_batch;

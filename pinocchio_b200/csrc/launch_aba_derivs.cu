@@ -10,6 +10,8 @@ brbd_status launch_aba_derivs(brbd_pool * p, DeviceCtx & d, const T * q, int64_t
                               int64_t ld_dtau, T * ddq, int64_t ldddq, int64_t B)
 {
   const ModelPOD<double> & M = p->model.pd;
+  if (!std::getenv("BRBD_DABA_V") && use_generated<T>(p, BRBD_GEN_ABA_DERIVATIVES, B))
+    return launch_generated_derivs<T>(p, d, BRBD_GEN_ABA_DERIVATIVES, q, ldq, v, ldv, tau, ldtau, dq, ld_dq, dv, ld_dv, dtau, ld_dtau, ddq, ldddq, B);
   // preferred: one kernel, G lanes per configuration, everything in shared memory (aba_deriv_coop.cuh)
   {
     const int G = coop_group_size(M.nv);

@@ -73,7 +73,7 @@ brbd_status compile_cubin(const char * source, const char * name, std::vector<ch
 
 void release_generated(brbd_pool * p)
 {
-  for (int a = 0; a < 3; ++a)
+  for (int a = 0; a < 5; ++a)
     for (int f = 0; f < 2; ++f)
     {
       GenSet & g = p->gen[a][f];
@@ -85,7 +85,7 @@ void release_generated(brbd_pool * p)
 
 namespace
 {
-const char * kAlgoNames[] = {"rnea", "aba", "crba"};
+const char * kAlgoNames[] = {"rnea", "aba", "crba", "rnea_derivatives", "aba_derivatives"};
 
 // generate + compile + load one variant; BRBD_OK with k.kernel == nullptr when it does not fit the SM (too much shared memory)
 brbd_status build_variant(brbd_pool * p, int algo, bool fp32, int nt, bool direct, bool slots, GenKernel & k)
@@ -140,6 +140,13 @@ brbd_status specialize_one(brbd_pool * p, int algo, bool fp32, int flags)
   if (const char * e = std::getenv("BRBD_GEN_SLOTS")) slots = std::atoi(e) != 0;
   if (const char * e = std::getenv("BRBD_GEN_DIRECT")) direct = std::atoi(e) != 0;
   if (const char * e = std::getenv("BRBD_GEN_NT")) nts.push_back(std::max(32, std::min(1024, std::atoi(e) / 32 * 32)));
+  else if (algo >= BRBD_GEN_RNEA_DERIVATIVES)
+  { // every result stays alive (registers limit the warps); as many warps (<= 8) as the per-warp result tiles leave room for
+    const int nvm = p->model.pd.nv;
+    const size_t tile_bytes = (size_t)32 * (3 * ((nvm * nvm) | 1) + (nvm | 1)) * (fp32 ? 4 : 8);
+    const int w = (int)std::min<size_t>(8, (220 * 1024) / tile_bytes);
+    nts = {w >= 4 ? 32 * w : 256}; // fewer than 4 warps: no tiles, every lane stores its own results
+  }
   else if (algo == BRBD_GEN_CRBA) nts = {512, 384, 256}; // small state (128 registers at 16 warps, no spills): one staging row per lane
   else if (direct) nts = {448, 512, 256};
   else
@@ -201,6 +208,23 @@ brbd_status launch_generated(brbd_pool * p, DeviceCtx & d, int algo, const T * q
   p->launches += 1;
   return BRBD_OK;
 }
+template<class T>
+brbd_status launch_generated_derivs(brbd_pool * p, DeviceCtx & d, int algo, const T * q, int64_t ldq, const T * v, int64_t ldv, const T * x,
+                                    int64_t ldx, T * o0, int64_t ld0, T * o1, int64_t ld1, T * o2, int64_t ld2, T * o3, int64_t ld3, int64_t B)
+{
+  const GenKernel & k = p->gen[algo][sizeof(T) == 4 ? 1 : 0].var[0];
+  const int64_t ctas_needed = (B + k.nt - 1) / k.nt;
+  const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(ctas_needed, (int64_t)d.sm_count * (k.smem_bytes > 110 * 1024 ? 1 : 2)));
+  long long ldq_ = ldq, ldv_ = ldv, ldx_ = ldx, l0 = ld0, l1 = ld1, l2 = ld2, l3 = ld3, B_ = B;
+  void * args[] = {(void *)&q, &ldq_, (void *)&v, &ldv_, (void *)&x, &ldx_, (void *)&o0, &l0, (void *)&o1, &l1, (void *)&o2, &l2, (void *)&o3, &l3, &B_};
+  CUDA_TRY(cudaLaunchKernel((const void *)k.kernel, dim3(grid), dim3(k.nt), args, k.smem_bytes, d.s()));
+  p->launches += 1;
+  return BRBD_OK;
+}
+template brbd_status launch_generated_derivs<double>(brbd_pool *, DeviceCtx &, int, const double *, int64_t, const double *, int64_t, const double *,
+                                                     int64_t, double *, int64_t, double *, int64_t, double *, int64_t, double *, int64_t, int64_t);
+template brbd_status launch_generated_derivs<float>(brbd_pool *, DeviceCtx &, int, const float *, int64_t, const float *, int64_t, const float *,
+                                                    int64_t, float *, int64_t, float *, int64_t, float *, int64_t, float *, int64_t, int64_t);
 template brbd_status launch_generated<double>(brbd_pool *, DeviceCtx &, int, const double *, int64_t, const double *, int64_t, const double *,
                                               int64_t, double *, int64_t, int64_t);
 template brbd_status launch_generated<float>(brbd_pool *, DeviceCtx &, int, const float *, int64_t, const float *, int64_t, const float *,

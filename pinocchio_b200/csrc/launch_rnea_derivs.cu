@@ -9,6 +9,8 @@ brbd_status launch_rnea_derivs(brbd_pool * p, DeviceCtx & d, const T * q, int64_
                                int64_t ld_da, T * tau, int64_t ldtau, int64_t B)
 {
   const ModelPOD<double> & M = p->model.pd;
+  if (!std::getenv("BRBD_DRNEA_V") && use_generated<T>(p, BRBD_GEN_RNEA_DERIVATIVES, B))
+    return launch_generated_derivs<T>(p, d, BRBD_GEN_RNEA_DERIVATIVES, q, ldq, v, ldv, a, lda, dq, ld_dq, dv, ld_dv, da, ld_da, tau, ldtau, B);
   const CoopLayout L = coop_layout(M.nq, M.nv, M.njoints);
   const int G = coop_group_size(M.nv);
   const size_t static_bytes = sizeof(ModelPOD<T>) + sizeof(CoopTables) + 1024;

@@ -119,6 +119,8 @@ class ModelPool:
         from .codegen import ALGOS
         mask = 0
         for a in algos:
+            if a in ("rnea_derivatives", "aba_derivatives") and self.nv > 16:
+                continue  # these programs keep all 3 nv^2 results alive: small models only (the cooperative kernels serve the rest)
             mask |= 1 << ALGOS[a]
         try:
             _capi.check(_capi.lib().brbd_pool_specialize(self._h_pool, mask, 4 if fp32 else 0))

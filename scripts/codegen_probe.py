@@ -32,7 +32,7 @@ from oracle import Oracle
 orc = Oracle(model)
 B = 16
 q, v, x = random_inputs(model, B, 5)
-nout = model.nv * model.nv if args.algo == "crba" else model.nv
+nout = model.nv * model.nv if args.algo == "crba" else (3 * model.nv ** 2 + model.nv if "derivatives" in args.algo else model.nv)
 res = np.zeros((nout, B), order="F")
 rec = np.zeros(max(1, info["record_slots"])); park = np.zeros(max(1, info["park_slots"]))
 P = lambda a: a.ctypes.data_as(ctypes.c_void_p)
@@ -41,7 +41,13 @@ for i in range(B):
     rec[:] = np.nan; park[:] = np.nan
     fn(P(qi), P(vi), P(xi), P(oi), P(rec), P(park))
     res[:, i] = oi
-ref = orc.aba(q, v, x) if args.algo == "aba" else (orc.crba(q, world=False) if args.algo == "crba" else orc.rnea(q, v, x))
+if "derivatives" in args.algo:
+    parts = orc.rnea_derivatives(q, v, x) if args.algo == "rnea_derivatives" else orc.aba_derivatives(q, v, x)
+    ref = np.vstack(parts)
+    if args.algo == "rnea_derivatives":  # dtau_da: upper triangle only in the reference; the engine's v1 code fills the same
+        pass
+else:
+    ref = orc.aba(q, v, x) if args.algo == "aba" else (orc.crba(q, world=False) if args.algo == "crba" else orc.rnea(q, v, x))
 print("max |err| / max |ref| vs oracle: %.2e" % (np.abs(res - ref).max() / np.abs(ref).max()))
 if not args.no_device:
     src, info = codegen_source(model, args.algo, explicit_slots=args.slots, nt=args.nt, minb=args.minb, direct_io=args.direct)

@@ -388,3 +388,31 @@ def test_specialized_fp32(ctx):
     ref = orc.aba(q, v, a)
     assert np.abs(a32 - ref).max() / np.abs(ref).max() < 2e-5
     pool.close()
+
+
+@pytest.mark.parametrize("name", ["manipulator", "mixed", "wheeled", "unaligned"])
+def test_specialized_derivative_kernels(ctx, name):
+    """computeRNEADerivatives / computeABADerivatives generated for a small model (the engine's generic per-thread algorithm
+    traced on the recording scalar; BASELINE configs[2] runs the 6-dof manipulator through them): same parity bar, exact zeros
+    outside the tree sparsity, optional tau / ddq output."""
+    import pinocchio_b200 as pb
+    model, _, orc = ctx(name)
+    pool = pb.ModelPool(model, [0])
+    pool.specialize(["rnea_derivatives", "aba_derivatives"], min_batch=1)
+    assert set(pool.specialized()) == {"rnea_derivatives", "aba_derivatives"}
+    for B in (1, 300, 148 * 256 * 2 + 77):
+        q, v, a = random_inputs(model, B, 91)
+        tq, tv, ta = to_dev(q, v, a)
+        n0 = pool.launch_count()
+        got = pb.computeRNEADerivativesInParallel(1, pool, tq, tv, ta)
+        ref = orc.rnea_derivatives(q, v, a)
+        for g, r, nm in zip(got, ref, ("dtau_dq", "dtau_dv", "dtau_da", "tau")):
+            assert_close(to_host(g), r, rtol=1e-10, atol=1e-12 + 1e-11 * np.abs(r).max(axis=0, keepdims=True), what=f"{nm}[generated] {name} B={B}")
+        assert not to_host(got[2])[~structural_mask(model)].any()
+        assert not to_host(got[0])[~structural_mask(model, lower=True)].any()
+        got = pb.computeABADerivativesInParallel(1, pool, tq, tv, ta)
+        ref = orc.aba_derivatives(q, v, a)
+        for g, r, nm in zip(got, ref, ("ddq_dq", "ddq_dv", "ddq_dtau", "ddq")):
+            assert_close(to_host(g), r, rtol=1e-10, atol=1e-12 + 1e-10 * np.abs(r).max(axis=0, keepdims=True), what=f"{nm}[generated] {name} B={B}")
+        assert pool.launch_count() == n0 + 2
+    pool.close()
