@@ -254,10 +254,11 @@ std::string wrap_device(const std::string & body, const char * name, bool fp32, 
 //                       by one lane and asynchronous — the scheme of crba_tma_kernel (crba_dfs.cuh), including its shifted boxes
 //                       for odd nv: same tensor maps (crba_tma_setup), same CrbaTmaGeom.
 // q is read directly (nq strided loads per lane).
-std::string wrap_device_crba(const std::string & body, bool fp32, const cg::EmitStats & st, int nt, int nq, int nv, const std::string & ktable, int nbuf)
+std::string wrap_device_crba(const std::string & body, bool fp32, const cg::EmitStats & st, int nt, int nq, int nv, const std::string & ktable, int nbuf,
+                             int group)
 {
   std::ostringstream os;
-  const int pitch = nv | 1;       // LSU variant: odd pitch, conflict-free rows
+  const int pitch = (nv * group) | 1; // LSU variant: odd pitch, conflict-free rows
   const int epad = nv + (nv & 1); // TMA variant: the box's inner extent (even: rows stay 16-byte aligned)
   os << "// generated by pinocchio_b200 codegen: crba" << (fp32 ? " (FP32)" : " (FP64)") << "\n";
   os << math_macros(fp32) << "#undef BRBD_SINCOS\n" << device_sincos(fp32) << ktable;
@@ -266,17 +267,17 @@ std::string wrap_device_crba(const std::string & body, bool fp32, const cg::Emit
   os << "#define BRBD_IN0(k) ld_in(tq + (k))\n#define BRBD_SYNC()\n";
   os << "struct __align__(64) TensorMap { unsigned long long opaque[16]; };\n";
   // column `col` of the warp's configurations: element k = c * nv + r of the staging buffer goes to gM[c * ldM + r]
-  os << "__device__ __noinline__ void flush_col(real * colbuf, real * __restrict__ g, long long ldM, int nvalid, int lane)\n{\n"
-        "  __syncwarp();\n  int c = 0, r = lane;\n  while (r >= " << nv << ") { r -= " << nv << "; ++c; }\n"
-        "  const int total = nvalid * " << nv << ";\n"
+  os << "__device__ __noinline__ void flush_col(real * colbuf, real * __restrict__ g, long long ldM, int nvalid, int lane, int len)\n{\n"
+        "  __syncwarp();\n  int c = 0, r = lane;\n  while (r >= len) { r -= len; ++c; }\n"
+        "  const int total = nvalid * len;\n"
         "#pragma unroll 4\n  for (int k = lane; k < total; k += 32)\n  {\n    g[c * ldM + r] = colbuf[c * " << pitch << " + r];\n    r += 32;\n"
-        "    while (r >= " << nv << ") { r -= " << nv << "; ++c; }\n  }\n  __syncwarp();\n}\n";
+        "    while (r >= len) { r -= len; ++c; }\n  }\n  __syncwarp();\n}\n";
   os << "__device__ __forceinline__ void tma_store_2d(const void * tmap, const void * ssrc, int x, int y)\n{\n"
         "  asm volatile(\"cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];\" ::\"l\"(tmap),\n"
         "               \"r\"((unsigned)__cvta_generic_to_shared(ssrc)), \"r\"(x), \"r\"(y) : \"memory\");\n}\n";
   // ---- LSU variant ----
   os << "#define BRBD_OUT0(row, val) cb[(row)] = (val)\n#define BRBD_COLBEGIN(col)\n#define BRBD_CLEAR(row) cb[(row)] = BRBD_C(0.0)\n";
-  os << "#define BRBD_FLUSH(col) do { flush_col(colbuf + buf * " << 32 * pitch << ", gM + (col) * " << nv << ", ldM, nvalid, lane); buf = buf + 1 == " << nbuf
+  os << "#define BRBD_FLUSH(cc) do { flush_col(colbuf + buf * " << 32 * pitch << ", gM + ((cc) & 0xffff) * " << nv << ", ldM, nvalid, lane, ((cc) >> 16) * " << nv << "); buf = buf + 1 == " << nbuf
      << " ? 0 : buf + 1; cb = colbuf + buf * " << 32 * pitch << " + lane * " << pitch << "; } while (0)\n";
   os << "extern \"C\" __global__ void __launch_bounds__(" << nt << ", 1)\nbrbd_gen_crba_0"
      << "(const real * __restrict__ q, long long ldq, const real * __restrict__ v, long long ldv, const real * __restrict__ x, long long ldx,\n"
@@ -294,14 +295,16 @@ std::string wrap_device_crba(const std::string & body, bool fp32, const cg::Emit
   os << "    const long long cfg = cfg0 + (lane < nvalid ? lane : nvalid - 1);\n";
   os << "    const real * __restrict__ tq = q + cfg * ldq;\n    real * __restrict__ gM = out + cfg0 * ldM;\n";
   os << "    {\n" << body << "    }\n  }\n}\n";
+  if (group > 1) return os.str(); // the tensor-store variant takes one column per store
   // ---- TMA variant ----
   os << "#undef BRBD_OUT0\n#undef BRBD_COLBEGIN\n#undef BRBD_CLEAR\n#undef BRBD_FLUSH\n";
   os << "#define BRBD_OUT0(row, val) myrow[cs + (row)] = (val)\n#define BRBD_CLEAR(row) myrow[ps[buf] + (row)] = BRBD_C(0.0)\n";
   // the tile is free again once the engine has read the previous column block out of it; then this column's shift: one
   // element early where the segment starts at an odd element, two where it starts at an even one, none for the plain columns
   os << "#define BRBD_COLBEGIN(col) do { if (lane == 0) asm volatile(\"cp.async.bulk.wait_group.read " << nbuf - 1 << ";\" ::: \"memory\"); __syncwarp(); \\\n"
-        "    if (odd) { const int a_ = (half + (col)) & 1; plain = (col) == 0 || ((col) == " << nv - 1 << " && a_ == 0); cs = plain ? 0 : (a_ ? 1 : 2); } } while (0)\n";
-  os << "#define BRBD_FLUSH(col) do { asm volatile(\"fence.proxy.async.shared::cta;\" ::: \"memory\"); __syncwarp(); \\\n"
+        "    if (odd) { const int a_ = (half + ((col) & 0xffff)) & 1; plain = ((col) & 0xffff) == 0 || ((col) == " << nv - 1 << " && a_ == 0); cs = plain ? 0 : (a_ ? 1 : 2); } } while (0)\n";
+  os << "#define BRBD_FLUSH(cc) BRBD_FLUSH1(((cc) & 0xffff))\n";
+  os << "#define BRBD_FLUSH1(col) do { asm volatile(\"fence.proxy.async.shared::cta;\" ::: \"memory\"); __syncwarp(); \\\n"
         "    if (odd) { \\\n"
         "      const int a0_ = (col) & 1, a1_ = ((col) + 1) & 1; \\\n"
         "      const bool plain0_ = (col) == 0 || ((col) == " << nv - 1 << " && a0_ == 0), plain1_ = (col) == 0 || ((col) == " << nv - 1 << " && a1_ == 0); \\\n"
@@ -429,7 +432,7 @@ std::string wrap_host(const std::string & body, const char * name, bool fp32, co
   if (std::string(name) == "crba")
   { // matrix output: BRBD_OUT0 fills the staging row of the current column, BRBD_FLUSH copies it into column `col` of oc
     os << "#undef BRBD_OUT0\n#define BRBD_OUT0(row, val) colbuf[(row)] = (val)\n#define BRBD_COLBEGIN(col)\n#define BRBD_CLEAR(row) colbuf[(row)] = BRBD_C(0.0)\n"
-          "#define BRBD_FLUSH(col) for (int r_ = 0; r_ < BRBD_NV; ++r_) oc[(col) * BRBD_NV + r_] = colbuf[r_]\n";
+          "#define BRBD_FLUSH(cc) for (int r_ = 0; r_ < BRBD_NV; ++r_) oc[((cc) & 0xffff) * BRBD_NV + r_] = colbuf[r_]\n";
     os << "extern \"C\" void brbd_gen_crba_host(const real * qc, const real * vc, const real * xc, real * oc, real * rec, real * park)\n{\n"
           "  real colbuf[BRBD_NV];\n  for (int r_ = 0; r_ < BRBD_NV; ++r_) colbuf[r_] = BRBD_C(0.0);\n";
     os << body << "}\n";
@@ -456,9 +459,12 @@ brbd_status brbd_codegen_source(const brbd_model * m, int algo, int flags, char 
   int crba_nbuf = 1;
   if (const char * e = std::getenv("BRBD_GEN_CRBA_NBUF")) crba_nbuf = std::max(1, std::min(4, std::atoi(e)));
   if (flags & BRBD_GEN_HOST) crba_nbuf = 1;
+  // CRBA: adjacent columns per flush (see trace_crba); the host variant and the TMA variant take one column at a time
+  int crba_group = (flags >> 24) & 0x1f ? (flags >> 24) & 0x1f : 1;
+  if (flags & BRBD_GEN_HOST) crba_group = 1;
   cg::Tracer T(m->pd, (flags & BRBD_GEN_EXPLICIT_SLOTS) != 0);
   if (algo == BRBD_GEN_ABA) cg::trace_aba(T);
-  else if (algo == BRBD_GEN_CRBA) cg::trace_crba(T, crba_nbuf);
+  else if (algo == BRBD_GEN_CRBA) cg::trace_crba(T, crba_nbuf, crba_group);
   else if (algo == BRBD_GEN_RNEA_DERIVATIVES) cg::trace_rnea_derivatives(T);
   else if (algo == BRBD_GEN_ABA_DERIVATIVES) cg::trace_aba_derivatives(T);
   else cg::trace_rnea(T);
@@ -494,7 +500,7 @@ brbd_status brbd_codegen_source(const brbd_model * m, int algo, int flags, char 
   const std::string src = (algo >= BRBD_GEN_RNEA_DERIVATIVES && !(flags & BRBD_GEN_HOST))
                             ? wrap_device_derivs(body, algo_name(algo), fp32, nt, K.definition("__constant__"), m->pd.nv, derivs_staged)
                             : (algo == BRBD_GEN_CRBA && !(flags & BRBD_GEN_HOST))
-                            ? wrap_device_crba(body, fp32, st, nt, m->pd.nq, m->pd.nv, K.definition("__constant__"), crba_nbuf)
+                            ? wrap_device_crba(body, fp32, st, nt, m->pd.nq, m->pd.nv, K.definition("__constant__"), crba_nbuf, crba_group)
                             : (flags & BRBD_GEN_HOST) ? wrap_host(body, algo_name(algo), fp32, st, K.definition("static const"), m->pd.nv)
                                                   : wrap_device(body, algo_name(algo), fp32, T.nrec, st, nt, minb, tmem_cols, m->pd.nq, m->pd.nv, copies,
                                                                 direct_io, K.definition("__constant__"));
@@ -510,7 +516,7 @@ brbd_status brbd_codegen_source(const brbd_model * m, int algo, int flags, char 
     info->threads_per_block = nt;
     info->copies = copies;
     if (algo >= BRBD_GEN_RNEA_DERIVATIVES) info->dynamic_smem_bytes = derivs_staged ? (int32_t)(derivs_tile_bytes * (nt / 32)) : 0;
-    else if (algo == BRBD_GEN_CRBA) info->dynamic_smem_bytes = (int32_t)((size_t)crba_nbuf * (nt / 32) * 32 * (m->pd.nv + 2) * (fp32 ? 4 : 8));
+    else if (algo == BRBD_GEN_CRBA) info->dynamic_smem_bytes = (int32_t)((size_t)crba_nbuf * (nt / 32) * 32 * (m->pd.nv * crba_group + 2) * (fp32 ? 4 : 8));
     else info->dynamic_smem_bytes = (int32_t)(((direct_io ? 0 : (size_t)(nt / 32) * 32 * ((m->pd.nq | 1) + 2 * (m->pd.nv | 1))) + (size_t)st.smem_slots * nt) * (fp32 ? 4 : 8));
   }
   return BRBD_OK;

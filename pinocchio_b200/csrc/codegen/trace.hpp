@@ -672,7 +672,10 @@ inline void trace_rnea(Tracer & T)
 // Output: row r of the current column through Tracer::output (the wrapper's staging row of this configuration), then
 // Tracer::flush(column); rows outside the tree sparsity are zeros (a fresh Data, data.hxx:43).
 // ======================================================================================================================
-inline void trace_crba(Tracer & T, int nbuf = 1)
+// `group`: up to that many ADJACENT columns (the unwind of a chain emits columns c, c - 1, c - 2, ...) share one flush, so that
+// the wrapper writes group * nv contiguous elements per configuration at a time instead of nv (DRAM page locality of the store
+// stream); staging offsets and flush ranges are then relative to the group's first column.
+inline void trace_crba(Tracer & T, int nbuf = 1, int group = 1)
 {
   const ModelPOD<double> & M = T.M;
   const int nj = M.njoints;
@@ -682,8 +685,27 @@ inline void trace_crba(Tracer & T, int nbuf = 1)
   std::vector<Inertia<Sym>> Yacc(nj);
   std::vector<char> has_acc(nj, 0);
   // the wrapper may rotate over `nbuf` staging rows: the one a column is assembled in still holds the column of nbuf flushes ago
-  std::vector<std::vector<char>> prev_rows(nbuf, std::vector<char>(M.nv, 0));
+  std::vector<std::vector<char>> prev_rows(nbuf, std::vector<char>((size_t)M.nv * group, 0));
   int ncol = 0;
+  // the column order is static: partition it into groups of adjacent columns before tracing
+  std::vector<int> order, g_lo(M.nv, 0), g_last(M.nv, 0), g_hi(M.nv, 0);
+  for (int i = 1; i < nj; ++i)
+    for (int j = i; j != topo.stop[i]; j = M.parent[j])
+      for (int k = 0; k < M.nvj[j]; ++k) order.push_back(M.idx_v[j] + k);
+  for (size_t a = 0; a < order.size();)
+  {
+    int lo = order[a], hi = order[a];
+    size_t b = a + 1;
+    while (b < order.size() && (int)(b - a) < group && (order[b] == lo - 1 || order[b] == hi + 1))
+    {
+      lo = std::min(lo, order[b]); hi = std::max(hi, order[b]);
+      ++b;
+    }
+    for (size_t c = a; c < b; ++c) { g_lo[order[c]] = lo; g_hi[order[c]] = hi; g_last[order[c]] = (c + 1 == b); }
+    a = b;
+  }
+  std::vector<char> cur_rows((size_t)M.nv * group, 0);
+  bool group_open = false;
   auto liMi_of = [&](int a) { return sym_liMi(M, a, sc[a].s, sc[a].c, sc[a].q); };
   auto S_col = [&](int type, int k) { return joint_S_col<Sym>(type, k); };
   for (int i = 1; i < nj; ++i)
@@ -708,17 +730,23 @@ inline void trace_crba(Tracer & T, int nbuf = 1)
       for (int k = 0; k < nvj; ++k)
       {
         const int col = iv + k;
-        std::vector<char> rows(M.nv, 0);
-        T.colbegin(col);
-        for (int r = 0; r < M.nv; ++r)
-          if (prev_rows[ncol % nbuf][r]) T.clear(r);
+        const int off = (col - g_lo[col]) * M.nv; // position of this column in the group's staging row
+        if (!group_open)
+        {
+          T.colbegin(g_lo[col]);
+          for (int r = 0; r < M.nv * group; ++r)
+            if (prev_rows[ncol % nbuf][r]) T.clear(r);
+          std::fill(cur_rows.begin(), cur_rows.end(), 0);
+          group_open = true;
+        }
+        std::vector<char> & rows = cur_rows;
         Force<Sym> f = Y * S_col(tj, k);
         for (int kk = 0; kk < nvj; ++kk)
         { // the joint's own diagonal block (full, as M.block(idx_v, idx_v, nv, nvSubtree) = S^T F writes it)
           Sym val = dot6(S_col(tj, kk), f);
           if (kk == k) val += Sym(M.armature[col]);
-          T.output(OUT_MAIN, iv + kk, val);
-          rows[iv + kk] = 1;
+          T.output(OUT_MAIN, off + iv + kk, val);
+          rows[off + iv + kk] = 1;
         }
         for (int a = j; M.parent[a] > 0; a = M.parent[a])
         {
@@ -726,13 +754,17 @@ inline void trace_crba(Tracer & T, int nbuf = 1)
           f = liMi_of(a).act(f); // into the parent's frame
           for (int kk = 0; kk < M.nvj[pa]; ++kk)
           {
-            T.output(OUT_MAIN, M.idx_v[pa] + kk, dot6(S_col(M.type[pa], kk), f));
-            rows[M.idx_v[pa] + kk] = 1;
+            T.output(OUT_MAIN, off + M.idx_v[pa] + kk, dot6(S_col(M.type[pa], kk), f));
+            rows[off + M.idx_v[pa] + kk] = 1;
           }
         }
-        T.flush(col);
-        prev_rows[ncol % nbuf] = rows;
-        ++ncol;
+        if (g_last[col])
+        {
+          T.flush(g_lo[col] | ((g_hi[col] - g_lo[col] + 1) << 16)); // first column | number of columns << 16
+          prev_rows[ncol % nbuf] = rows;
+          ++ncol;
+          group_open = false;
+        }
       }
       if (pj > 0)
       {

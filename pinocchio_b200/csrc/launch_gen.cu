@@ -92,7 +92,16 @@ brbd_status build_variant(brbd_pool * p, int algo, bool fp32, int nt, bool direc
 {
   char * src = nullptr;
   brbd_codegen_info info;
-  const int gflags = (direct ? BRBD_GEN_DIRECT_IO : 0) | (slots ? BRBD_GEN_EXPLICIT_SLOTS : 0) | (fp32 ? BRBD_GEN_FP32 : 0) | (nt << 8) | (1 << 20);
+  // CRBA: adjacent columns per flush — as many as keep a staging row under ~1.5 KB (the whole matrix of a 6-dof arm).
+  // Measured on the 35-dof humanoid (profiles/r2_gen_crba_experiments.txt): 1 / 3 / 5 columns 4.11 / 3.00 / - ms at 2^20.
+  int group = 1;
+  if (algo == BRBD_GEN_CRBA)
+  {
+    const int nvm = p->model.pd.nv;
+    group = std::max(1, std::min(std::min(nvm, 31), 192 / std::max(1, nvm)));
+    if (const char * e = std::getenv("BRBD_GEN_CRBA_K")) group = std::max(1, std::min(31, std::atoi(e)));
+  }
+  const int gflags = (direct ? BRBD_GEN_DIRECT_IO : 0) | (slots ? BRBD_GEN_EXPLICIT_SLOTS : 0) | (fp32 ? BRBD_GEN_FP32 : 0) | (nt << 8) | (1 << 20) | (group << 24);
   brbd_status st = brbd_codegen_source(&p->model, algo, gflags, &src, &info);
   if (st != BRBD_OK) return st;
   if ((size_t)info.dynamic_smem_bytes + 2048 > (size_t)p->devs[0].max_smem_optin)
@@ -115,7 +124,11 @@ brbd_status build_variant(brbd_pool * p, int algo, bool fp32, int nt, bool direc
   }
   k.smem_bytes = (size_t)info.dynamic_smem_bytes;
   cudaKernel_t kern_tma = nullptr;
-  if (algo == BRBD_GEN_CRBA && cudaLibraryGetKernel(&kern_tma, lib, "brbd_gen_crba_tma") != cudaSuccess) kern_tma = nullptr;
+  if (algo == BRBD_GEN_CRBA && cudaLibraryGetKernel(&kern_tma, lib, "brbd_gen_crba_tma") != cudaSuccess)
+  { // grouped columns: the source has no tensor-store variant
+    kern_tma = nullptr;
+    (void)cudaGetLastError();
+  }
   if (k.smem_bytes > 48 * 1024)
     for (const DeviceCtx & d : p->devs)
     {
@@ -139,7 +152,8 @@ brbd_status specialize_one(brbd_pool * p, int algo, bool fp32, int flags)
   bool direct = algo == BRBD_GEN_ABA, slots = algo == BRBD_GEN_ABA || (flags & BRBD_GEN_EXPLICIT_SLOTS);
   if (const char * e = std::getenv("BRBD_GEN_SLOTS")) slots = std::atoi(e) != 0;
   if (const char * e = std::getenv("BRBD_GEN_DIRECT")) direct = std::atoi(e) != 0;
-  if (const char * e = std::getenv("BRBD_GEN_NT")) nts.push_back(std::max(32, std::min(1024, std::atoi(e) / 32 * 32)));
+  const char * nt_env = std::getenv(algo == BRBD_GEN_CRBA ? "BRBD_GEN_CRBA_NT" : "BRBD_GEN_NT");
+  if (nt_env) nts.push_back(std::max(32, std::min(1024, std::atoi(nt_env) / 32 * 32)));
   else if (algo >= BRBD_GEN_RNEA_DERIVATIVES)
   { // every result stays alive (registers limit the warps); as many warps (<= 8) as the per-warp result tiles leave room for
     const int nvm = p->model.pd.nv;
@@ -147,7 +161,7 @@ brbd_status specialize_one(brbd_pool * p, int algo, bool fp32, int flags)
     const int w = (int)std::min<size_t>(8, (220 * 1024) / tile_bytes);
     nts = {w >= 4 ? 32 * w : 256}; // fewer than 4 warps: no tiles, every lane stores its own results
   }
-  else if (algo == BRBD_GEN_CRBA) nts = {512, 384, 256}; // small state (128 registers at 16 warps, no spills): one staging row per lane
+  else if (algo == BRBD_GEN_CRBA) nts = {512, 384, 256, 128}; // small state (128 registers at 16 warps, no spills): one staging row per lane
   else if (direct) nts = {448, 512, 256};
   else
   {

@@ -1,5 +1,8 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_gpu_large.py -q -x -k "specialized_derivative" 2>&1 | tail -3
-timeout 900 python bench.py --config C3 --steps 5 > gpurun_out/bench_C3.json 2> gpurun_out/bench_C3.err; echo "C3 rc=$?"; python -c "
-import json; d=json.load(open('gpurun_out/bench_C3.json')); print('C3 value %.3e ms/step %.3f e2e %.3e' % (d['value'], d['ms_per_step'], d['e2e']['value'])); [print('  ',k,v['kernel'][:40],'%.3f ms'%v['ms_per_launch'], 'hbm %.3f' % v['hbm_frac']) for k,v in d['kernels'].items()]"
+for cfg in "1 512" "2 384" "3 256" "4 192" "5 160" "7 96"; do
+  set -- $cfg
+  echo "== CRBA group K=$1 NT=$2"
+  BRBD_CRBA_V=gen BRBD_GEN_CRBA_K=$1 BRBD_GEN_CRBA_NT=$2 timeout 300 python scripts/gen_quick.py simple_humanoid_ff talos_reduced_ff 2>&1 | grep -E "generated crba|rror" | tee -a gpurun_out/gen_quick.log
+done
+BRBD_CRBA_V=gen BRBD_GEN_CRBA_K=3 BRBD_GEN_CRBA_NT=256 timeout 300 python scripts/gen_quick.py simple_humanoid_ff --batch 1048576 --reps 5 2>&1 | grep -E "generated crba|rror"
