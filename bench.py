@@ -50,8 +50,10 @@ KERNEL_NAME = {"rnea": "rnea_dfs_kernel<double>", "aba": "aba_rr_kernel<double>"
 # dram__bytes_read.sum + dram__bytes_write.sum per launch, RECORDED from the committed `ncu --set full` capture named in
 # `source` (not measured in this run); only quoted for the exact configuration / batch of that capture, null otherwise.
 NCU_TRAFFIC = {
-    ("C2", 65536, "crba"): {"bytes": 643.4e6, "source": "profiles/r1_v8_step_ncu_full.csv (crba_tma_kernel<double,224,1>, commit 74f969d)"},
-    ("C2", 65536, "aba"): {"bytes": 814.2e6, "source": "profiles/r1_v8_step_ncu_full.csv (aba_rr_kernel<double,224>, commit 74f969d)"},
+    ("C2", 65536, "crba"): {"bytes": 644.2e6, "source": "profiles/r2_v1_step_ncu_full.csv (crba_tma_kernel<double,224,1>: 47.3 MB read + 596.9 MB written)"},
+    ("C2", 65536, "aba:generic"): {"bytes": 814.2e6, "source": "profiles/r1_v8_step_ncu_full.csv (aba_rr_kernel<double,224>: 388.1 MB read + 426.1 MB written)"},
+    ("C2", 65536, "aba"): {"bytes": 457.6e6, "source": "profiles/r2_v1_step_ncu_full.csv (brbd_gen_aba_0, 448 threads: 257.8 MB read + 199.8 MB written; "
+                                                       "the generic aba_rr_kernel: 814.2 MB, profiles/r1_v8_step_ncu_full.csv)"},
 }
 
 
@@ -284,7 +286,12 @@ def main():
     pool = pb.ModelPool(model, [local_rank])
     spec = [] if args.generic else [k for k in algos if k in ("rnea", "aba", "crba") or (k.endswith("derivatives") and model.nv <= 16)]
     if spec:
-        pool.specialize(spec)  # kernels generated for this model (codegen + NVRTC), outside the timed region like the pool itself
+        try:
+            pool.specialize(spec)  # kernels generated for this model (codegen + NVRTC), outside the timed region like the pool itself
+        except Exception as e:  # no NVRTC on this box: the generic kernels remain in use, and the line says so
+            print(f"bench.py: pool.specialize failed ({e}); generic kernels", file=sys.stderr)
+            spec = []
+        spec = [k for k in spec if k in pool.specialized()]
     stream = torch.cuda.current_stream()
     pool.set_stream(stream.cuda_stream)
 
@@ -435,7 +442,7 @@ def main():
 
     def roofline_of(name):
         k = kern[name]
-        tr = NCU_TRAFFIC.get((cfg_name, B, name))
+        tr = NCU_TRAFFIC.get((cfg_name, B, name if (name in spec or name == "crba") else name + ":generic"))
         if k["bound"] == "fp64":
             r = {"bound": "fp64", "kernel": k["kernel"], "achieved": k["achieved_fp64_TFLOPs"], "peak": fp64_peak / 1e12, "unit": "TFLOP/s",
                  "frac": k["fp64_frac_of_measured_dfma_peak"], "peak_source": "measured in this run (register-resident DFMA loop)"}
