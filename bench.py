@@ -50,7 +50,7 @@ KERNEL_NAME = {"rnea": "rnea_dfs_kernel<double>", "aba": "aba_rr_kernel<double>"
 # dram__bytes_read.sum + dram__bytes_write.sum per launch, RECORDED from the committed `ncu --set full` capture named in
 # `source` (not measured in this run); only quoted for the exact configuration / batch of that capture, null otherwise.
 NCU_TRAFFIC = {
-    ("C2", 65536, "crba"): {"bytes": 644.2e6, "source": "profiles/r2_v1_step_ncu_full.csv (crba_tma_kernel<double,224,1>: 47.3 MB read + 596.9 MB written)"},
+    ("C2", 65536, "crba:generic"): {"bytes": 644.2e6, "source": "profiles/r2_v1_step_ncu_full.csv (crba_tma_kernel<double,224,1>: 47.3 MB read + 596.9 MB written)"},
     ("C2", 65536, "aba:generic"): {"bytes": 814.2e6, "source": "profiles/r1_v8_step_ncu_full.csv (aba_rr_kernel<double,224>: 388.1 MB read + 426.1 MB written)"},
     ("C2", 65536, "aba"): {"bytes": 457.6e6, "source": "profiles/r2_v1_step_ncu_full.csv (brbd_gen_aba_0, 448 threads: 257.8 MB read + 199.8 MB written; "
                                                        "the generic aba_rr_kernel: 814.2 MB, profiles/r1_v8_step_ncu_full.csv)"},
@@ -433,7 +433,7 @@ def main():
         gbs = alg[name]["bytes"] * B / (ms * 1e-3) / 1e9
         tfl = alg[name]["flops"] * B / (ms * 1e-3) / 1e12
         hbm_frac, fp64_frac = gbs / hbm_peak, tfl / (fp64_peak / 1e12)
-        kern[name] = {"kernel": (f"brbd_gen_{name} (generated for the model, NVRTC)" if name in spec and not (name == "crba" and nv > 24) else KERNEL_NAME[name]), "ms_per_launch": ms, "share_of_step": ms / step_sum, "configs_per_s": B / (ms * 1e-3),
+        kern[name] = {"kernel": (f"brbd_gen_{name} (generated for the model, NVRTC)" if name in spec else KERNEL_NAME[name]), "ms_per_launch": ms, "share_of_step": ms / step_sum, "configs_per_s": B / (ms * 1e-3),
                       "algorithmic_bytes_per_config": alg[name]["bytes"], "algorithmic_flops_per_config": alg[name]["flops"],
                       "sincos_per_config": alg[name]["sincos"], "achieved_GBs": gbs, "hbm_frac": hbm_frac,
                       "achieved_fp64_TFLOPs": tfl, "fp64_frac_of_measured_dfma_peak": fp64_frac,
@@ -442,7 +442,7 @@ def main():
 
     def roofline_of(name):
         k = kern[name]
-        tr = NCU_TRAFFIC.get((cfg_name, B, name if (name in spec or name == "crba") else name + ":generic"))
+        tr = NCU_TRAFFIC.get((cfg_name, B, name if name in spec else name + ":generic"))
         if k["bound"] == "fp64":
             r = {"bound": "fp64", "kernel": k["kernel"], "achieved": k["achieved_fp64_TFLOPs"], "peak": fp64_peak / 1e12, "unit": "TFLOP/s",
                  "frac": k["fp64_frac_of_measured_dfma_peak"], "peak_source": "measured in this run (register-resident DFMA loop)"}

@@ -146,6 +146,17 @@ brbd_status brbd_aba_batch(brbd_pool * p, const void * q, int64_t ldq, const voi
  * written as zeros (crba.hpp:15-22; a fresh Data holds zeros there, data.hxx:43). ldM >= nv*nv. */
 brbd_status brbd_crba_batch(brbd_pool * p, const void * q, int64_t ldq, void * M, int64_t ldM,
                             int64_t batch, int flags);
+/* Packed CRBA (opt-in; not a reference signature): P[:,i] = the nnz entries of crba(q[:,i]) that lie inside the structural
+ * pattern of the model — for every column the dofs of its own joint and of the joint's ancestors; everything else in
+ * the reference's data.M is a structural zero (crba.hxx:94-95 writes M.block(idx_v, idx_v, nv, nvSubtree) only) — in
+ * column-major order: P[k,i] = M_i[rows[k], cols[k]] with (rows, cols) from brbd_model_crba_pattern.  For a humanoid
+ * that is a third of nv*nv, i.e. a third of the device-to-host traffic that bounds a host-pointer CRBA call.
+ * Runs the kernel generated for the pool's model (specialises CRBA at the first call: needs NVRTC).  ldP >= nnz. */
+brbd_status brbd_crba_packed_batch(brbd_pool * p, const void * q, int64_t ldq, void * P, int64_t ldP,
+                                   int64_t batch, int flags);
+/* The pattern: rows / cols may be NULL (size query); otherwise `capacity` entries each. */
+brbd_status brbd_model_crba_pattern(const brbd_model * m, int32_t * rows, int32_t * cols, int64_t capacity,
+                                    int64_t * nnz);
 /* computeRNEADerivatives per column (rnea-derivatives.hpp:110-128). dtau_dq, dtau_dv: full
  * tree-sparse matrices; dtau_da: upper triangle of M (others zero). tau may be NULL. */
 brbd_status brbd_rnea_derivatives_batch(brbd_pool * p, const void * q, int64_t ldq, const void * v,
@@ -194,8 +205,13 @@ enum {
   BRBD_GEN_EXPLICIT_SLOTS = 1, /* long-lived values in explicit on-chip slots instead of compiler-managed local memory */
   BRBD_GEN_HOST = 2,           /* emit the host-callable variant (tests of the generator only)                          */
   BRBD_GEN_FP32 = 4,           /* element type float                                                                     */
-  BRBD_GEN_DIRECT_IO = 8       /* no shared-memory input / output tiles: every lane reads its own column from global memory */
-  /* bits 8..19: threads per block (0 = default), bits 20..23: min blocks per SM of __launch_bounds__                     */
+  BRBD_GEN_DIRECT_IO = 8,      /* no shared-memory input / output tiles: every lane reads its own column from global memory */
+  BRBD_GEN_CRBA_COMPACT = 16,  /* CRBA: only the entries of the structural pattern are staged on chip; the kernel writes the  *
+                                * dense matrices (zeros put back by the flush) or the packed entries (brbd_crba_packed_batch)  */
+  BRBD_GEN_CRBA_BULK = 32      /* CRBA: every lane hands the staged columns of its configuration to the copy engine           *
+                                * (cp.async.bulk, asynchronous); bits 29..30: staging rows per lane - 1                        */
+  /* bits 8..19: threads per block (0 = default), bits 20..23: min blocks per SM of __launch_bounds__,                    *
+   * bits 24..28: CRBA: adjacent columns per flush (0 = 1); with BRBD_GEN_CRBA_COMPACT: pattern entries per flush / 8   */
 };
 typedef struct brbd_codegen_info {
   int32_t record_slots, park_slots, nodes, live_nodes, adds, muls, recips, sqrts, sincos, loads, stores, threads_per_block;

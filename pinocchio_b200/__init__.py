@@ -12,6 +12,6 @@ from .joint_configuration import (LibcRand, batched_random_configuration, batche
                                   neutral, randomConfiguration)
 from .pool import (ModelPool, abaEulerStepInParallel, abaInParallel, computeABADerivativesInParallel,  # noqa: F401
                    computeGeneralizedGravityInParallel, computeMinverseInParallel, computeRNEADerivativesInParallel,
-                   crbaInParallel, integrateInParallel, nonLinearEffectsInParallel, pin_host, rneaInParallel, unpin_host)
+                   crbaInParallel, crbaPackedInParallel, expandPackedCrba, integrateInParallel, nonLinearEffectsInParallel, pin_host, rneaInParallel, unpin_host)
 
 __version__ = "0.1.0"

@@ -507,6 +507,17 @@ brbd_status brbd_crba_batch(brbd_pool * p, const void * q, int64_t ldq, void * M
            })));
 }
 
+brbd_status brbd_crba_packed_batch(brbd_pool * p, const void * q, int64_t ldq, void * P, int64_t ldP, int64_t batch, int flags)
+{
+  if (!p) return fail(BRBD_EINVAL, "null pool");
+  const int nq = p->model.pd.nq;
+  const int64_t nnz = crba_pattern_nnz(p->model);
+  std::vector<Arg> args = {{q, nullptr, ldq, nq, false}, {nullptr, P, ldP, nnz, false}};
+  DISPATCH(flags, (run_call<T>(p, args, batch, flags, [&](DeviceCtx & d, std::vector<void *> & PP, int64_t B) {
+             return launch_crba_packed<T>(p, d, (const T *)PP[0], args[0].ld, (T *)PP[1], args[1].ld, B);
+           })));
+}
+
 brbd_status brbd_rnea_derivatives_batch(brbd_pool * p, const void * q, int64_t ldq, const void * v, int64_t ldv,
                                         const void * a, int64_t lda, void * dtau_dq, int64_t ld_dq, void * dtau_dv,
                                         int64_t ld_dv, void * dtau_da, int64_t ld_da, void * tau, int64_t ldtau,

@@ -254,11 +254,15 @@ std::string wrap_device(const std::string & body, const char * name, bool fp32, 
 //                       by one lane and asynchronous — the scheme of crba_tma_kernel (crba_dfs.cuh), including its shifted boxes
 //                       for odd nv: same tensor maps (crba_tma_setup), same CrbaTmaGeom.
 // q is read directly (nq strided loads per lane).
+//   compact staging (pat != nullptr; brbd_gen_crba_0 only): the staging row holds the entries of the group's structural pattern
+//                       only (a third of the group for a humanoid: three times the warps fit per SM), the flush puts the zeros
+//                       back from a position table in shared memory.  `ldx` carries the output mode: 0 = dense (the caller's
+//                       nv x nv matrices), 1 = packed (the rows leave as they are: nnz entries per configuration).
 std::string wrap_device_crba(const std::string & body, bool fp32, const cg::EmitStats & st, int nt, int nq, int nv, const std::string & ktable, int nbuf,
-                             int group)
+                             int group, const cg::CrbaPattern * pat)
 {
   std::ostringstream os;
-  const int pitch = (nv * group) | 1; // LSU variant: odd pitch, conflict-free rows
+  const int pitch = pat ? (pat->maxrow | 1) : ((nv * group) | 1); // LSU variant: odd pitch, conflict-free rows
   const int epad = nv + (nv & 1); // TMA variant: the box's inner extent (even: rows stay 16-byte aligned)
   os << "// generated by pinocchio_b200 codegen: crba" << (fp32 ? " (FP32)" : " (FP64)") << "\n";
   os << math_macros(fp32) << "#undef BRBD_SINCOS\n" << device_sincos(fp32) << ktable;
@@ -276,9 +280,33 @@ std::string wrap_device_crba(const std::string & body, bool fp32, const cg::Emit
         "  asm volatile(\"cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];\" ::\"l\"(tmap),\n"
         "               \"r\"((unsigned)__cvta_generic_to_shared(ssrc)), \"r\"(x), \"r\"(y) : \"memory\");\n}\n";
   // ---- LSU variant ----
+  if (pat)
+  {
+    os << "__constant__ short BRBD_CPOS[" << nv * nv << "] = {";
+    for (int k = 0; k < nv * nv; ++k) os << (k ? "," : "") << pat->pos[k];
+    os << "};\n__constant__ int BRBD_GBASE[" << nv << "] = {";
+    for (int k = 0; k < nv; ++k) os << (k ? "," : "") << pat->gbase[k];
+    os << "};\n__constant__ int BRBD_GNNZ[" << nv << "] = {";
+    for (int k = 0; k < nv; ++k) os << (k ? "," : "") << pat->gnnz[k];
+    os << "};\n";
+    // dense: element r of the group's run (len = columns * nv contiguous elements of configuration c) is the staged entry
+    // tab[r] of that configuration, or a structural zero
+    os << "__device__ __noinline__ void flush_dense(const real * colbuf, real * __restrict__ g, long long ldM, int nvalid, int lane, int len, const short * tab)\n{\n"
+          "  __syncwarp();\n  int c = 0, r = lane;\n  while (r >= len) { r -= len; ++c; }\n"
+          "  const int total = nvalid * len;\n"
+          "#pragma unroll 4\n  for (int k = lane; k < total; k += 32)\n  {\n    const int o = tab[r];\n"
+          "    g[c * ldM + r] = o >= 0 ? colbuf[c * " << pitch << " + o] : BRBD_C(0.0);\n    r += 32;\n"
+          "    while (r >= len) { r -= len; ++c; }\n  }\n  __syncwarp();\n}\n";
+    os << "#define BRBD_OUT0(row, val) cb[(row)] = (val)\n#define BRBD_COLBEGIN(col)\n#define BRBD_CLEAR(row)\n";
+    os << "#define BRBD_FLUSH(cc) do { if (packed) flush_col(colbuf, gM + BRBD_GBASE[(cc) & 0xffff], ldM, nvalid, lane, BRBD_GNNZ[(cc) & 0xffff]); \\\n"
+          "    else flush_dense(colbuf, gM + ((cc) & 0xffff) * " << nv << ", ldM, nvalid, lane, ((cc) >> 16) * " << nv << ", cpos + ((cc) & 0xffff) * " << nv << "); } while (0)\n";
+  }
+  else
+  {
   os << "#define BRBD_OUT0(row, val) cb[(row)] = (val)\n#define BRBD_COLBEGIN(col)\n#define BRBD_CLEAR(row) cb[(row)] = BRBD_C(0.0)\n";
   os << "#define BRBD_FLUSH(cc) do { flush_col(colbuf + buf * " << 32 * pitch << ", gM + ((cc) & 0xffff) * " << nv << ", ldM, nvalid, lane, ((cc) >> 16) * " << nv << "); buf = buf + 1 == " << nbuf
      << " ? 0 : buf + 1; cb = colbuf + buf * " << 32 * pitch << " + lane * " << pitch << "; } while (0)\n";
+  }
   os << "extern \"C\" __global__ void __launch_bounds__(" << nt << ", 1)\nbrbd_gen_crba_0"
      << "(const real * __restrict__ q, long long ldq, const real * __restrict__ v, long long ldv, const real * __restrict__ x, long long ldx,\n"
         "     real * __restrict__ out, long long ldM, real * __restrict__ recbase, long long B)\n{\n";
@@ -286,8 +314,13 @@ std::string wrap_device_crba(const std::string & body, bool fp32, const cg::Emit
   os << "  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;\n";
   os << "  real * colbuf = smem + warp * " << nbuf * 32 * pitch << ";\n  real * cb = colbuf + lane * " << pitch << ";\n  int buf = 0;\n";
   os << "  for (int k = lane; k < " << nbuf * 32 * pitch << "; k += 32) colbuf[k] = BRBD_C(0.0);\n  __syncwarp();\n";
+  if (pat)
+    os << "  __shared__ short cpos[" << nv * nv << "];\n  for (int k = threadIdx.x; k < " << nv * nv << "; k += " << nt << ") cpos[k] = BRBD_CPOS[k];\n"
+          "  __syncthreads();\n  const bool packed = ldx != 0;\n  (void)buf;\n";
   os << "  const long long nthreads = (long long)gridDim.x * " << nt << ";\n";
   os << "  const long long rounds = (B + nthreads - 1) / nthreads;\n";
+  if (const char * e = std::getenv("BRBD_GEN_CRBA_STAGGER")) // experiment: warps start that many cycles apart (out of phase)
+    os << "  if (rounds > 2) { const long long t0_ = clock64(); while (clock64() - t0_ < (long long)((warp * 7 + blockIdx.x) % " << nt / 32 << ") * " << std::atoi(e) << "ll) { } }\n";
   os << "  for (long long rd = 0; rd < rounds; ++rd)\n  {\n";
   os << "    const long long cfg0 = rd * nthreads + (long long)blockIdx.x * " << nt << " + warp * 32;\n";
   os << "    if (cfg0 >= B) continue; // warp-uniform\n";
@@ -295,7 +328,7 @@ std::string wrap_device_crba(const std::string & body, bool fp32, const cg::Emit
   os << "    const long long cfg = cfg0 + (lane < nvalid ? lane : nvalid - 1);\n";
   os << "    const real * __restrict__ tq = q + cfg * ldq;\n    real * __restrict__ gM = out + cfg0 * ldM;\n";
   os << "    {\n" << body << "    }\n  }\n}\n";
-  if (group > 1) return os.str(); // the tensor-store variant takes one column per store
+  if (group > 1 || pat) return os.str(); // the tensor-store variant takes one whole column per store
   // ---- TMA variant ----
   os << "#undef BRBD_OUT0\n#undef BRBD_COLBEGIN\n#undef BRBD_CLEAR\n#undef BRBD_FLUSH\n";
   os << "#define BRBD_OUT0(row, val) myrow[cs + (row)] = (val)\n#define BRBD_CLEAR(row) myrow[ps[buf] + (row)] = BRBD_C(0.0)\n";
@@ -338,6 +371,64 @@ std::string wrap_device_crba(const std::string & body, bool fp32, const cg::Emit
   os << "    {\n" << body << "    }\n  }\n";
   os << "  if (lane == 0) asm volatile(\"cp.async.bulk.wait_group 0;\" ::: \"memory\");\n  __syncwarp();\n}\n";
   (void)st; (void)nq;
+  return os.str();
+}
+
+// Device wrapper of the generated CRBA, bulk-copy variant (brbd_gen_crba_0, same arguments as the LSU variant).  Every lane
+// stages `group` adjacent columns of ITS configuration — group * nv contiguous elements of the caller's matrix — in its own row
+// of shared memory and hands the row to the copy engine with ONE cp.async.bulk.global.shared::cta: the store is asynchronous
+// (the lane goes on with the next columns in another of its `nbuf` rows), lane-local (no warp synchronisation: the lane that
+// wrote the row issues the copy) and one run of >= 600 bytes per copy.  Measured (scripts/micro/bulk_store_bw.cu): such copies
+// from 4-8 warps per SM sustain 5.2-5.7 TB/s into this very layout, coalesced STG from as few warps 2.5-4.6 TB/s, and both
+// fall with the number of resident warps (more configurations, i.e. more DRAM pages, written at the same time).
+// A bulk copy needs 16-byte aligned source, destination and size: the row is filled `sh` elements in, sh = the destination's
+// misalignment in elements (odd nv: every other configuration / column group), so that source and destination are congruent;
+// the few elements before / after the aligned interior leave through plain stores.
+std::string wrap_device_crba_bulk(const std::string & body, bool fp32, int nt, int nv, const std::string & ktable, int nbuf, int group)
+{
+  std::ostringstream os;
+  const int A = fp32 ? 4 : 2; // elements per 16 bytes
+  const int pitch = crba_bulk_pitch(nv, group, fp32); // rows 2 * odd (4 * odd) elements apart: at most 2-way (4-way) bank conflicts on the row writes
+  os << "// generated by pinocchio_b200 codegen: crba" << (fp32 ? " (FP32)" : " (FP64)") << ", bulk-copy variant\n";
+  os << math_macros(fp32) << "#undef BRBD_SINCOS\n" << device_sincos(fp32) << ktable;
+  os << (fp32 ? "__device__ __forceinline__ real ld_in(const real * p) { real v; asm volatile(\"ld.global.nc.f32 %0, [%1];\" : \"=f\"(v) : \"l\"(p)); return v; }\n"
+              : "__device__ __forceinline__ real ld_in(const real * p) { real v; asm volatile(\"ld.global.nc.f64 %0, [%1];\" : \"=d\"(v) : \"l\"(p)); return v; }\n");
+  os << "#define BRBD_IN0(k) ld_in(tq + (k))\n#define BRBD_SYNC()\n";
+  // row[sh + e] -> g[e], e in [0, L): plain stores for the unaligned head / tail, one bulk copy for the rest
+  os << "__device__ __forceinline__ void bulk_flush(const real * row, int sh, real * __restrict__ g, int L, bool live)\n{\n"
+        "  const int e0 = (" << A << " - sh) & " << A - 1 << ", n = (L - e0) & ~" << A - 1 << ";\n"
+        "  if (live)\n  {\n"
+        "    for (int e = 0; e < e0; ++e) g[e] = row[sh + e];\n"
+        "    for (int e = e0 + n; e < L; ++e) g[e] = row[sh + e];\n"
+        "    asm volatile(\"fence.proxy.async.shared::cta;\" ::: \"memory\");\n"
+        "    if (n > 0)\n"
+        "      asm volatile(\"cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\" ::\"l\"(g + e0), \"r\"((unsigned)__cvta_generic_to_shared(row + sh + e0)),\n"
+        "                   \"r\"(n * " << (fp32 ? 4 : 8) << ") : \"memory\");\n"
+        "  }\n"
+        "  asm volatile(\"cp.async.bulk.commit_group;\" ::: \"memory\");\n}\n";
+  os << "#define BRBD_OUT0(row, val) myrow[sh + (row)] = (val)\n#define BRBD_CLEAR(row) myrow[ps[buf] + (row)] = BRBD_C(0.0)\n";
+  // the row is free again once the copy engine has read the group of nbuf flushes ago out of it
+  os << "#define BRBD_COLBEGIN(col) do { asm volatile(\"cp.async.bulk.wait_group.read " << nbuf - 1 << ";\" ::: \"memory\"); sh = (par + ((col) & 0xffff) * " << nv << ") & " << A - 1 << "; } while (0)\n";
+  os << "#define BRBD_FLUSH(cc) do { bulk_flush(myrow, sh, gcfg + ((cc) & 0xffff) * " << nv << ", ((cc) >> 16) * " << nv << ", live); ps[buf] = sh; \\\n"
+        "    buf = buf + 1 == " << nbuf << " ? 0 : buf + 1; myrow = em + buf * " << 32 * pitch << " + lane * " << pitch << "; } while (0)\n";
+  os << "extern \"C\" __global__ void __launch_bounds__(" << nt << ", 1)\nbrbd_gen_crba_0"
+     << "(const real * __restrict__ q, long long ldq, const real * __restrict__ v, long long ldv, const real * __restrict__ x, long long ldx,\n"
+        "     real * __restrict__ out, long long ldM, real * __restrict__ recbase, long long B)\n{\n";
+  os << "  extern __shared__ __align__(128) unsigned char smem_raw[];\n  real * smem = reinterpret_cast<real *>(smem_raw);\n";
+  os << "  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;\n";
+  os << "  real * em = smem + warp * " << nbuf * 32 * pitch << ";\n  real * myrow = em + lane * " << pitch << ";\n";
+  os << "  for (int k = lane; k < " << nbuf * 32 * pitch << "; k += 32) em[k] = BRBD_C(0.0);\n  __syncwarp();\n";
+  os << "  int ps[" << nbuf << "] = {0}, sh = 0, buf = 0;\n";
+  os << "  const long long nthreads = (long long)gridDim.x * " << nt << ";\n";
+  os << "  const long long rounds = (B + nthreads - 1) / nthreads;\n";
+  os << "  for (long long rd = 0; rd < rounds; ++rd)\n  {\n";
+  os << "    const long long cfg0 = rd * nthreads + (long long)blockIdx.x * " << nt << " + warp * 32;\n";
+  os << "    if (cfg0 >= B) continue; // warp-uniform\n";
+  os << "    const bool live = cfg0 + lane < B;\n    const long long cfg = live ? cfg0 + lane : B - 1;\n";
+  os << "    const real * __restrict__ tq = q + cfg * ldq;\n    real * __restrict__ gcfg = out + cfg * ldM;\n";
+  os << "    const int par = (int)((reinterpret_cast<unsigned long long>(gcfg) / " << (fp32 ? 4 : 8) << "ull) & " << A - 1 << "ull);\n";
+  os << "    {\n" << body << "    }\n  }\n";
+  os << "  asm volatile(\"cp.async.bulk.wait_group 0;\" ::: \"memory\");\n}\n";
   return os.str();
 }
 
@@ -397,7 +488,8 @@ std::string wrap_device_derivs(const std::string & body, const char * name, bool
   return os.str();
 }
 
-std::string wrap_host(const std::string & body, const char * name, bool fp32, const cg::EmitStats & st, const std::string & ktable, int nv)
+std::string wrap_host(const std::string & body, const char * name, bool fp32, const cg::EmitStats & st, const std::string & ktable, int nv,
+                      const cg::CrbaPattern * pat = nullptr)
 {
   std::ostringstream os;
   os << "#define BRBD_NV " << nv << "\n";
@@ -429,12 +521,31 @@ std::string wrap_host(const std::string & body, const char * name, bool fp32, co
     os << body << "}\n";
     return os.str();
   }
+  if (std::string(name) == "crba" && pat)
+  { // compact staging: oc = [dense nv x nv matrix | packed entries]; the flush expands the group's row through the position table
+    // exactly as the device wrapper's flush_dense / flush_col do
+    os << "static const short BRBD_CPOS[" << nv * nv << "] = {";
+    for (int k = 0; k < nv * nv; ++k) os << (k ? "," : "") << pat->pos[k];
+    os << "};\nstatic const int BRBD_GBASE[" << nv << "] = {";
+    for (int k = 0; k < nv; ++k) os << (k ? "," : "") << pat->gbase[k];
+    os << "};\nstatic const int BRBD_GNNZ[" << nv << "] = {";
+    for (int k = 0; k < nv; ++k) os << (k ? "," : "") << pat->gnnz[k];
+    os << "};\n";
+    os << "#undef BRBD_OUT0\n#define BRBD_OUT0(row, val) colbuf[(row)] = (val)\n#define BRBD_COLBEGIN(col) for (int r_ = 0; r_ < " << (pat->maxrow | 1) << "; ++r_) colbuf[r_] = nan(\"\")\n#define BRBD_CLEAR(row)\n"
+          "#define BRBD_FLUSH(cc) do { const int lo_ = (cc) & 0xffff, len_ = ((cc) >> 16) * BRBD_NV; \\\n"
+          "    for (int r_ = 0; r_ < len_; ++r_) { const int o_ = BRBD_CPOS[lo_ * BRBD_NV + r_]; oc[lo_ * BRBD_NV + r_] = o_ >= 0 ? colbuf[o_] : BRBD_C(0.0); } \\\n"
+          "    for (int o_ = 0; o_ < BRBD_GNNZ[lo_]; ++o_) oc[BRBD_NV * BRBD_NV + BRBD_GBASE[lo_] + o_] = colbuf[o_]; } while (0)\n";
+    os << "extern \"C\" void brbd_gen_crba_host(const real * qc, const real * vc, const real * xc, real * oc, real * rec, real * park)\n{\n"
+          "  real colbuf[" << (pat->maxrow | 1) << "];\n";
+    os << body << "}\n";
+    return os.str();
+  }
   if (std::string(name) == "crba")
   { // matrix output: BRBD_OUT0 fills the staging row of the current column, BRBD_FLUSH copies it into column `col` of oc
     os << "#undef BRBD_OUT0\n#define BRBD_OUT0(row, val) colbuf[(row)] = (val)\n#define BRBD_COLBEGIN(col)\n#define BRBD_CLEAR(row) colbuf[(row)] = BRBD_C(0.0)\n"
           "#define BRBD_FLUSH(cc) for (int r_ = 0; r_ < BRBD_NV; ++r_) oc[((cc) & 0xffff) * BRBD_NV + r_] = colbuf[r_]\n";
     os << "extern \"C\" void brbd_gen_crba_host(const real * qc, const real * vc, const real * xc, real * oc, real * rec, real * park)\n{\n"
-          "  real colbuf[BRBD_NV];\n  for (int r_ = 0; r_ < BRBD_NV; ++r_) colbuf[r_] = BRBD_C(0.0);\n";
+          "  static real colbuf[BRBD_NV]; // keeps the last column of the previous call, as a lane's staging row does from round to round\n";
     os << body << "}\n";
     return os.str();
   }
@@ -443,6 +554,11 @@ std::string wrap_host(const std::string & body, const char * name, bool fp32, co
   return os.str();
 }
 } // namespace
+
+namespace brbd
+{
+int crba_pattern_nnz(const brbd_model & m) { return cg::crba_pattern(m.pd, 1).nnz; }
+} // namespace brbd
 
 extern "C" {
 
@@ -461,10 +577,20 @@ brbd_status brbd_codegen_source(const brbd_model * m, int algo, int flags, char 
   if (flags & BRBD_GEN_HOST) crba_nbuf = 1;
   // CRBA: adjacent columns per flush (see trace_crba); the host variant and the TMA variant take one column at a time
   int crba_group = (flags >> 24) & 0x1f ? (flags >> 24) & 0x1f : 1;
-  if (flags & BRBD_GEN_HOST) crba_group = 1;
+  if ((flags & BRBD_GEN_HOST) && !(flags & BRBD_GEN_CRBA_COMPACT)) crba_group = 1;
+  // CRBA, compact staging: only the entries of the structural pattern are staged (see CrbaPattern); one staging tile per warp
+  const bool crba_compact = algo == BRBD_GEN_CRBA && (flags & BRBD_GEN_CRBA_COMPACT) != 0;
+  // (the flags' group field then counts ENTRIES per group, in units of 8, instead of columns)
+  int crba_budget = 0;
+  if (crba_compact) { crba_nbuf = 1; crba_budget = 8 * ((flags >> 24) & 0x1f ? (flags >> 24) & 0x1f : 1); crba_group = 31; }
+  cg::CrbaPattern pat;
+  if (crba_compact) pat = cg::crba_pattern(m->pd, crba_group, crba_budget);
+  // CRBA, bulk-copy variant: `group` adjacent columns per lane and copy, rotating over bits 29..30 (+1) staging rows
+  const bool crba_bulk = algo == BRBD_GEN_CRBA && !crba_compact && (flags & BRBD_GEN_CRBA_BULK) != 0 && !(flags & BRBD_GEN_HOST);
+  if (crba_bulk) crba_nbuf = ((flags >> 29) & 3) + 1;
   cg::Tracer T(m->pd, (flags & BRBD_GEN_EXPLICIT_SLOTS) != 0);
   if (algo == BRBD_GEN_ABA) cg::trace_aba(T);
-  else if (algo == BRBD_GEN_CRBA) cg::trace_crba(T, crba_nbuf, crba_group);
+  else if (algo == BRBD_GEN_CRBA) cg::trace_crba(T, crba_nbuf, crba_group, crba_compact, crba_budget);
   else if (algo == BRBD_GEN_RNEA_DERIVATIVES) cg::trace_rnea_derivatives(T);
   else if (algo == BRBD_GEN_ABA_DERIVATIVES) cg::trace_aba_derivatives(T);
   else cg::trace_rnea(T);
@@ -499,9 +625,10 @@ brbd_status brbd_codegen_source(const brbd_model * m, int algo, int flags, char 
   }
   const std::string src = (algo >= BRBD_GEN_RNEA_DERIVATIVES && !(flags & BRBD_GEN_HOST))
                             ? wrap_device_derivs(body, algo_name(algo), fp32, nt, K.definition("__constant__"), m->pd.nv, derivs_staged)
+                            : crba_bulk ? wrap_device_crba_bulk(body, fp32, nt, m->pd.nv, K.definition("__constant__"), crba_nbuf, crba_group)
                             : (algo == BRBD_GEN_CRBA && !(flags & BRBD_GEN_HOST))
-                            ? wrap_device_crba(body, fp32, st, nt, m->pd.nq, m->pd.nv, K.definition("__constant__"), crba_nbuf, crba_group)
-                            : (flags & BRBD_GEN_HOST) ? wrap_host(body, algo_name(algo), fp32, st, K.definition("static const"), m->pd.nv)
+                            ? wrap_device_crba(body, fp32, st, nt, m->pd.nq, m->pd.nv, K.definition("__constant__"), crba_nbuf, crba_group, crba_compact ? &pat : nullptr)
+                            : (flags & BRBD_GEN_HOST) ? wrap_host(body, algo_name(algo), fp32, st, K.definition("static const"), m->pd.nv, crba_compact ? &pat : nullptr)
                                                   : wrap_device(body, algo_name(algo), fp32, T.nrec, st, nt, minb, tmem_cols, m->pd.nq, m->pd.nv, copies,
                                                                 direct_io, K.definition("__constant__"));
   char * buf = (char *)std::malloc(src.size() + 1);
@@ -516,11 +643,29 @@ brbd_status brbd_codegen_source(const brbd_model * m, int algo, int flags, char 
     info->threads_per_block = nt;
     info->copies = copies;
     if (algo >= BRBD_GEN_RNEA_DERIVATIVES) info->dynamic_smem_bytes = derivs_staged ? (int32_t)(derivs_tile_bytes * (nt / 32)) : 0;
+    else if (crba_bulk)
+      info->dynamic_smem_bytes = (int32_t)((size_t)crba_nbuf * (nt / 32) * 32 * crba_bulk_pitch(m->pd.nv, crba_group, fp32) * (fp32 ? 4 : 8));
+    else if (algo == BRBD_GEN_CRBA && crba_compact) info->dynamic_smem_bytes = (int32_t)((size_t)(nt / 32) * 32 * (pat.maxrow | 1) * (fp32 ? 4 : 8));
     else if (algo == BRBD_GEN_CRBA) info->dynamic_smem_bytes = (int32_t)((size_t)crba_nbuf * (nt / 32) * 32 * (m->pd.nv * crba_group + 2) * (fp32 ? 4 : 8));
     else info->dynamic_smem_bytes = (int32_t)(((direct_io ? 0 : (size_t)(nt / 32) * 32 * ((m->pd.nq | 1) + 2 * (m->pd.nv | 1))) + (size_t)st.smem_slots * nt) * (fp32 ? 4 : 8));
   }
   return BRBD_OK;
 }
 void brbd_codegen_free(char * source) { std::free(source); }
+
+brbd_status brbd_model_crba_pattern(const brbd_model * m, int32_t * rows, int32_t * cols, int64_t capacity, int64_t * nnz)
+{
+  if (!m || !nnz) return fail(BRBD_EINVAL, "null argument");
+  const cg::CrbaPattern pat = cg::crba_pattern(m->pd, 1);
+  *nnz = pat.nnz;
+  if (!rows && !cols) return BRBD_OK; // size query
+  if (capacity < pat.nnz) return fail(BRBD_EINVAL, "crba pattern: capacity smaller than the number of structural non-zeros");
+  for (int k = 0; k < pat.nnz; ++k)
+  {
+    if (rows) rows[k] = pat.rows[k];
+    if (cols) cols[k] = pat.cols[k];
+  }
+  return BRBD_OK;
+}
 
 } // extern "C"

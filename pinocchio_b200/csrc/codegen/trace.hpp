@@ -675,7 +675,90 @@ inline void trace_rnea(Tracer & T)
 // `group`: up to that many ADJACENT columns (the unwind of a chain emits columns c, c - 1, c - 2, ...) share one flush, so that
 // the wrapper writes group * nv contiguous elements per configuration at a time instead of nv (DRAM page locality of the store
 // stream); staging offsets and flush ranges are then relative to the group's first column.
-inline void trace_crba(Tracer & T, int nbuf = 1, int group = 1)
+//
+// The structural pattern of the result (static: the dofs of the column's own joint and of its ancestors) and the column groups.
+// COMPACT staging keeps only the pattern's entries of a group in the staging row, in column-major order; the wrapper's flush
+// puts the zeros back from the `pos` table (dense result) or writes the rows as they are (packed result, brbd_crba_packed_batch:
+// entry k of a configuration = M[rows[k], cols[k]], column-major over the pattern whatever the grouping).
+struct CrbaPattern
+{
+  int nv = 0, nnz = 0, maxrow = 0;
+  std::vector<int> order;               // the columns in the order the sweep finishes them
+  std::vector<int> g_lo, g_hi, g_last;  // per column: first / last column of its group, "closes the group"
+  std::vector<int> pos;                 // [col * nv + row]: position inside the group's compact row, -1 outside the pattern
+  std::vector<int> gbase, gnnz;         // per group, indexed by its first column: packed index of its first entry, entries
+  std::vector<int> rows, cols;          // the packed order
+  std::vector<std::vector<char>> staged; // per group in the order the sweep closes them: the positions (column - lo) * nv + row it stages
+};
+// `budget` > 0: a group also closes before its pattern would exceed that many entries (compact staging: the rows of all groups
+// then have about the same length, which is what sizes the warp's staging tile)
+inline CrbaPattern crba_pattern(const ModelPOD<double> & M, int group, int budget = 0)
+{
+  CrbaPattern P;
+  const int nj = M.njoints, nv = M.nv;
+  const JointTopo topo(M);
+  P.nv = nv;
+  P.g_lo.assign(nv, 0); P.g_hi.assign(nv, 0); P.g_last.assign(nv, 0);
+  P.pos.assign((size_t)nv * nv, -1); P.gbase.assign(nv, 0); P.gnnz.assign(nv, 0);
+  for (int i = 1; i < nj; ++i)
+    for (int j = i; j != topo.stop[i]; j = M.parent[j])
+      for (int k = 0; k < M.nvj[j]; ++k) P.order.push_back(M.idx_v[j] + k);
+  // pattern of a column: the full diagonal block of its joint (M.block(idx_v, idx_v, nv, nvSubtree) = S^T F writes it whole)
+  // and the dofs of every ancestor
+  std::vector<char> nz((size_t)nv * nv, 0);
+  std::vector<int> colnnz(nv, 0);
+  for (int j = 1; j < nj; ++j)
+    for (int k = 0; k < M.nvj[j]; ++k)
+    {
+      const int col = M.idx_v[j] + k;
+      for (int kk = 0; kk < M.nvj[j]; ++kk) nz[(size_t)col * nv + M.idx_v[j] + kk] = 1;
+      for (int a = j; M.parent[a] > 0; a = M.parent[a])
+        for (int kk = 0; kk < M.nvj[M.parent[a]]; ++kk) nz[(size_t)col * nv + M.idx_v[M.parent[a]] + kk] = 1;
+      for (int r = 0; r < nv; ++r) colnnz[col] += nz[(size_t)col * nv + r];
+    }
+  for (size_t a = 0; a < P.order.size();)
+  {
+    int lo = P.order[a], hi = P.order[a], entries = colnnz[P.order[a]];
+    size_t b = a + 1;
+    while (b < P.order.size() && (int)(b - a) < group && (P.order[b] == lo - 1 || P.order[b] == hi + 1) &&
+           (budget <= 0 || entries + colnnz[P.order[b]] <= budget))
+    {
+      lo = std::min(lo, P.order[b]); hi = std::max(hi, P.order[b]);
+      entries += colnnz[P.order[b]];
+      ++b;
+    }
+    for (size_t c = a; c < b; ++c) { P.g_lo[P.order[c]] = lo; P.g_hi[P.order[c]] = hi; P.g_last[P.order[c]] = (c + 1 == b); }
+    a = b;
+  }
+  for (int c : P.order)
+    if (P.g_last[c])
+    {
+      std::vector<char> rows((size_t)nv * std::max(1, group), 0);
+      for (int cc = P.g_lo[c]; cc <= P.g_hi[c]; ++cc)
+        for (int r = 0; r < nv; ++r)
+          if (nz[(size_t)cc * nv + r]) rows[(size_t)(cc - P.g_lo[c]) * nv + r] = 1;
+      P.staged.push_back(rows);
+    }
+  for (int col = 0; col < nv;)
+  { // groups are disjoint runs of columns; walk them in column order: the packed order is column-major over the pattern
+    const int lo = P.g_lo[col], hi = P.g_hi[col];
+    int n = 0;
+    for (int c = lo; c <= hi; ++c)
+      for (int r = 0; r < nv; ++r)
+        if (nz[(size_t)c * nv + r])
+        {
+          P.pos[(size_t)c * nv + r] = n++;
+          P.rows.push_back(r); P.cols.push_back(c);
+        }
+    P.gbase[lo] = P.nnz; P.gnnz[lo] = n;
+    P.nnz += n;
+    P.maxrow = std::max(P.maxrow, n);
+    col = hi + 1;
+  }
+  return P;
+}
+
+inline void trace_crba(Tracer & T, int nbuf = 1, int group = 1, bool compact = false, int budget = 0)
 {
   const ModelPOD<double> & M = T.M;
   const int nj = M.njoints;
@@ -688,21 +771,15 @@ inline void trace_crba(Tracer & T, int nbuf = 1, int group = 1)
   std::vector<std::vector<char>> prev_rows(nbuf, std::vector<char>((size_t)M.nv * group, 0));
   int ncol = 0;
   // the column order is static: partition it into groups of adjacent columns before tracing
-  std::vector<int> order, g_lo(M.nv, 0), g_last(M.nv, 0), g_hi(M.nv, 0);
-  for (int i = 1; i < nj; ++i)
-    for (int j = i; j != topo.stop[i]; j = M.parent[j])
-      for (int k = 0; k < M.nvj[j]; ++k) order.push_back(M.idx_v[j] + k);
-  for (size_t a = 0; a < order.size();)
+  const CrbaPattern pat = crba_pattern(M, group, budget);
+  const std::vector<int> & g_lo = pat.g_lo, & g_hi = pat.g_hi, & g_last = pat.g_last;
+  // the body runs once per round of the persistent grid: when it starts again, the staging rows still hold the LAST nbuf groups
+  // of the previous configuration (in the first round they hold zeros and the clears are idle)
+  for (int k = 0; k < nbuf && !compact; ++k)
   {
-    int lo = order[a], hi = order[a];
-    size_t b = a + 1;
-    while (b < order.size() && (int)(b - a) < group && (order[b] == lo - 1 || order[b] == hi + 1))
-    {
-      lo = std::min(lo, order[b]); hi = std::max(hi, order[b]);
-      ++b;
-    }
-    for (size_t c = a; c < b; ++c) { g_lo[order[c]] = lo; g_hi[order[c]] = hi; g_last[order[c]] = (c + 1 == b); }
-    a = b;
+    const int n = (int)pat.staged.size();
+    const int g = ((n - nbuf + k) % n + n) % n;
+    if (n > 0) prev_rows[k] = pat.staged[g];
   }
   std::vector<char> cur_rows((size_t)M.nv * group, 0);
   bool group_open = false;
@@ -734,8 +811,9 @@ inline void trace_crba(Tracer & T, int nbuf = 1, int group = 1)
         if (!group_open)
         {
           T.colbegin(g_lo[col]);
-          for (int r = 0; r < M.nv * group; ++r)
-            if (prev_rows[ncol % nbuf][r]) T.clear(r);
+          if (!compact) // compact rows hold entries of the pattern only, every one of them rewritten
+            for (int r = 0; r < M.nv * group; ++r)
+              if (prev_rows[ncol % nbuf][r]) T.clear(r);
           std::fill(cur_rows.begin(), cur_rows.end(), 0);
           group_open = true;
         }
@@ -745,7 +823,7 @@ inline void trace_crba(Tracer & T, int nbuf = 1, int group = 1)
         { // the joint's own diagonal block (full, as M.block(idx_v, idx_v, nv, nvSubtree) = S^T F writes it)
           Sym val = dot6(S_col(tj, kk), f);
           if (kk == k) val += Sym(M.armature[col]);
-          T.output(OUT_MAIN, off + iv + kk, val);
+          T.output(OUT_MAIN, compact ? pat.pos[(size_t)col * M.nv + iv + kk] : off + iv + kk, val);
           rows[off + iv + kk] = 1;
         }
         for (int a = j; M.parent[a] > 0; a = M.parent[a])
@@ -754,7 +832,7 @@ inline void trace_crba(Tracer & T, int nbuf = 1, int group = 1)
           f = liMi_of(a).act(f); // into the parent's frame
           for (int kk = 0; kk < M.nvj[pa]; ++kk)
           {
-            T.output(OUT_MAIN, off + M.idx_v[pa] + kk, dot6(S_col(M.type[pa], kk), f));
+            T.output(OUT_MAIN, compact ? pat.pos[(size_t)col * M.nv + M.idx_v[pa] + kk] : off + M.idx_v[pa] + kk, dot6(S_col(M.type[pa], kk), f));
             rows[off + M.idx_v[pa] + kk] = 1;
           }
         }

@@ -86,6 +86,8 @@ struct GenKernel
   void * lib = nullptr;    // cudaLibrary_t
   void * kernel = nullptr; // cudaKernel_t
   void * kernel_tma = nullptr; // CRBA: the variant whose column blocks leave through TMA tensor stores
+  bool compact = false;        // CRBA: compact staging (dense and packed output modes, see codegen.cu)
+  int nnz = 0;                 // CRBA: entries of the structural pattern (rows of the packed result)
   int nt = 0, nrec = 0;
   size_t smem_bytes = 0;
 };
@@ -103,6 +105,7 @@ struct GenSet
 struct brbd_pool
 {
   brbd::GenSet gen[5][2]; // [BRBD_GEN_*][fp64, fp32]
+  brbd::GenKernel crba_packed[2]; // the generated CRBA with compact staging (brbd_crba_packed_batch), built at its first call
   int64_t gen_min_batch = 8192; // batches at least this large use a specialised kernel when there is one
   brbd_model model;
   std::vector<brbd::DeviceCtx> devs;
@@ -386,10 +389,23 @@ void release_generated(brbd_pool * p);
 template<class T>
 brbd_status launch_generated(brbd_pool * p, DeviceCtx & d, int algo, const T * q, int64_t ldq, const T * v, int64_t ldv, const T * x,
                              int64_t ldx, T * out, int64_t ldo, int64_t B);
+// packed CRBA through the generated kernel with compact staging (specialises CRBA first if need be)
+template<class T>
+brbd_status launch_crba_packed(brbd_pool * p, DeviceCtx & d, const T * q, int64_t ldq, T * P, int64_t ldP, int64_t B);
+int crba_pattern_nnz(const brbd_model & m);
 // generated computeRNEADerivatives / computeABADerivatives (small models): q, v, x -> three nv*nv blocks + an nv block
 template<class T>
 brbd_status launch_generated_derivs(brbd_pool * p, DeviceCtx & d, int algo, const T * q, int64_t ldq, const T * v, int64_t ldv, const T * x,
                                     int64_t ldx, T * o0, int64_t ld0, T * o1, int64_t ld1, T * o2, int64_t ld2, T * o3, int64_t ld3, int64_t B);
+// generated CRBA, bulk-copy variant: elements between the staging rows of two lanes for `group` columns (room for the alignment
+// shift, 16-byte aligned rows, an odd number of 16-byte units so that the lanes' row writes spread over the banks)
+inline int crba_bulk_pitch(int nv, int group, bool fp32)
+{
+  const int A = fp32 ? 4 : 2;
+  int pitch = (nv * group + (A - 1) + (A - 1)) / A * A;
+  if ((pitch / A) % 2 == 0) pitch += A;
+  return pitch;
+}
 template<class T> inline bool use_generated(const brbd_pool * p, int algo, int64_t B)
 {
   return p->gen[algo][sizeof(T) == 4 ? 1 : 0].nvar > 0 && B >= p->gen_min_batch;

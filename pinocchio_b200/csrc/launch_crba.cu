@@ -12,9 +12,9 @@ brbd_status launch_crba(brbd_pool * p, DeviceCtx & d, const T * q, int64_t ldq, 
   brbd_status st = BRBD_OK;
   const char * ver = std::getenv("BRBD_CRBA_V"); // "tmem" (LSU emitter), "dfs" (crba_dfs_kernel), "v1" (crba_kernel)
   if (ver && std::strcmp(ver, "v1") == 0) return launch_crba_v1<T>(p, d, q, ldq, Mout, ldM, B);
-  // the generated CRBA wins where the arithmetic matters (6-dof manipulator: 0.034 -> 0.016 ms at 65 536 configurations);
-  // from ~25 dofs on the column stores bound both kernels alike and the hand-written one is kept (BRBD_CRBA_V=gen forces it)
-  if ((!ver && use_generated<T>(p, BRBD_GEN_CRBA, B) && t.nv <= 24) || (ver && std::strncmp(ver, "gen", 3) == 0 && p->gen[BRBD_GEN_CRBA][sizeof(T) == 4 ? 1 : 0].nvar > 0))
+  // a pool specialised for its model runs the generated CRBA (launch_gen.cu): 6-dof manipulator 0.034 -> 0.016 ms, 35-dof
+  // humanoid 0.225 -> 0.160 ms at 65 536 configurations; BRBD_CRBA_V=gen forces it below the specialised minimum batch too
+  if ((!ver && use_generated<T>(p, BRBD_GEN_CRBA, B)) || (ver && std::strncmp(ver, "gen", 3) == 0 && p->gen[BRBD_GEN_CRBA][sizeof(T) == 4 ? 1 : 0].nvar > 0))
     return launch_generated<T>(p, d, BRBD_GEN_CRBA, q, ldq, (const T *)nullptr, 0, (const T *)nullptr, 0, Mout, ldM, B);
   // preferred: oYcrb / oMi stacks in tensor memory (<= 8 warps per CTA, one CTA per SM)
   if (!(ver && std::strcmp(ver, "dfs") == 0))

@@ -81,6 +81,11 @@ void release_generated(brbd_pool * p)
         if (g.var[k].lib) cudaLibraryUnload((cudaLibrary_t)g.var[k].lib);
       g = GenSet();
     }
+  for (int f = 0; f < 2; ++f)
+  {
+    if (p->crba_packed[f].lib) cudaLibraryUnload((cudaLibrary_t)p->crba_packed[f].lib);
+    p->crba_packed[f] = GenKernel();
+  }
 }
 
 namespace
@@ -88,23 +93,49 @@ namespace
 const char * kAlgoNames[] = {"rnea", "aba", "crba", "rnea_derivatives", "aba_derivatives"};
 
 // generate + compile + load one variant; BRBD_OK with k.kernel == nullptr when it does not fit the SM (too much shared memory)
-brbd_status build_variant(brbd_pool * p, int algo, bool fp32, int nt, bool direct, bool slots, GenKernel & k)
+// crba_mode (CRBA only): 0 = default (BRBD_GEN_CRBA_MODE or the built-in choice), 1 = compact staging (packed output)
+brbd_status build_variant(brbd_pool * p, int algo, bool fp32, int nt, bool direct, bool slots, GenKernel & k, int crba_mode = 0)
 {
   char * src = nullptr;
   brbd_codegen_info info;
   // CRBA: adjacent columns per flush — as many as keep a staging row under ~1.5 KB (the whole matrix of a 6-dof arm).
   // Measured on the 35-dof humanoid (profiles/r2_gen_crba_experiments.txt): 1 / 3 / 5 columns 4.11 / 3.00 / - ms at 2^20.
-  int group = 1;
+  int group = 1, nbuf = 1;
+  bool compact = false, bulk = false;
   if (algo == BRBD_GEN_CRBA)
   {
     const int nvm = p->model.pd.nv;
+    // how the columns leave (codegen.cu): "bulk" — every lane hands `group` adjacent columns of its configuration to the copy
+    // engine (asynchronous, one run of group * nv elements per copy); "lsu" — coalesced stores by the warp (+ the TMA
+    // tensor-store kernel for single columns); "compact" — only the structural pattern staged (the packed result).
+    // Measured (profiles/r2_crba_bulk_sweep.txt): the bulk variant is the faster the FEWER warps run and the MORE columns a copy
+    // takes — 3 warps per SM with one staging row per lane as long as shared memory allows (8 columns of a 35-dof humanoid):
+    // 65 536 configurations 0.225 -> 0.160 ms, 2^20: 3.13 -> 2.22 ms (73 % of the copy bandwidth); small models (a 6-dof arm's
+    // whole matrix is 288 bytes) stay with the warp's coalesced stores.
+    const char * mode = std::getenv("BRBD_GEN_CRBA_MODE");
+    bulk = mode ? std::strcmp(mode, "bulk") == 0 : nvm > 24;
+    compact = crba_mode == 1 || (mode && std::strcmp(mode, "compact") == 0);
+    if (compact) bulk = false;
     group = std::max(1, std::min(std::min(nvm, 31), 192 / std::max(1, nvm)));
-    if (const char * e = std::getenv("BRBD_GEN_CRBA_K")) group = std::max(1, std::min(31, std::atoi(e)));
+    if (bulk)
+    { // as many columns as the CTA's staging rows leave room for
+      group = 1;
+      while (group < std::min(nvm, 31) &&
+             (size_t)nt * crba_bulk_pitch(nvm, group + 1, fp32) * (fp32 ? 4 : 8) + 2048 <= (size_t)p->devs[0].max_smem_optin - 4096)
+        ++group;
+    }
+    if (compact) group = 8; // entries of the pattern per flush, in units of 8
+    if (crba_mode == 0)
+    {
+      if (const char * e = std::getenv("BRBD_GEN_CRBA_K")) group = std::max(1, std::min(31, std::atoi(e)));
+      if (const char * e = std::getenv("BRBD_GEN_CRBA_NBUF")) nbuf = std::max(1, std::min(4, std::atoi(e)));
+    }
   }
-  const int gflags = (direct ? BRBD_GEN_DIRECT_IO : 0) | (slots ? BRBD_GEN_EXPLICIT_SLOTS : 0) | (fp32 ? BRBD_GEN_FP32 : 0) | (nt << 8) | (1 << 20) | (group << 24);
+  const int gflags = (direct ? BRBD_GEN_DIRECT_IO : 0) | (slots ? BRBD_GEN_EXPLICIT_SLOTS : 0) | (fp32 ? BRBD_GEN_FP32 : 0) | (nt << 8) | (1 << 20) | (group << 24) |
+                     (compact ? BRBD_GEN_CRBA_COMPACT : 0) | (bulk ? (BRBD_GEN_CRBA_BULK | ((nbuf - 1) << 29)) : 0);
   brbd_status st = brbd_codegen_source(&p->model, algo, gflags, &src, &info);
   if (st != BRBD_OK) return st;
-  if ((size_t)info.dynamic_smem_bytes + 2048 > (size_t)p->devs[0].max_smem_optin)
+  if ((size_t)info.dynamic_smem_bytes + 2048 + (compact ? 2 * (size_t)p->model.pd.nv * p->model.pd.nv : 0) > (size_t)p->devs[0].max_smem_optin)
   {
     brbd_codegen_free(src);
     return BRBD_OK;
@@ -129,13 +160,15 @@ brbd_status build_variant(brbd_pool * p, int algo, bool fp32, int nt, bool direc
     kern_tma = nullptr;
     (void)cudaGetLastError();
   }
-  if (k.smem_bytes > 48 * 1024)
+  if (k.smem_bytes + 8 * 1024 > 48 * 1024) // (the compact CRBA also holds its position table, nv * nv shorts, in static shared memory)
     for (const DeviceCtx & d : p->devs)
     {
       CUDA_TRY(cudaKernelSetAttributeForDevice(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k.smem_bytes, d.dev));
       if (kern_tma) CUDA_TRY(cudaKernelSetAttributeForDevice(kern_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k.smem_bytes, d.dev));
     }
   k.kernel_tma = kern_tma;
+  k.compact = compact;
+  k.nnz = algo == BRBD_GEN_CRBA ? crba_pattern_nnz(p->model) : 0;
   k.lib = lib; k.kernel = kern; k.nt = nt; k.nrec = info.record_slots;
   return BRBD_OK;
 }
@@ -161,7 +194,7 @@ brbd_status specialize_one(brbd_pool * p, int algo, bool fp32, int flags)
     const int w = (int)std::min<size_t>(8, (220 * 1024) / tile_bytes);
     nts = {w >= 4 ? 32 * w : 256}; // fewer than 4 warps: no tiles, every lane stores its own results
   }
-  else if (algo == BRBD_GEN_CRBA) nts = {512, 384, 256, 128}; // small state (128 registers at 16 warps, no spills): one staging row per lane
+  else if (algo == BRBD_GEN_CRBA) nts = p->model.pd.nv > 24 ? std::vector<int>{96, 64, 32} : std::vector<int>{512, 384, 256, 128}; // see build_variant
   else if (direct) nts = {448, 512, 256};
   else
   {
@@ -222,6 +255,35 @@ brbd_status launch_generated(brbd_pool * p, DeviceCtx & d, int algo, const T * q
   p->launches += 1;
   return BRBD_OK;
 }
+template<class T>
+brbd_status launch_crba_packed(brbd_pool * p, DeviceCtx & d, const T * q, int64_t ldq, T * P, int64_t ldP, int64_t B)
+{
+  const bool fp32 = sizeof(T) == 4;
+  GenKernel & k = p->crba_packed[fp32 ? 1 : 0];
+  if (!k.kernel)
+  { // first call: generate + compile the compact-staging kernel, with as many warps as its staging rows leave room for
+    for (int nt : {480, 384, 256, 128, 64, 32})
+    {
+      brbd_status st = build_variant(p, BRBD_GEN_CRBA, fp32, nt, false, false, k, 1);
+      if (st != BRBD_OK) return st;
+      if (k.kernel) break;
+    }
+    if (!k.kernel) return fail(BRBD_EINVAL, "packed crba: the staging rows of the model's pattern do not fit the SM");
+  }
+  const int64_t ctas_needed = (B + k.nt - 1) / k.nt;
+  const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(ctas_needed, (int64_t)d.sm_count));
+  // the kernel's v / x / record arguments are unused by CRBA; ldx carries the output mode (1 = packed)
+  const T * nul = nullptr;
+  T * rec = nullptr;
+  long long ldq_ = ldq, zero = 0, one = 1, ldo_ = ldP, B_ = B;
+  void * args[] = {(void *)&q, &ldq_, (void *)&nul, &zero, (void *)&nul, &one, (void *)&P, &ldo_, (void *)&rec, &B_};
+  CUDA_TRY(cudaLaunchKernel((const void *)k.kernel, dim3(grid), dim3(k.nt), args, k.smem_bytes, d.s()));
+  p->launches += 1;
+  return BRBD_OK;
+}
+template brbd_status launch_crba_packed<double>(brbd_pool *, DeviceCtx &, const double *, int64_t, double *, int64_t, int64_t);
+template brbd_status launch_crba_packed<float>(brbd_pool *, DeviceCtx &, const float *, int64_t, float *, int64_t, int64_t);
+
 template<class T>
 brbd_status launch_generated_derivs(brbd_pool * p, DeviceCtx & d, int algo, const T * q, int64_t ldq, const T * v, int64_t ldv, const T * x,
                                     int64_t ldx, T * o0, int64_t ld0, T * o1, int64_t ld1, T * o2, int64_t ld2, T * o3, int64_t ld3, int64_t B)

@@ -129,6 +129,17 @@ class ModelPool:
         except EngineError as e:
             _raise(e)
 
+    def crbaPattern(self):
+        """(rows, cols) of the structural pattern of crba's result (brbd_model_crba_pattern): entry k of a packed column
+        (crbaPackedInParallel) is M[rows[k], cols[k]]; column-major; everything outside it is a structural zero."""
+        L = _capi.lib()
+        n = ctypes.c_int64()
+        _capi.check(L.brbd_model_crba_pattern(self._h_model, None, None, 0, ctypes.byref(n)))
+        rows, cols = np.zeros(n.value, dtype=np.int32), np.zeros(n.value, dtype=np.int32)
+        _capi.check(L.brbd_model_crba_pattern(self._h_model, rows.ctypes.data_as(ctypes.c_void_p), cols.ctypes.data_as(ctypes.c_void_p),
+                                              n.value, ctypes.byref(n)))
+        return rows, cols
+
     def specialized(self):
         from .codegen import ALGOS
         mask = int(_capi.lib().brbd_pool_specialized(self._h_pool))
@@ -358,6 +369,27 @@ def crbaInParallel(num_threads: int, pool: ModelPool, q, M=None, async_: bool = 
     if M is None:
         M = _alloc_like(q, nn, aq.cols)
     _call(pool, "brbd_crba_batch", [aq], [_describe(M, nn, "M", out=True)], async_)
+    return M
+
+
+def crbaPackedInParallel(num_threads: int, pool: ModelPool, q, P=None, async_: bool = False):
+    """P[:, i] = the entries of crba(model, q[:, i]) inside the structural pattern (pool.crbaPattern()), column-major:
+    (nnz x B).  Opt-in output format (brbd_crba_packed_batch): a third of the bytes of the dense block for a humanoid."""
+    _check_pool(num_threads, pool)
+    aq = _describe(q, pool.nq, "q")
+    nnz = len(pool.crbaPattern()[0])
+    if P is None:
+        P = _alloc_like(q, nnz, aq.cols)
+    _call(pool, "brbd_crba_packed_batch", [aq], [_describe(P, nnz, "P", out=True)], async_)
+    return P
+
+
+def expandPackedCrba(pool: ModelPool, P):
+    """Dense (nv*nv x B) block from a packed host block (numpy) — what a caller that wants data.M back does."""
+    rows, cols = pool.crbaPattern()
+    P = np.asarray(P)
+    M = np.zeros((pool.nv * pool.nv, P.shape[1]), dtype=P.dtype, order="F")
+    M[cols.astype(np.int64) * pool.nv + rows, :] = P
     return M
 
 

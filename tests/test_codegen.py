@@ -17,10 +17,10 @@ ALL = MODEL_NAMES + ["mixed", "double_ff", "unaligned", "humanoid_hands", "wheel
 EXTRA = make_extra_models()
 
 
-def build_host(model, algo, explicit_slots, tmp):
+def build_host(model, algo, explicit_slots, tmp, **kw):
     from pinocchio_b200.codegen import codegen_source
-    src, info = codegen_source(model, algo, explicit_slots=explicit_slots, host=True)
-    cpp = os.path.join(tmp, f"gen_{algo}_{int(explicit_slots)}.cpp")
+    src, info = codegen_source(model, algo, explicit_slots=explicit_slots, host=True, **kw)
+    cpp = os.path.join(tmp, f"gen_{algo}_{int(explicit_slots)}_{'_'.join(str(v) for v in kw.values())}.cpp")
     with open(cpp, "w") as fh:
         fh.write(src)
     so = cpp[:-4] + ".so"
@@ -66,6 +66,56 @@ def test_generated_program_matches_the_oracle(oracle_cls, name, explicit_slots):
             assert np.isfinite(got).all(), (name, "crba")  # every entry written, zeros outside the tree sparsity
             assert np.abs(got - ref).max() <= 1e-12 * max(1.0, np.abs(ref).max()), (name, "crba")
             assert not got[ref == 0].any() or np.abs(got[ref == 0]).max() < 1e-13
+
+
+def crba_pattern(model):
+    """The structural pattern through the C ABI (brbd_model_crba_pattern)."""
+    from pinocchio_b200 import _capi
+    L = _capi.lib()
+    fm, keep = _capi.make_flat(model.flat())
+    h = ctypes.c_void_p()
+    _capi.check(L.brbd_model_create(ctypes.byref(fm), ctypes.byref(h)))
+    try:
+        n = ctypes.c_int64()
+        _capi.check(L.brbd_model_crba_pattern(h, None, None, 0, ctypes.byref(n)))
+        rows, cols = np.zeros(n.value, dtype=np.int32), np.zeros(n.value, dtype=np.int32)
+        _capi.check(L.brbd_model_crba_pattern(h, rows.ctypes.data_as(ctypes.c_void_p), cols.ctypes.data_as(ctypes.c_void_p), n.value, ctypes.byref(n)))
+        with pytest.raises(_capi.EngineError):
+            _capi.check(L.brbd_model_crba_pattern(h, rows.ctypes.data_as(ctypes.c_void_p), None, n.value - 1, ctypes.byref(n)))
+        return rows, cols
+    finally:
+        L.brbd_model_destroy(h)
+
+
+@pytest.mark.parametrize("name", ALL)
+@pytest.mark.parametrize("group", [1, 3, 31])
+def test_generated_crba_compact_staging(oracle_cls, name, group):
+    """CRBA with compact staging: the staging row holds the entries of the structural pattern only; the flush expands it through
+    the position table (dense result) or writes it as it is (packed result, brbd_crba_packed_batch).  Both against the oracle,
+    and the pattern covers every non-zero of the oracle's matrix whatever the column grouping."""
+    model = EXTRA[name] if name in EXTRA else load_model(name)
+    orc = oracle_cls(model)
+    q, v, x = random_inputs(model, 4, 5)
+    rows, cols = crba_pattern(model)
+    nv, nnz = model.nv, len(rows)
+    key = cols.astype(np.int64) * nv + rows
+    assert (np.diff(key) > 0).all()  # column-major, no duplicates
+    from conftest import structural_mask
+    assert np.array_equal(np.flatnonzero(structural_mask(model)), key)  # = the tree sparsity of crba.hxx:94-95
+    ref = orc.crba(q, world=True)
+    outside = np.ones(nv * nv, dtype=bool)
+    outside[key] = False
+    assert not ref[outside].any()  # the pattern covers the oracle's non-zeros
+    with tempfile.TemporaryDirectory() as tmp:
+        fn, info = build_host(model, "crba", False, tmp, crba_compact=True, crba_group=group)
+        got = run_host(fn, info, model, q, v, x, nout=nv * nv + nnz)
+    assert np.isfinite(got).all(), name  # every dense and packed entry written
+    dense, packed = got[: nv * nv], got[nv * nv:]
+    tol = 1e-12 * max(1.0, np.abs(ref).max())
+    assert np.abs(dense - ref).max() <= tol, (name, np.abs(dense - ref).max())
+    assert not dense[outside].any()  # exact zeros outside the pattern
+    assert np.abs(packed - ref[key]).max() <= tol, name
+    assert np.array_equal(packed, dense[key])  # the two output modes carry the same values
 
 
 def test_constant_folding_shrinks_the_program(oracle_cls):

@@ -421,3 +421,75 @@ def test_specialized_derivative_kernels(ctx, name):
             assert_close(to_host(g), r, rtol=1e-10, atol=1e-12 + 1e-10 * np.abs(r).max(axis=0, keepdims=True), what=f"{nm}[generated] {name} B={B}")
         assert pool.launch_count() == n0 + 2
     pool.close()
+
+
+@pytest.mark.parametrize("name", ["simple_humanoid_ff", "talos_reduced_ff", "humanoid_random", "mixed", "humanoid_hands"])
+@pytest.mark.parametrize("mode", ["bulk", "lsu", "compact"])
+def test_generated_crba_store_modes(ctx, name, mode, monkeypatch):
+    """The three ways the generated CRBA writes M (codegen.cu): one asynchronous bulk copy per lane and column group (the default
+    above 24 dofs), coalesced stores by the warp, compact staging of the structural pattern.  Every caller layout: dense and
+    padded leading dimensions of either parity, a base pointer 8 (4) bytes off a 16-byte boundary — the bulk copies' alignment
+    shift — FP64 and FP32, ragged batches, a canary around the block."""
+    import torch
+    import pinocchio_b200 as pb
+    model, _, orc = ctx(name)
+    nv, nn = model.nv, model.nv * model.nv
+    monkeypatch.setenv("BRBD_GEN_CRBA_MODE", mode)
+    monkeypatch.setenv("BRBD_CRBA_V", "gen")
+    mask = structural_mask(model)
+    for fp32 in (False, True):
+        pool = pb.ModelPool(model, [0])
+        pool.specialize(["crba"], fp32=fp32, min_batch=1)
+        dt = torch.float32 if fp32 else torch.float64
+        for B, pad, shift in ((1, 0, 0), (33, 1, 1), (148 * 96 + 45, 0, 0), (1000, 2, 3), (517, 3, 1)):
+            q, _, _ = random_inputs(model, B, 5 + B)
+            refM = orc.crba(q, world=True)
+            tq = torch.from_numpy(np.ascontiguousarray(q.T)).to(dt).cuda()
+            flat = torch.full(((B + 1) * (nn + pad) + 8,), -7.0, dtype=dt, device="cuda")
+            blk = flat[shift:shift + B * (nn + pad)].view(B, nn + pad)
+            pb.crbaInParallel(1, pool, tq, blk[:, :nn])
+            torch.cuda.synchronize()
+            got = flat.cpu().numpy().astype(np.float64)
+            G = got[shift:shift + B * (nn + pad)].reshape(B, nn + pad)
+            what = f"crba[generated, {mode}, {'fp32' if fp32 else 'fp64'}] {name} B={B} pad={pad} shift={shift}"
+            if fp32:
+                assert np.abs(G[:, :nn].T - refM).max() <= 2e-5 * np.abs(refM).max(), what
+            else:
+                assert_close(G[:, :nn].T, refM, rtol=1e-10, atol=1e-12 + 1e-12 * np.abs(refM).max(axis=0, keepdims=True), what=what)
+            assert not G[:, :nn].T[~mask].any(), what + ": entries outside the tree sparsity must be exact zeros"
+            assert (G[:, nn:] == -7.0).all() and (got[:shift] == -7.0).all() and (got[shift + B * (nn + pad):] == -7.0).all(), what + ": wrote outside the block"
+        pool.close()
+
+
+@pytest.mark.parametrize("name", ["simple_humanoid_ff", "talos_reduced_ff", "manipulator", "mixed", "double_ff", "wheeled"])
+def test_crba_packed(ctx, name):
+    """brbd_crba_packed_batch: the entries of crba's result inside the structural pattern (brbd_model_crba_pattern), column-major;
+    device and host pointers, padded leading dimension, FP32; expanding it gives the dense result of brbd_crba_batch exactly."""
+    import torch
+    import pinocchio_b200 as pb
+    model, _, orc = ctx(name)
+    nv = model.nv
+    pool = pb.ModelPool(model, [0])
+    rows, cols = pool.crbaPattern()
+    nnz = len(rows)
+    key = cols.astype(np.int64) * nv + rows
+    assert np.array_equal(np.flatnonzero(structural_mask(model)), key)  # the pattern is the tree sparsity of crba.hxx:94-95, column-major
+    for B, pad in ((1, 0), (300, 5), (148 * 480 + 99, 0)):
+        q, _, _ = random_inputs(model, B, 17 + B)
+        refM = orc.crba(q, world=True)
+        assert not np.delete(refM, key, axis=0).any()  # and covers every non-zero of the reference
+        tq, = to_dev(q)
+        big = torch.full((B + 1, nnz + pad), -7.0, dtype=torch.float64, device="cuda")
+        pb.crbaPackedInParallel(1, pool, tq, big[:B, :nnz])
+        torch.cuda.synchronize()
+        got = big.cpu().numpy()
+        assert_close(got[:B, :nnz].T, refM[key], rtol=1e-10, atol=1e-12 + 1e-12 * np.abs(refM).max(axis=0, keepdims=True), what=f"crba packed {name} B={B}")
+        assert (got[:B, nnz:] == -7.0).all() and (got[B] == -7.0).all(), "wrote outside the caller's block"
+        if B <= 300:
+            Ph = pb.crbaPackedInParallel(1, pool, q)  # host pointers
+            assert np.array_equal(Ph, got[:B, :nnz].T)
+            dense = pb.crbaInParallel(1, pool, q)
+            assert_close(pb.expandPackedCrba(pool, Ph), dense, rtol=1e-12, atol=1e-13 * np.abs(dense).max(), what=f"expand(packed) vs dense {name}")
+            P32 = pb.crbaPackedInParallel(1, pool, np.asfortranarray(q.astype(np.float32)))
+            assert P32.dtype == np.float32 and np.abs(P32 - refM[key]).max() <= 2e-5 * np.abs(refM).max()
+    pool.close()
