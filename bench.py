@@ -415,6 +415,41 @@ def main():
                "note": "pinned host buffers -> brbd_*_batch(BRBD_PTR_HOST): H2D + kernels + D2H, wall clock, max over ranks"
                        + ("" if Be == B else f"; host blocks capped at {Be} configurations per GPU (6 GB of pinned memory)")}
 
+        # the same step with the opt-in packed CRBA output (brbd_crba_packed_batch: only the entries inside the structural
+        # pattern travel; a side figure — the headline `e2e` above is the reference's dense layout)
+        if "crba" in algos and "crba" in spec:
+            try:
+                nnz = len(pool.crbaPattern()[0])
+                hp = torch.empty((Be, nnz), dtype=torch.float64).pin_memory()
+                hpv = hp.numpy().T
+
+                def packed_step():
+                    acc = 0.0
+                    for k in algos:
+                        o = hviews[k]
+                        if k == "rnea":
+                            pb.rneaInParallel(1, pool, hq, hv, hx, o[0])
+                        elif k == "aba":
+                            pb.abaInParallel(1, pool, hq, hv, hx, o[0])
+                        else:
+                            pb.crbaPackedInParallel(1, pool, hq, hpv)
+                            o = [hpv]
+                        acc += float(o[0][0, 0])
+                    return acc
+
+                packed_step()
+                barrier()
+                t0 = time.perf_counter()
+                for _ in range(e2e_steps):
+                    packed_step()
+                barrier()
+                ps = max_over_ranks([time.perf_counter() - t0])[0]
+                e2e["packed_crba"] = {"value": len(algos) * Be * world * e2e_steps / ps, "unit": "evals/s",
+                                      "d2h_bytes_per_step": int(Be * (per_cfg_out - 8 * (nv * nv - nnz))),
+                                      "note": f"same step, CRBA through brbd_crba_packed_batch ({nnz} of {nv * nv} entries per configuration)"}
+            except Exception as e:  # a side figure must not cost the line
+                print(f"bench.py: packed CRBA leg failed ({e})", file=sys.stderr)
+
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()

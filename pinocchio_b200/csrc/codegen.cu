@@ -433,13 +433,16 @@ std::string wrap_device_crba_bulk(const std::string & body, bool fp32, int nt, i
 }
 
 // Device wrapper of the generated derivative kernels (small models): every lane reads its own q / v / x column.  Results:
-// `staged` — each lane fills its row of three per-warp tiles (32 x nv^2, odd pitch) in shared memory and the warp writes them
-// out with coalesced stores (906 MB per algorithm at 2^20 x manipulator: strided 8-byte stores were the whole run time);
-// otherwise every lane stores its own results directly.
+// `staged` — each lane fills its rows of three per-warp tiles (32 x nv^2) in shared memory and hands every row to the copy
+// engine with one cp.async.bulk when the configuration is finished: asynchronous, lane-local, one run of nv^2 elements per copy
+// (the scheme of wrap_device_crba_bulk, including the alignment shift; first version: the warp wrote the tiles with coalesced
+// stores — 906 MB per algorithm at 2^20 x manipulator at the 2.2 TB/s that pattern reaches from 8 warps,
+// profiles/r2_bulk_store_bw.txt); otherwise every lane stores its own results directly.
 std::string wrap_device_derivs(const std::string & body, const char * name, bool fp32, int nt, const std::string & ktable, int nv, bool staged)
 {
   std::ostringstream os;
-  const int nn = nv * nv, pitch = nn | 1, vp = nv | 1, tile = 32 * (3 * pitch + vp);
+  const int nn = nv * nv, pitch = crba_bulk_pitch(nn, 1, fp32), vp = crba_bulk_pitch(nv, 1, fp32), tile = 32 * (3 * pitch + vp);
+  const int A = fp32 ? 4 : 2, es = fp32 ? 4 : 8;
   os << "// generated by pinocchio_b200 codegen: " << name << (fp32 ? " (FP32)" : " (FP64)") << "\n";
   os << math_macros(fp32) << "#undef BRBD_SINCOS\n" << device_sincos(fp32) << ktable;
   os << (fp32 ? "__device__ __forceinline__ real ld_in(const real * p) { real v; asm volatile(\"ld.global.nc.f32 %0, [%1];\" : \"=f\"(v) : \"l\"(p)); return v; }\n"
@@ -447,12 +450,20 @@ std::string wrap_device_derivs(const std::string & body, const char * name, bool
   os << "#define BRBD_IN0(k) ld_in(tq + (k))\n#define BRBD_IN1(k) ld_in(tv + (k))\n#define BRBD_IN2(k) ld_in(tx + (k))\n#define BRBD_SYNC()\n";
   if (staged)
   {
-    os << "__device__ __noinline__ void tile_out(real * __restrict__ g, long long ld, const real * t, int pitch, int rows, int nvalid, int lane)\n{\n"
-          "  if (ld == rows && nvalid == 32)\n  {\n    int c = 0, r = lane;\n    while (r >= rows) { r -= rows; ++c; }\n"
-          "#pragma unroll 4\n    for (int k = lane; k < 32 * rows; k += 32)\n    {\n      g[k] = t[c * pitch + r];\n      r += 32;\n"
-          "      while (r >= rows) { r -= rows; ++c; }\n    }\n  }\n  else\n"
-          "    for (int c = 0; c < nvalid; ++c)\n      for (int r = lane; r < rows; r += 32) g[c * ld + r] = t[c * pitch + r];\n}\n";
-    for (int k = 0; k < 4; ++k) os << "#define BRBD_OUT" << k << "(i, val) s" << k << "[(i)] = (val)\n";
+    // row[sh + e] -> g[e], e in [0, L): plain stores for the unaligned head / tail, one bulk copy for the rest
+    os << "__device__ __forceinline__ int misalign(const real * g) { return (int)((reinterpret_cast<unsigned long long>(g) / " << es << "ull) & " << A - 1 << "ull); }\n";
+    os << "__device__ __forceinline__ void bulk_flush(const real * row, int sh, real * __restrict__ g, int L, bool live)\n{\n"
+          "  const int e0 = (" << A << " - sh) & " << A - 1 << ", n = (L - e0) & ~" << A - 1 << ";\n"
+          "  if (live)\n  {\n"
+          "    for (int e = 0; e < e0; ++e) g[e] = row[sh + e];\n"
+          "    for (int e = e0 + n; e < L; ++e) g[e] = row[sh + e];\n"
+          "    asm volatile(\"fence.proxy.async.shared::cta;\" ::: \"memory\");\n"
+          "    if (n > 0)\n"
+          "      asm volatile(\"cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\" ::\"l\"(g + e0), \"r\"((unsigned)__cvta_generic_to_shared(row + sh + e0)),\n"
+          "                   \"r\"(n * " << es << ") : \"memory\");\n"
+          "  }\n"
+          "  asm volatile(\"cp.async.bulk.commit_group;\" ::: \"memory\");\n}\n";
+    for (int k = 0; k < 4; ++k) os << "#define BRBD_OUT" << k << "(i, val) s" << k << "[sh" << k << " + (i)] = (val)\n";
   }
   else
     for (int k = 0; k < 4; ++k) os << "#define BRBD_OUT" << k << "(i, val) do { if (live" << (k == 3 ? " && o3" : "") << ") p" << k << "[(i)] = (val); } while (0)\n";
@@ -462,7 +473,7 @@ std::string wrap_device_derivs(const std::string & body, const char * name, bool
   os << "  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;\n";
   if (staged)
   {
-    os << "  extern __shared__ __align__(16) unsigned char smem_raw[];\n  real * tile = reinterpret_cast<real *>(smem_raw) + warp * " << tile << ";\n";
+    os << "  extern __shared__ __align__(128) unsigned char smem_raw[];\n  real * tile = reinterpret_cast<real *>(smem_raw) + warp * " << tile << ";\n";
     os << "  real * s0 = tile + lane * " << pitch << ";\n  real * s1 = s0 + " << 32 * pitch << ";\n  real * s2 = s1 + " << 32 * pitch << ";\n"
           "  real * s3 = tile + " << 3 * 32 * pitch << " + lane * " << vp << ";\n";
   }
@@ -471,20 +482,20 @@ std::string wrap_device_derivs(const std::string & body, const char * name, bool
   os << "    const long long cfg_raw = cfg0 + lane;\n    const bool live = cfg_raw < B;\n    const long long cfg = live ? cfg_raw : B - 1;\n";
   os << "    const int nvalid = (int)(B - cfg0 < 32 ? B - cfg0 : 32);\n";
   os << "    const real * __restrict__ tq = q + cfg * ldq;\n    const real * __restrict__ tv = v + cfg * ldv;\n    const real * __restrict__ tx = x + cfg * ldx;\n";
-  if (!staged)
-    os << "    real * __restrict__ p0 = o0 + cfg * ld0;\n    real * __restrict__ p1 = o1 + cfg * ld1;\n    real * __restrict__ p2 = o2 + cfg * ld2;\n"
-          "    real * __restrict__ p3 = o3 ? o3 + cfg * ld3 : o3;\n";
+  os << "    real * __restrict__ p0 = o0 + cfg * ld0;\n    real * __restrict__ p1 = o1 + cfg * ld1;\n    real * __restrict__ p2 = o2 + cfg * ld2;\n"
+        "    real * __restrict__ p3 = o3 ? o3 + cfg * ld3 : o3;\n";
+  if (staged) // the rows are free once the copy engine has read the previous configuration out of them
+    os << "    asm volatile(\"cp.async.bulk.wait_group.read 0;\" ::: \"memory\");\n"
+          "    const int sh0 = misalign(p0), sh1 = misalign(p1), sh2 = misalign(p2), sh3 = misalign(p3);\n";
   os << "    {\n" << body << "    }\n";
   if (staged)
   {
-    os << "    __syncwarp();\n";
-    os << "    tile_out(o0 + cfg0 * ld0, ld0, tile, " << pitch << ", " << nn << ", nvalid, lane);\n";
-    os << "    tile_out(o1 + cfg0 * ld1, ld1, tile + " << 32 * pitch << ", " << pitch << ", " << nn << ", nvalid, lane);\n";
-    os << "    tile_out(o2 + cfg0 * ld2, ld2, tile + " << 2 * 32 * pitch << ", " << pitch << ", " << nn << ", nvalid, lane);\n";
-    os << "    if (o3) tile_out(o3 + cfg0 * ld3, ld3, tile + " << 3 * 32 * pitch << ", " << vp << ", " << nv << ", nvalid, lane);\n";
-    os << "    __syncwarp();\n";
+    os << "    bulk_flush(s0, sh0, p0, " << nn << ", live);\n    bulk_flush(s1, sh1, p1, " << nn << ", live);\n    bulk_flush(s2, sh2, p2, " << nn << ", live);\n";
+    os << "    if (o3) bulk_flush(s3, sh3, p3, " << nv << ", live);\n";
   }
-  os << "    (void)live; (void)nvalid;\n  }\n}\n";
+  os << "    (void)live; (void)nvalid; (void)p0; (void)p1; (void)p2; (void)p3;\n  }\n";
+  if (staged) os << "  asm volatile(\"cp.async.bulk.wait_group 0;\" ::: \"memory\");\n";
+  os << "}\n";
   return os.str();
 }
 
@@ -596,7 +607,8 @@ brbd_status brbd_codegen_source(const brbd_model * m, int algo, int flags, char 
   else cg::trace_rnea(T);
   cg::EmitStats st;
   // derivative programs: results through per-warp tiles when a warp's three nv^2 blocks fit beside those of its CTA's other warps
-  const size_t derivs_tile_bytes = (size_t)32 * (3 * ((m->pd.nv * m->pd.nv) | 1) + (m->pd.nv | 1)) * ((flags & BRBD_GEN_FP32) ? 4 : 8);
+  const size_t derivs_tile_bytes = (size_t)32 * (3 * crba_bulk_pitch(m->pd.nv * m->pd.nv, 1, (flags & BRBD_GEN_FP32) != 0) + crba_bulk_pitch(m->pd.nv, 1, (flags & BRBD_GEN_FP32) != 0)) *
+                                   ((flags & BRBD_GEN_FP32) ? 4 : 8);
   const bool derivs_staged = derivs_tile_bytes * ((((flags >> 8) & 0xfff) ? ((flags >> 8) & 0xfff) : 128) / 32) <= 220 * 1024;
   const int nt = (flags >> 8) & 0xfff ? (flags >> 8) & 0xfff : 128;
   const int minb = (flags >> 20) & 0xf ? (flags >> 20) & 0xf : 1;

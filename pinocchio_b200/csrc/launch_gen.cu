@@ -190,7 +190,7 @@ brbd_status specialize_one(brbd_pool * p, int algo, bool fp32, int flags)
   else if (algo >= BRBD_GEN_RNEA_DERIVATIVES)
   { // every result stays alive (registers limit the warps); as many warps (<= 8) as the per-warp result tiles leave room for
     const int nvm = p->model.pd.nv;
-    const size_t tile_bytes = (size_t)32 * (3 * ((nvm * nvm) | 1) + (nvm | 1)) * (fp32 ? 4 : 8);
+    const size_t tile_bytes = (size_t)32 * (3 * crba_bulk_pitch(nvm * nvm, 1, fp32) + crba_bulk_pitch(nvm, 1, fp32)) * (fp32 ? 4 : 8);
     const int w = (int)std::min<size_t>(8, (220 * 1024) / tile_bytes);
     nts = {w >= 4 ? 32 * w : 256}; // fewer than 4 warps: no tiles, every lane stores its own results
   }

@@ -1,13 +1,57 @@
-// launch_minverse.cu — launch of batched computeMinverse (algorithm/aba.hpp:106): MODE 1 of the cooperative computeABADerivatives kernel
+// launch_minverse.cu — launch of batched computeMinverse (algorithm/aba.hpp:106): the batched CRBA followed by the dense
+// Cholesky inversion of minv_chol.cuh (default), or MODE 1 of the cooperative computeABADerivatives kernel (BRBD_MINV_V=coop)
 #include "host_ctx.hpp"
+#include "minv_chol.cuh"
 
 namespace brbd
 {
 // computeMinverse: the Minv phases of the warp-cooperative computeABADerivatives kernel (MODE 1)
+// M (crba, whatever kernel the pool runs for it) into the device's aux buffer, chunk by chunk, then M^-1 by Cholesky
+template<class T>
+brbd_status launch_minverse_chol(brbd_pool * p, DeviceCtx & d, const T * q, int64_t ldq, T * Minv, int64_t ldM, int64_t B)
+{
+  const int nv = p->model.pd.nv;
+  const int64_t nn = (int64_t)nv * nv;
+  const int G = coop_group_size(nv);
+  const MinvCholLayout L = minv_chol_layout(nv);
+  const size_t per_warp = (size_t)L.per_group * sizeof(T) * (32 / G);
+  int warps = (int)std::max<size_t>(1, std::min<size_t>(16, ((size_t)d.max_smem_optin - 1024) / per_warp));
+  // small batches: spread the configurations over all SMs
+  while (warps > 1 && (int64_t)(warps - 1) * (32 / G) * d.sm_count >= B) --warps;
+  const size_t dyn = (size_t)warps * per_warp;
+  const int64_t chunk = std::min<int64_t>(B, 32768); // M of a chunk: 321 MB for a 35-dof humanoid in FP64
+  brbd_status st = ensure_aux(d, (size_t)chunk * nn * sizeof(T));
+  if (st != BRBD_OK) return st;
+  T * Mbuf = (T *)d.aux;
+  for (int64_t c0 = 0; c0 < B; c0 += chunk)
+  {
+    const int64_t bc = std::min<int64_t>(chunk, B - c0);
+    st = launch_crba<T>(p, d, q + c0 * ldq, ldq, Mbuf, nn, bc);
+    if (st != BRBD_OK) return st;
+    const int64_t per_cta = (int64_t)warps * (32 / G);
+    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((bc + per_cta - 1) / per_cta, (int64_t)d.sm_count));
+#define BRBD_LAUNCH_CHOL(GG, RR)                                                                                 \
+  {                                                                                                              \
+    st = set_smem(minv_chol_kernel<T, GG, RR>, dyn);                                                             \
+    if (st != BRBD_OK) return st;                                                                                \
+    minv_chol_kernel<T, GG, RR><<<grid, warps * 32, dyn, d.s()>>>(Mbuf, nn, Minv + c0 * ldM, ldM, nv, L, bc);    \
+  }
+    if (G == 8) BRBD_LAUNCH_CHOL(8, 1)
+    else if (G == 16) BRBD_LAUNCH_CHOL(16, 1)
+    else if (nv <= 32) BRBD_LAUNCH_CHOL(32, 1)
+    else BRBD_LAUNCH_CHOL(32, 2)
+#undef BRBD_LAUNCH_CHOL
+    p->launches += 1;
+    CUDA_TRY(cudaGetLastError());
+  }
+  return BRBD_OK;
+}
+
 template<class T>
 brbd_status launch_minverse(brbd_pool * p, DeviceCtx & d, const T * q, int64_t ldq, T * Minv, int64_t ldM, int64_t B)
 {
   const ModelPOD<double> & M = p->model.pd;
+  if (!forced_path("BRBD_MINV_V", "coop")) return launch_minverse_chol<T>(p, d, q, ldq, Minv, ldM, B);
   const int G = coop_group_size(M.nv);
   const AbaCoopLayout L = aba_coop_layout(M.nq, M.nv, M.njoints, G);
   const size_t static_bytes = sizeof(ModelPOD<T>) + sizeof(CoopTables) + 1024;

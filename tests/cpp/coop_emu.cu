@@ -33,6 +33,7 @@ __host__ __device__ inline void brbd_emu_syncwarp()
 
 #include "../../pinocchio_b200/csrc/model_build.hpp"
 #include "../../pinocchio_b200/csrc/aba_deriv_coop.cuh"
+#include "../../pinocchio_b200/csrc/minv_chol.cuh"
 
 using namespace brbd;
 
@@ -125,11 +126,34 @@ void emu_rnea(const ModelPOD<double> & m, const CoopTables & tb, const double * 
     free(base);
   }
 }
+// computeMinverse by Cholesky (minv_chol.cuh): Min = the upper triangles of crba, column-major, one matrix per column
+template<int G, int R>
+void emu_minv_chol(int nv, const double * Min, double * out, int64_t B)
+{
+  const MinvCholLayout L = minv_chol_layout(nv);
+  const int64_t nn = (int64_t)nv * nv;
+  for (int64_t cfg = 0; cfg < B; ++cfg)
+  {
+    double * base = alloc_region((size_t)L.per_group);
+    run_lanes(G, [&](int gl) { minv_chol_config<double, G, R>(nv, L, base, gl, Min + cfg * nn, out + cfg * nn, true); });
+    free(base);
+  }
+}
 } // namespace
 
 extern "C" {
 
 const char * emu_last_error(void) { return g_err.c_str(); }
+
+int emu_minv_chol_run(int nv, const double * Min, double * out, int64_t B)
+{
+  if (nv <= 8) emu_minv_chol<8, 1>(nv, Min, out, B);
+  else if (nv <= 16) emu_minv_chol<16, 1>(nv, Min, out, B);
+  else if (nv <= 32) emu_minv_chol<32, 1>(nv, Min, out, B);
+  else if (nv <= 64) emu_minv_chol<32, 2>(nv, Min, out, B);
+  else return -1;
+  return 0;
+}
 
 // algo: 0 = computeRNEADerivatives (third input = a; outputs dtau_dq, dtau_dv, dtau_da, tau),
 //       1 = computeABADerivatives  (third input = tau; outputs ddq_dq, ddq_dv, ddq_dtau, ddq),

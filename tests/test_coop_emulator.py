@@ -91,6 +91,29 @@ def test_emulated_minverse(emu, oracle_cls, name):
         assert not np.tril(Minv[:, b].reshape(nv, nv, order="F"), -1).any()
 
 
+@pytest.mark.parametrize("name", _models()[0] + ["humanoid_random"])
+def test_emulated_minverse_cholesky(emu, oracle_cls, name):
+    """computeMinverse as the engine runs it by default (minv_chol.cuh): Cholesky of crba's matrix, two triangular substitutions,
+    G lanes per configuration — against the oracle's articulated-body Minv (aba.hxx:613-902); the lower triangle stays zero and
+    the strictly-lower part of the input (garbage here) is never read."""
+    model = _get(name, _models()[1])
+    orc = oracle_cls(model)
+    q, _, _ = random_inputs(model, 2, 23)
+    nv = model.nv
+    M = np.asfortranarray(orc.crba(q, world=True))
+    for b in range(q.shape[1]):
+        A = M[:, b].reshape(nv, nv, order="F")
+        A[np.tril_indices(nv, -1)] = np.nan  # only the upper triangle may be read
+        M[:, b] = A.reshape(-1, order="F")
+    out = np.full((nv * nv, q.shape[1]), np.nan, order="F")
+    p = lambda z: z.ctypes.data_as(ctypes.c_void_p)
+    assert emu.emu_minv_chol_run(ctypes.c_int(nv), p(M), p(out), ctypes.c_int64(q.shape[1])) == 0
+    ref = orc.minverse(q)
+    assert_close(out, ref, atol=1e-12 + 1e-11 * np.abs(ref).max(), what="Minv (Cholesky)")
+    for b in range(q.shape[1]):
+        assert not np.tril(out[:, b].reshape(nv, nv, order="F"), -1).any()
+
+
 @pytest.mark.parametrize("name", _models()[0])
 def test_emulated_small_batch_rnea_and_aba(emu, oracle_cls, name):
     """The small-batch (cooperative) kernels of rneaInParallel / abaInParallel; aba(rnea(a)) == a closes the loop

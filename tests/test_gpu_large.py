@@ -148,7 +148,8 @@ def test_persistent_grid_rounds(ctx, name, monkeypatch):
 
 FORCED = [("BRBD_ABA_V", "v3", "aba"), ("BRBD_ABA_V", "dfs", "aba"), ("BRBD_ABA_V", "v1", "aba"),
           ("BRBD_CRBA_V", "tmem", "crba"), ("BRBD_CRBA_V", "dfs", "crba"), ("BRBD_CRBA_V", "v1", "crba"),
-          ("BRBD_RNEA_V", "v1", "rnea"), ("BRBD_DRNEA_V", "v1", "drnea"), ("BRBD_DABA_V", "v1", "daba")]
+          ("BRBD_RNEA_V", "v1", "rnea"), ("BRBD_DRNEA_V", "v1", "drnea"), ("BRBD_DABA_V", "v1", "daba"),
+          ("BRBD_MINV_V", "coop", "minv")]
 
 
 @pytest.mark.parametrize("var,val,algo", FORCED)
@@ -177,6 +178,10 @@ def test_forced_paths(ctx, name, var, val, algo, monkeypatch):
         got = pb.computeRNEADerivativesInParallel(1, pool, q, v, a)
         for g, r, nm in zip(got, orc.rnea_derivatives(q, v, a), ("dtau_dq", "dtau_dv", "dtau_da", "tau")):
             assert_close(g, r, rtol=1e-10, atol=1e-12 + 1e-11 * np.abs(r).max(axis=0, keepdims=True), what=f"{nm}[{val}] {name}")
+    elif algo == "minv":  # the articulated-body computeMinverse of the cooperative kernel (the default is crba + Cholesky)
+        ref = orc.minverse(q)
+        got = pb.computeMinverseInParallel(1, pool, q)
+        assert_close(got, ref, rtol=1e-10, atol=1e-12 + 1e-10 * np.abs(ref).max(axis=0, keepdims=True), what=f"Minv[{val}] {name}")
     else:
         got = pb.computeABADerivativesInParallel(1, pool, q, v, a)
         for g, r, nm in zip(got, orc.aba_derivatives(q, v, a), ("ddq_dq", "ddq_dv", "ddq_dtau", "ddq")):
@@ -493,3 +498,36 @@ def test_crba_packed(ctx, name):
             P32 = pb.crbaPackedInParallel(1, pool, np.asfortranarray(q.astype(np.float32)))
             assert P32.dtype == np.float32 and np.abs(P32 - refM[key]).max() <= 2e-5 * np.abs(refM).max()
     pool.close()
+
+
+@pytest.mark.parametrize("name", ["simple_humanoid_ff", "talos_reduced_ff", "manipulator", "humanoid_hands", "mixed"])
+def test_minverse_large(ctx, name):
+    """computeMinverse at bench sizes: crba into the device's work buffer in chunks of 32 768 configurations, then the dense
+    Cholesky inversion (minv_chol.cuh); sampled columns against the oracle's articulated-body Minv, upper triangle + exact zeros,
+    padded leading dimension, the generated and the generic CRBA underneath, FP32."""
+    import torch
+    import pinocchio_b200 as pb
+    model, _, orc = ctx(name)
+    nv, nn = model.nv, model.nv * model.nv
+    B = 70001
+    q, _, _ = random_inputs(model, B, 31)
+    cols = sample_columns(B, 5)
+    ref = orc.minverse(np.asfortranarray(q[:, cols]))
+    tq, = to_dev(q)
+    low = np.tril(np.ones((nv, nv), dtype=bool), -1).reshape(-1, order="F")
+    for spec in (False, True):
+        pool = pb.ModelPool(model, [0])
+        if spec:
+            pool.specialize(["crba"])
+        big = torch.full((B + 1, nn + 1), -7.0, dtype=torch.float64, device="cuda")
+        pb.computeMinverseInParallel(1, pool, tq, big[:B, :nn])
+        torch.cuda.synchronize()
+        got = big[torch.from_numpy(cols).cuda()].cpu().numpy()
+        assert_close(got[:, :nn].T, ref, rtol=1e-10, atol=1e-12 + 1e-10 * np.abs(ref).max(axis=0, keepdims=True), what=f"Minv[chol, specialised={spec}] {name} B={B}")
+        assert not got[:, :nn].T[low].any(), "strictly-lower part must be exact zeros"
+        assert (got[:, nn] == -7.0).all() and (big[B].cpu().numpy() == -7.0).all(), "wrote outside the caller's block"
+        if not spec:
+            m32 = pb.computeMinverseInParallel(1, pool, np.asfortranarray(q[:, :500].astype(np.float32)))
+            r32 = orc.minverse(np.asfortranarray(q[:, :500]))
+            assert m32.dtype == np.float32 and np.abs(m32 - r32).max() <= (2e-3 if name == "talos_reduced_ff" else 2e-4) * np.abs(r32).max()
+        pool.close()
