@@ -146,6 +146,21 @@ public:
   }
   int nq() const { return brbd_model_nq(model_); }
   int nv() const { return brbd_model_nv(model_); }
+  // the structural pattern of crba's result (crba.hxx:94-95: M.block(idx_v, idx_v, nv, nvSubtree) is all crba writes), column-major:
+  // entry k of a packed column (crbaPackedInParallel) is M(rows[k], cols[k])
+  void crbaPattern(std::vector<int32_t> & rows, std::vector<int32_t> & cols) const
+  {
+    int64_t nnz = 0;
+    check_status(brbd_model_crba_pattern(model_, nullptr, nullptr, 0, &nnz));
+    rows.resize((size_t)nnz); cols.resize((size_t)nnz);
+    check_status(brbd_model_crba_pattern(model_, rows.data(), cols.data(), nnz, &nnz));
+  }
+  int64_t crbaPatternSize() const
+  {
+    int64_t nnz = 0;
+    check_status(brbd_model_crba_pattern(model_, nullptr, nullptr, 0, &nnz));
+    return nnz;
+  }
   brbd_pool * handle() { return pool_; }
   // Unlike the reference (parallel/rnea.hpp:53 "The pool is too small"), num_threads is NOT checked against size(): the GPU
   // path has no per-thread replicas, any num_threads is accepted.
@@ -218,6 +233,15 @@ inline void crbaInParallel(size_t num_threads, DeviceModelPool & pool, ConstMatr
   detail::check_rows("M", M.rows, (int64_t)pool.nv() * pool.nv());
   detail::check_cols("M", M.cols, q.cols);
   check_status(brbd_crba_batch(pool.handle(), q.data, q.ld, M.data, M.ld, q.cols, BRBD_PTR_HOST | BRBD_FP64));
+}
+// P.col(i) = the entries of crba(q.col(i)) inside the structural pattern (pool.crbaPattern), column-major — opt-in output format
+inline void crbaPackedInParallel(size_t num_threads, DeviceModelPool & pool, ConstMatrixView q, MatrixView P)
+{
+  detail::check_pool(num_threads, pool);
+  detail::check_rows("q", q.rows, pool.nq());
+  detail::check_rows("P", P.rows, pool.crbaPatternSize());
+  detail::check_cols("P", P.cols, q.cols);
+  check_status(brbd_crba_packed_batch(pool.handle(), q.data, q.ld, P.data, P.ld, q.cols, BRBD_PTR_HOST | BRBD_FP64));
 }
 
 // computeRNEADerivatives per column — rnea-derivatives.hpp:110-128 (outputs need not be pre-zeroed here)
@@ -352,6 +376,11 @@ template<class Q, class M1>
 void crbaInParallel(const size_t num_threads, DeviceModelPool & pool, const Eigen::MatrixBase<Q> & q, const Eigen::MatrixBase<M1> & M)
 {
   crbaInParallel(num_threads, pool, detail::cview(q), detail::mview(M));
+}
+template<class Q, class M1>
+void crbaPackedInParallel(const size_t num_threads, DeviceModelPool & pool, const Eigen::MatrixBase<Q> & q, const Eigen::MatrixBase<M1> & P)
+{
+  crbaPackedInParallel(num_threads, pool, detail::cview(q), detail::mview(P));
 }
 // argument order of computeRNEADerivatives(model, data, q, v, a, rnea_partial_dq, rnea_partial_dv, rnea_partial_da), rnea-derivatives.hpp:110-128
 template<class Q, class V1, class V2, class M1, class M2, class M3>

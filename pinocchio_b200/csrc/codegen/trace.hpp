@@ -11,6 +11,7 @@
 // (sin, cos, U Dinv, Dinv, u) from the per-thread record store.  `Tracer::park / fetch` mark what is long-lived: the emitter
 // decides where it lives (registers + local memory under the compiler's control, or explicit on-chip slots).
 #pragma once
+#include <cstdlib>
 
 #include <string>
 #include <vector>
@@ -470,7 +471,8 @@ inline void trace_aba(Tracer & T)
     if (M.nvj[i] > 1) p3[i].qj = qseg(i, 2);
     p3[i].vj = vseg(i, 2);
   };
-  constexpr int P3_AHEAD = 2;
+  int P3_AHEAD = 1; // joints (measured, BRBD_GEN_ABA_P3AHEAD = 0 .. 4: 0.1583 / 0.1556 / 0.1575 / 0.1628 / 0.1667 ms at 65 536 x simple_humanoid)
+  if (const char * e = std::getenv("BRBD_GEN_ABA_P3AHEAD")) P3_AHEAD = std::max(0, std::min(8, std::atoi(e)));
   for (int i = 1; i < nj && i <= P3_AHEAD; ++i) p3_load(i);
   for (int i = 1; i < nj; ++i)
   {

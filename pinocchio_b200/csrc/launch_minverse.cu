@@ -14,8 +14,10 @@ brbd_status launch_minverse_chol(brbd_pool * p, DeviceCtx & d, const T * q, int6
   const int64_t nn = (int64_t)nv * nv;
   const int G = coop_group_size(nv);
   const MinvCholLayout L = minv_chol_layout(nv);
-  const size_t per_warp = (size_t)L.per_group * sizeof(T) * (32 / G);
+  const MinvCholBlockedLayout LB = minv_chol_blocked_layout(nv); // 32 lanes per configuration: the 4 x 4 blocked kernel
+  const size_t per_warp = G == 32 ? (size_t)LB.per_group * sizeof(T) : (size_t)L.per_group * sizeof(T) * (32 / G);
   int warps = (int)std::max<size_t>(1, std::min<size_t>(16, ((size_t)d.max_smem_optin - 1024) / per_warp));
+  if (const char * e = std::getenv("BRBD_MINV_WARPS")) warps = std::max(1, std::min(warps, std::atoi(e))); // experiments
   // small batches: spread the configurations over all SMs
   while (warps > 1 && (int64_t)(warps - 1) * (32 / G) * d.sm_count >= B) --warps;
   const size_t dyn = (size_t)warps * per_warp;
@@ -36,10 +38,17 @@ brbd_status launch_minverse_chol(brbd_pool * p, DeviceCtx & d, const T * q, int6
     if (st != BRBD_OK) return st;                                                                                \
     minv_chol_kernel<T, GG, RR><<<grid, warps * 32, dyn, d.s()>>>(Mbuf, nn, Minv + c0 * ldM, ldM, nv, L, bc);    \
   }
+#define BRBD_LAUNCH_BLOCKED(RR)                                                                                  \
+  {                                                                                                              \
+    st = set_smem(minv_chol_blocked_kernel<T, RR>, dyn);                                                         \
+    if (st != BRBD_OK) return st;                                                                                \
+    minv_chol_blocked_kernel<T, RR><<<grid, warps * 32, dyn, d.s()>>>(Mbuf, nn, Minv + c0 * ldM, ldM, nv, LB, bc); \
+  }
     if (G == 8) BRBD_LAUNCH_CHOL(8, 1)
     else if (G == 16) BRBD_LAUNCH_CHOL(16, 1)
-    else if (nv <= 32) BRBD_LAUNCH_CHOL(32, 1)
-    else BRBD_LAUNCH_CHOL(32, 2)
+    else if (LB.nvp <= 32) BRBD_LAUNCH_BLOCKED(1)
+    else BRBD_LAUNCH_BLOCKED(2)
+#undef BRBD_LAUNCH_BLOCKED
 #undef BRBD_LAUNCH_CHOL
     p->launches += 1;
     CUDA_TRY(cudaGetLastError());
@@ -51,7 +60,12 @@ template<class T>
 brbd_status launch_minverse(brbd_pool * p, DeviceCtx & d, const T * q, int64_t ldq, T * Minv, int64_t ldM, int64_t B)
 {
   const ModelPOD<double> & M = p->model.pd;
-  if (!forced_path("BRBD_MINV_V", "coop")) return launch_minverse_chol<T>(p, d, q, ldq, Minv, ldM, B);
+  // crba + Cholesky wins where a configuration takes 8 or 16 lanes (6-dof manipulator, 65 536 configurations: 0.209 -> 0.097 ms);
+  // with 32 lanes per configuration its inner loops are bound by shared-memory bandwidth (one 256-byte own-row load per warp
+  // FMA: 3.9 ms against the articulated-body kernel's 4.1 ms for a 35-dof humanoid, 5.2 against 4.9 for talos) and the
+  // articulated-body kernel stays the default (profiles/r2_minv_chol.txt).  BRBD_MINV_V=chol / coop force either.
+  const bool chol = forced_path("BRBD_MINV_V", "chol") || (!forced_path("BRBD_MINV_V", "coop") && M.nv <= 16);
+  if (chol) return launch_minverse_chol<T>(p, d, q, ldq, Minv, ldM, B);
   const int G = coop_group_size(M.nv);
   const AbaCoopLayout L = aba_coop_layout(M.nq, M.nv, M.njoints, G);
   const size_t static_bytes = sizeof(ModelPOD<T>) + sizeof(CoopTables) + 1024;

@@ -16,7 +16,7 @@ for name in models:
         out = torch.empty((B, model.nv ** 2), dtype=torch.float64, device="cuda")
         for mode in ("coop", "chol", "chol+gen"):
             if mode == "coop": os.environ["BRBD_MINV_V"] = "coop"
-            else: os.environ.pop("BRBD_MINV_V", None)
+            else: os.environ["BRBD_MINV_V"] = "chol"
             pool = pb.ModelPool(model, [0]); pool.set_stream(torch.cuda.current_stream().cuda_stream)
             if mode == "chol+gen": pool.specialize(["crba"])
             for _ in range(2): pb.computeMinverseInParallel(1, pool, tq, out, async_=True)

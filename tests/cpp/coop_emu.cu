@@ -139,11 +139,31 @@ void emu_minv_chol(int nv, const double * Min, double * out, int64_t B)
     free(base);
   }
 }
+template<int R>
+void emu_minv_chol_blocked(int nv, const double * Min, double * out, int64_t B)
+{
+  const MinvCholBlockedLayout L = minv_chol_blocked_layout(nv);
+  const int64_t nn = (int64_t)nv * nv;
+  for (int64_t cfg = 0; cfg < B; ++cfg)
+  {
+    double * base = alloc_region((size_t)L.per_group);
+    run_lanes(32, [&](int gl) { minv_chol_blocked_config<double, R>(nv, L, base, gl, Min + cfg * nn, out + cfg * nn, true); });
+    free(base);
+  }
+}
 } // namespace
 
 extern "C" {
 
 const char * emu_last_error(void) { return g_err.c_str(); }
+
+int emu_minv_chol_blocked_run(int nv, const double * Min, double * out, int64_t B)
+{
+  if (nv <= 32) emu_minv_chol_blocked<1>(nv, Min, out, B);
+  else if (nv <= 64) emu_minv_chol_blocked<2>(nv, Min, out, B);
+  else return -1;
+  return 0;
+}
 
 int emu_minv_chol_run(int nv, const double * Min, double * out, int64_t B)
 {

@@ -71,6 +71,22 @@ int main()
         }
       }
     if (!(err < 1e-9)) { std::printf("FAIL identities, %.3e\n", err); return 1; }
+    { // the packed output format: P(k, c) == M(rows[k] + nv * cols[k], c), and M has nothing outside the pattern
+      std::vector<int32_t> rows, cols;
+      pool->crbaPattern(rows, cols);
+      Eigen::MatrixXd P((long)rows.size(), B);
+      pb::crbaPackedInParallel(1, *pool, q, P);
+      std::vector<char> in_pattern((size_t)nv * nv, 0);
+      for (size_t k = 0; k < rows.size(); ++k)
+      {
+        in_pattern[(size_t)cols[k] * nv + rows[k]] = 1;
+        for (int c = 0; c < B; ++c) err = std::fmax(err, std::fabs(P((long)k, c) - M(cols[k] * nv + rows[k], c)));
+      }
+      for (int e = 0; e < nv * nv; ++e)
+        if (!in_pattern[e])
+          for (int c = 0; c < B; ++c) err = std::fmax(err, std::fabs(M(e, c)));
+      if (!(err < 1e-12)) { std::printf("FAIL packed crba, %.3e\n", err); return 1; }
+    }
     // a block of columns with the parent's outer stride, as q.middleCols(5, 7) would be
     Eigen::MatrixXd tau2(nv, B);
     Eigen::ColsBlock qb(q, 5, 7), vb(v, 5, 7), ab(a, 5, 7), tb(tau2, 5, 7);

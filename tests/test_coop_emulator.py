@@ -91,8 +91,9 @@ def test_emulated_minverse(emu, oracle_cls, name):
         assert not np.tril(Minv[:, b].reshape(nv, nv, order="F"), -1).any()
 
 
+@pytest.mark.parametrize("blocked", [False, True])
 @pytest.mark.parametrize("name", _models()[0] + ["humanoid_random"])
-def test_emulated_minverse_cholesky(emu, oracle_cls, name):
+def test_emulated_minverse_cholesky(emu, oracle_cls, name, blocked):
     """computeMinverse as the engine runs it by default (minv_chol.cuh): Cholesky of crba's matrix, two triangular substitutions,
     G lanes per configuration — against the oracle's articulated-body Minv (aba.hxx:613-902); the lower triangle stays zero and
     the strictly-lower part of the input (garbage here) is never read."""
@@ -107,7 +108,8 @@ def test_emulated_minverse_cholesky(emu, oracle_cls, name):
         M[:, b] = A.reshape(-1, order="F")
     out = np.full((nv * nv, q.shape[1]), np.nan, order="F")
     p = lambda z: z.ctypes.data_as(ctypes.c_void_p)
-    assert emu.emu_minv_chol_run(ctypes.c_int(nv), p(M), p(out), ctypes.c_int64(q.shape[1])) == 0
+    run = emu.emu_minv_chol_blocked_run if blocked else emu.emu_minv_chol_run  # 4 x 4 blocks, 32 lanes / the simple loops
+    assert run(ctypes.c_int(nv), p(M), p(out), ctypes.c_int64(q.shape[1])) == 0
     ref = orc.minverse(q)
     assert_close(out, ref, atol=1e-12 + 1e-11 * np.abs(ref).max(), what="Minv (Cholesky)")
     for b in range(q.shape[1]):

@@ -149,7 +149,7 @@ def test_persistent_grid_rounds(ctx, name, monkeypatch):
 FORCED = [("BRBD_ABA_V", "v3", "aba"), ("BRBD_ABA_V", "dfs", "aba"), ("BRBD_ABA_V", "v1", "aba"),
           ("BRBD_CRBA_V", "tmem", "crba"), ("BRBD_CRBA_V", "dfs", "crba"), ("BRBD_CRBA_V", "v1", "crba"),
           ("BRBD_RNEA_V", "v1", "rnea"), ("BRBD_DRNEA_V", "v1", "drnea"), ("BRBD_DABA_V", "v1", "daba"),
-          ("BRBD_MINV_V", "coop", "minv")]
+          ("BRBD_MINV_V", "coop", "minv"), ("BRBD_MINV_V", "chol", "minv")]
 
 
 @pytest.mark.parametrize("var,val,algo", FORCED)
@@ -501,7 +501,7 @@ def test_crba_packed(ctx, name):
 
 
 @pytest.mark.parametrize("name", ["simple_humanoid_ff", "talos_reduced_ff", "manipulator", "humanoid_hands", "mixed"])
-def test_minverse_large(ctx, name):
+def test_minverse_large(ctx, name, monkeypatch):
     """computeMinverse at bench sizes: crba into the device's work buffer in chunks of 32 768 configurations, then the dense
     Cholesky inversion (minv_chol.cuh); sampled columns against the oracle's articulated-body Minv, upper triangle + exact zeros,
     padded leading dimension, the generated and the generic CRBA underneath, FP32."""
@@ -509,6 +509,7 @@ def test_minverse_large(ctx, name):
     import pinocchio_b200 as pb
     model, _, orc = ctx(name)
     nv, nn = model.nv, model.nv * model.nv
+    monkeypatch.setenv("BRBD_MINV_V", "chol")  # the default above 16 dofs is the articulated-body kernel
     B = 70001
     q, _, _ = random_inputs(model, B, 31)
     cols = sample_columns(B, 5)
