@@ -50,9 +50,10 @@ KERNEL_NAME = {"rnea": "rnea_dfs_kernel<double>", "aba": "aba_rr_kernel<double>"
 # dram__bytes_read.sum + dram__bytes_write.sum per launch, RECORDED from the committed `ncu --set full` capture named in
 # `source` (not measured in this run); only quoted for the exact configuration / batch of that capture, null otherwise.
 NCU_TRAFFIC = {
+    ("C2", 65536, "crba"): {"bytes": 610.8e6, "source": "profiles/r2_v3_step_ncu_full.csv (brbd_gen_crba_0, 96 threads, bulk copies: 23.1 MB read + 587.7 MB written)"},
     ("C2", 65536, "crba:generic"): {"bytes": 644.2e6, "source": "profiles/r2_v1_step_ncu_full.csv (crba_tma_kernel<double,224,1>: 47.3 MB read + 596.9 MB written)"},
     ("C2", 65536, "aba:generic"): {"bytes": 814.2e6, "source": "profiles/r1_v8_step_ncu_full.csv (aba_rr_kernel<double,224>: 388.1 MB read + 426.1 MB written)"},
-    ("C2", 65536, "aba"): {"bytes": 457.6e6, "source": "profiles/r2_v1_step_ncu_full.csv (brbd_gen_aba_0, 448 threads: 257.8 MB read + 199.8 MB written; "
+    ("C2", 65536, "aba"): {"bytes": 465.1e6, "source": "profiles/r2_v3_step_ncu_full.csv (brbd_gen_aba_0, 448 threads: 260.6 MB read + 204.6 MB written; "
                                                        "the generic aba_rr_kernel: 814.2 MB, profiles/r1_v8_step_ncu_full.csv)"},
 }
 

@@ -60,11 +60,9 @@ template<class T>
 brbd_status launch_minverse(brbd_pool * p, DeviceCtx & d, const T * q, int64_t ldq, T * Minv, int64_t ldM, int64_t B)
 {
   const ModelPOD<double> & M = p->model.pd;
-  // crba + Cholesky wins where a configuration takes 8 or 16 lanes (6-dof manipulator, 65 536 configurations: 0.209 -> 0.097 ms);
-  // with 32 lanes per configuration its inner loops are bound by shared-memory bandwidth (one 256-byte own-row load per warp
-  // FMA: 3.9 ms against the articulated-body kernel's 4.1 ms for a 35-dof humanoid, 5.2 against 4.9 for talos) and the
-  // articulated-body kernel stays the default (profiles/r2_minv_chol.txt).  BRBD_MINV_V=chol / coop force either.
-  const bool chol = forced_path("BRBD_MINV_V", "chol") || (!forced_path("BRBD_MINV_V", "coop") && M.nv <= 16);
+  // crba + Cholesky (minv_chol.cuh) is the default — 65 536 configurations: 6-dof manipulator 0.209 -> 0.097 ms, 35-dof humanoid
+  // 4.08 -> 2.06 ms, talos 4.9 -> 2.5 ms (profiles/r2_minv_chol.txt); BRBD_MINV_V=coop keeps the articulated-body kernel
+  const bool chol = !forced_path("BRBD_MINV_V", "coop");
   if (chol) return launch_minverse_chol<T>(p, d, q, ldq, Minv, ldM, B);
   const int G = coop_group_size(M.nv);
   const AbaCoopLayout L = aba_coop_layout(M.nq, M.nv, M.njoints, G);

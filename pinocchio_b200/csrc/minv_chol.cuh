@@ -235,23 +235,28 @@ BRBD_DI void minv_chol_blocked_config(int nv, const MinvCholBlockedLayout & L, T
   const int ld = L.ld, nvp = L.nvp;
   // ---- S = the lower triangle of diag(M, I), everything else zero (the caller's upper triangle, column i -> row i) ----
   // eight independent global loads per lane in flight (one load per loop step exposed a DRAM round trip 43 times per configuration)
-  for (int e0 = gl; e0 < nvp * ld; e0 += 8 * G)
   {
-    T val[8];
-#pragma unroll
-    for (int u = 0; u < 8; ++u)
+    int i = 0, j = gl; // element e = i * ld + j, advanced without divisions
+    while (j >= ld) { j -= ld; ++i; }
+    for (int e0 = gl; e0 < nvp * ld; e0 += 8 * G)
     {
-      const int e = e0 + u * G, i = e / ld, j = e - i * ld;
-      val[u] = T(0);
-      if (e < nvp * ld)
-      {
-        if (i < nv) { if (j <= i) val[u] = gM[i * nv + j]; }
-        else if (j == i) val[u] = T(1);
-      }
-    }
+      T val[8];
 #pragma unroll
-    for (int u = 0; u < 8; ++u)
-      if (e0 + u * G < nvp * ld) S[e0 + u * G] = val[u];
+      for (int u = 0; u < 8; ++u)
+      {
+        val[u] = T(0);
+        if (e0 + u * G < nvp * ld)
+        {
+          if (i < nv) { if (j <= i) val[u] = gM[i * nv + j]; }
+          else if (j == i) val[u] = T(1);
+        }
+        j += G;
+        while (j >= ld) { j -= ld; ++i; }
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+        if (e0 + u * G < nvp * ld) S[e0 + u * G] = val[u];
+    }
   }
   BRBD_SYNCWARP();
   int row[R];

@@ -18,6 +18,7 @@ ap.add_argument("--algos", default="rnea,aba,crba,rnea_derivatives,aba_derivativ
 ap.add_argument("--batch", type=int, default=65536)
 ap.add_argument("--reps", type=int, default=5)
 ap.add_argument("--dtype", default="f64")
+ap.add_argument("--generic", action="store_true", help="do not specialise the pool (generic kernels)")
 args = ap.parse_args()
 build_oracle()
 hbm = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"] if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0
@@ -28,6 +29,8 @@ for name in args.models.split(","):
     model = load_model(name)
     pool = pb.ModelPool(model, [0])
     pool.set_stream(torch.cuda.current_stream().cuda_stream)  # CUDA events below are recorded on torch's stream
+    if not args.generic:  # kernels generated for the model (the derivative programs only for small models)
+        pool.specialize(["rnea", "aba", "crba", "rnea_derivatives", "aba_derivatives"], fp32=args.dtype != "f64")
     if fp64_peak is None:
         fp64_peak = pool.measure_fp64_peak()[0]
     orc = Oracle(model)

@@ -15,12 +15,16 @@ from oracle import Oracle, build_oracle
 ap = argparse.ArgumentParser()
 ap.add_argument("--models", default="talos_reduced_ff,humanoid_random")
 ap.add_argument("--max-log2", type=int, default=22)
+ap.add_argument("--generic", action="store_true", help="do not specialise the pool (generic kernels)")
 args = ap.parse_args()
 build_oracle()
 for name in args.models.split(","):
     model = load_model(name)
     pool = pb.ModelPool(model, [0])
     pool.set_stream(torch.cuda.current_stream().cuda_stream)
+    if not args.generic:  # kernels generated for the model, both precisions
+        pool.specialize(["rnea", "aba", "crba"])
+        pool.specialize(["rnea", "aba", "crba"], fp32=True)
     orc = Oracle(model)
     nq, nv = model.nq, model.nv
     nn = nv * nv

@@ -509,7 +509,6 @@ def test_minverse_large(ctx, name, monkeypatch):
     import pinocchio_b200 as pb
     model, _, orc = ctx(name)
     nv, nn = model.nv, model.nv * model.nv
-    monkeypatch.setenv("BRBD_MINV_V", "chol")  # the default above 16 dofs is the articulated-body kernel
     B = 70001
     q, _, _ = random_inputs(model, B, 31)
     cols = sample_columns(B, 5)
