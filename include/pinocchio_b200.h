@@ -234,6 +234,12 @@ brbd_status brbd_pool_set_specialized_min_batch(brbd_pool * p, int64_t min_batch
  * B200 hosts: 57 GB/s pinned vs 11-22 GB/s pageable) and lets the upload / compute / download pipeline of a
  * call overlap.  An Eigen::MatrixXd that is reused across calls should be registered once. */
 brbd_status brbd_host_register(void * ptr, uint64_t bytes);
+/* Host threads a host-pointer call may use — the `num_threads` of the reference's parallel API (parallel/rnea.hpp:38), which the
+ * reference spends on the algorithm itself.  Here they serve one purpose: with n >= 2 (and a single-device pool, NVRTC available),
+ * a host-pointer brbd_crba_batch moves only the entries inside the structural pattern over PCIe (brbd_crba_packed_batch's
+ * format, a third of nv * nv for a humanoid) and n threads rebuild the caller's dense matrices while the next chunk is in
+ * flight.  Results are bit-identical to the packed kernel's; 0 or 1 (default): the dense block is copied as it is. */
+brbd_status brbd_pool_set_host_threads(brbd_pool * p, int n);
 brbd_status brbd_host_unregister(void * ptr);
 
 /* Register-resident DFMA loop; returns achieved FP64 FLOP/s on the pool's device 0

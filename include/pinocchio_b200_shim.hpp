@@ -232,6 +232,8 @@ inline void crbaInParallel(size_t num_threads, DeviceModelPool & pool, ConstMatr
   detail::check_rows("q", q.rows, pool.nq());
   detail::check_rows("M", M.rows, (int64_t)pool.nv() * pool.nv());
   detail::check_cols("M", M.cols, q.cols);
+  // num_threads host threads rebuild the dense matrices from the packed transfer (brbd_pool_set_host_threads); 0 / 1: plain copy
+  check_status(brbd_pool_set_host_threads(pool.handle(), (int)num_threads));
   check_status(brbd_crba_batch(pool.handle(), q.data, q.ld, M.data, M.ld, q.cols, BRBD_PTR_HOST | BRBD_FP64));
 }
 // P.col(i) = the entries of crba(q.col(i)) inside the structural pattern (pool.crbaPattern), column-major — opt-in output format

@@ -202,6 +202,95 @@ brbd_status run_call(brbd_pool * p, std::vector<Arg> & args, int64_t B, int flag
   }
   return BRBD_OK;
 }
+
+// Host-pointer crba with packed transfer (brbd_pool_set_host_threads): per chunk, q up | the generated CRBA with compact staging
+// | the nnz pattern entries down into a pinned landing buffer | host threads rebuild the caller's dense matrices (host_expand.cpp)
+// while the next chunk is in flight.  Single-device pools.  *done = false when the packed kernel is not available (no NVRTC):
+// the caller then takes the dense path.
+template<class T>
+brbd_status run_crba_expand(brbd_pool * p, const T * q, int64_t ldq, T * M, int64_t ldM, int64_t B, bool * done)
+{
+  *done = false;
+  DeviceCtx & d = p->devs[0];
+  const int nq = p->model.pd.nq, nv = p->model.pd.nv, nn = nv * nv;
+  if (p->crba_idx.empty()) crba_pattern_index(p->model, p->crba_idx);
+  const int64_t nnz = (int64_t)p->crba_idx.size();
+  if (2 * nnz > nn) return BRBD_OK; // nothing to gain from packing (a chain: the upper triangle is the pattern)
+  CUDA_TRY(cudaSetDevice(d.dev));
+  const int64_t chunk = std::min<int64_t>(B, std::max<int64_t>(4096, (((int64_t)(48u << 20) / (int64_t)(nnz * sizeof(T))) / 1024) * 1024));
+  brbd_status st = BRBD_OK;
+  for (int b = 0; b < 2 && st == BRBD_OK; ++b)
+  {
+    st = ensure_stage(d, b, (size_t)nq * chunk * sizeof(T));
+    if (st == BRBD_OK) st = ensure_stage(d, 2 + b, (size_t)nnz * chunk * sizeof(T));
+    const size_t need = (size_t)nnz * chunk * sizeof(T);
+    if (st == BRBD_OK && p->host_stage_bytes[b] < need)
+    {
+      if (p->host_stage[b]) cudaFreeHost(p->host_stage[b]);
+      p->host_stage[b] = nullptr;
+      p->host_stage_bytes[b] = 0;
+      CUDA_TRY(cudaHostAlloc(&p->host_stage[b], need, cudaHostAllocDefault));
+      p->host_stage_bytes[b] = need;
+    }
+  }
+  if (st != BRBD_OK) return st;
+  const bool user = d.use_user_stream;
+  d.use_user_stream = false; // the kernels of host-pointer calls run on the pool's own streams
+  struct Guard
+  {
+    DeviceCtx & d; bool user;
+    ~Guard()
+    {
+      d.use_user_stream = user;
+      cudaStreamSynchronize(d.s_in); cudaStreamSynchronize(d.stream); cudaStreamSynchronize(d.s_out);
+    }
+  } guard{d, user};
+  const int64_t nchunks = (B + chunk - 1) / chunk;
+  auto expand = [&](int64_t it) -> brbd_status {
+    const int buf = (int)(it & 1);
+    const int64_t b0 = it * chunk, nb = std::min<int64_t>(chunk, B - b0);
+    CUDA_TRY(cudaEventSynchronize(d.ev_out[buf]));
+    expand_packed<T>(M + b0 * ldM, ldM, static_cast<const T *>(p->host_stage[buf]), nnz, p->crba_idx.data(), nn, nb, p->host_threads);
+    return BRBD_OK;
+  };
+  for (int64_t it = 0; it < nchunks; ++it)
+  {
+    const int buf = (int)(it & 1);
+    const int64_t b0 = it * chunk, nb = std::min<int64_t>(chunk, B - b0);
+    if (it >= 2) CUDA_TRY(cudaStreamWaitEvent(d.s_in, d.ev_k[buf], 0)); // the kernel that read this q buffer two chunks ago
+    const T * src = q + b0 * ldq;
+    if (ldq == nq) CUDA_TRY(cudaMemcpyAsync(d.stage[buf], src, (size_t)nq * nb * sizeof(T), cudaMemcpyHostToDevice, d.s_in));
+    else
+      CUDA_TRY(cudaMemcpy2DAsync(d.stage[buf], nq * sizeof(T), src, ldq * sizeof(T), nq * sizeof(T), nb, cudaMemcpyHostToDevice, d.s_in));
+    CUDA_TRY(cudaEventRecord(d.ev_in[buf], d.s_in));
+    CUDA_TRY(cudaStreamWaitEvent(d.stream, d.ev_in[buf], 0));
+    if (it >= 2) CUDA_TRY(cudaStreamWaitEvent(d.stream, d.ev_out[buf], 0)); // the download of this P buffer two chunks ago
+    st = launch_crba_packed<T>(p, d, (const T *)d.stage[buf], nq, (T *)d.stage[2 + buf], nnz, nb);
+    if (st != BRBD_OK)
+    {
+      if (it == 0)
+      { // no NVRTC on this host: remember it and let the caller copy the dense block
+        p->packed_unavailable = true;
+        return BRBD_OK;
+      }
+      return st;
+    }
+    CUDA_TRY(cudaEventRecord(d.ev_k[buf], d.stream));
+    CUDA_TRY(cudaStreamWaitEvent(d.s_out, d.ev_k[buf], 0));
+    // (the landing buffer of this parity was expanded before this chunk was queued: see below)
+    CUDA_TRY(cudaMemcpyAsync(p->host_stage[buf], d.stage[2 + buf], (size_t)nnz * nb * sizeof(T), cudaMemcpyDeviceToHost, d.s_out));
+    CUDA_TRY(cudaEventRecord(d.ev_out[buf], d.s_out));
+    if (it >= 1)
+    {
+      st = expand(it - 1);
+      if (st != BRBD_OK) return st;
+    }
+  }
+  st = expand(nchunks - 1);
+  if (st != BRBD_OK) return st;
+  *done = true;
+  return BRBD_OK;
+}
 } // namespace
 
 // ------------------------------------------------------------------------------------------------
@@ -286,6 +375,8 @@ void brbd_pool_destroy(brbd_pool * p)
 {
   if (!p) return;
   release_generated(p);
+  for (int b = 0; b < 2; ++b)
+    if (p->host_stage[b]) cudaFreeHost(p->host_stage[b]);
   for (DeviceCtx & d : p->devs)
   {
     if (cudaSetDevice(d.dev) != cudaSuccess) continue;
@@ -502,6 +593,15 @@ brbd_status brbd_crba_batch(brbd_pool * p, const void * q, int64_t ldq, void * M
   if (!p) return fail(BRBD_EINVAL, "null pool");
   const int nq = p->model.pd.nq, nv = p->model.pd.nv;
   std::vector<Arg> args = {{q, nullptr, ldq, nq, false}, {nullptr, M, ldM, (int64_t)nv * nv, false}};
+  // host pointers + host threads granted (brbd_pool_set_host_threads): packed transfer, dense matrices rebuilt by the threads
+  if (!(flags & BRBD_PTR_DEVICE) && p->host_threads >= 2 && p->devs.size() == 1 && !p->packed_unavailable && q && M && batch >= 4096 &&
+      ldq >= nq && ldM >= (int64_t)nv * nv)
+  {
+    bool done = false;
+    brbd_status st = (flags & BRBD_FP32) ? run_crba_expand<float>(p, (const float *)q, ldq, (float *)M, ldM, batch, &done)
+                                         : run_crba_expand<double>(p, (const double *)q, ldq, (double *)M, ldM, batch, &done);
+    if (st != BRBD_OK || done) return st;
+  }
   DISPATCH(flags, (run_call<T>(p, args, batch, flags, [&](DeviceCtx & d, std::vector<void *> & P, int64_t B) {
              return launch_crba<T>(p, d, (const T *)P[0], args[0].ld, (T *)P[1], args[1].ld, B);
            })));
@@ -618,6 +718,13 @@ brbd_status brbd_aba_euler_step_batch(brbd_pool * p, const void * q, int64_t ldq
            })));
 }
 
+brbd_status brbd_pool_set_host_threads(brbd_pool * p, int n)
+{
+  if (!p) return fail(BRBD_EINVAL, "null pool");
+  if (n < 0) return fail(BRBD_EINVAL, "negative number of host threads");
+  p->host_threads = n;
+  return BRBD_OK;
+}
 brbd_status brbd_host_register(void * ptr, uint64_t bytes)
 {
   if (!ptr || bytes == 0) return fail(BRBD_EINVAL, "null host block");

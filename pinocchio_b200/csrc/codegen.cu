@@ -569,6 +569,12 @@ std::string wrap_host(const std::string & body, const char * name, bool fp32, co
 namespace brbd
 {
 int crba_pattern_nnz(const brbd_model & m) { return cg::crba_pattern(m.pd, 1).nnz; }
+void crba_pattern_index(const brbd_model & m, std::vector<int32_t> & idx)
+{
+  const cg::CrbaPattern pat = cg::crba_pattern(m.pd, 1);
+  idx.resize((size_t)pat.nnz);
+  for (int k = 0; k < pat.nnz; ++k) idx[k] = pat.cols[k] * m.pd.nv + pat.rows[k];
+}
 } // namespace brbd
 
 extern "C" {

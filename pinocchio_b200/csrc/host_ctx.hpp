@@ -106,6 +106,13 @@ struct brbd_pool
 {
   brbd::GenSet gen[5][2]; // [BRBD_GEN_*][fp64, fp32]
   brbd::GenKernel crba_packed[2]; // the generated CRBA with compact staging (brbd_crba_packed_batch), built at its first call
+  // host-pointer crba with packed transfer (brbd_pool_set_host_threads): position of every packed entry inside a matrix, pinned
+  // landing buffers for two chunks in flight
+  int host_threads = 0;
+  std::vector<int32_t> crba_idx;
+  void * host_stage[2] = {nullptr, nullptr};
+  size_t host_stage_bytes[2] = {0, 0};
+  bool packed_unavailable = false; // the compact-staging kernel could not be built (no NVRTC): dense transfers
   int64_t gen_min_batch = 8192; // batches at least this large use a specialised kernel when there is one
   brbd_model model;
   std::vector<brbd::DeviceCtx> devs;
@@ -393,6 +400,10 @@ brbd_status launch_generated(brbd_pool * p, DeviceCtx & d, int algo, const T * q
 template<class T>
 brbd_status launch_crba_packed(brbd_pool * p, DeviceCtx & d, const T * q, int64_t ldq, T * P, int64_t ldP, int64_t B);
 int crba_pattern_nnz(const brbd_model & m);
+void crba_pattern_index(const brbd_model & m, std::vector<int32_t> & idx); // idx[k] = cols[k] * nv + rows[k]
+// host_expand.cpp
+template<class T>
+void expand_packed(T * dst, int64_t ld, const T * src, int64_t nnz, const int32_t * idx, int nn, int64_t count, int threads);
 // generated computeRNEADerivatives / computeABADerivatives (small models): q, v, x -> three nv*nv blocks + an nv block
 template<class T>
 brbd_status launch_generated_derivs(brbd_pool * p, DeviceCtx & d, int algo, const T * q, int64_t ldq, const T * v, int64_t ldv, const T * x,

@@ -86,6 +86,8 @@ void release_generated(brbd_pool * p)
     if (p->crba_packed[f].lib) cudaLibraryUnload((cudaLibrary_t)p->crba_packed[f].lib);
     p->crba_packed[f] = GenKernel();
   }
+  p->crba_idx.clear(); // the pattern belongs to the model the kernels were generated for
+  p->packed_unavailable = false;
 }
 
 namespace

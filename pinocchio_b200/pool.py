@@ -364,6 +364,9 @@ def abaInParallel(num_threads: int, pool: ModelPool, q, v, tau, a=None, async_: 
 def crbaInParallel(num_threads: int, pool: ModelPool, q, M=None, async_: bool = False):
     """M[:, i] = vec(crba(model, q[:, i])): (nv*nv x B), upper triangle + zeros (crba.hpp:15-22)."""
     _check_pool(num_threads, pool)
+    # the one place where the reference's num_threads does something here: with host blocks, only the entries inside the tree
+    # sparsity cross PCIe and num_threads host threads rebuild the dense matrices (brbd_pool_set_host_threads)
+    _capi.check(_capi.lib().brbd_pool_set_host_threads(pool._h_pool, int(num_threads)))
     aq = _describe(q, pool.nq, "q")
     nn = pool.nv * pool.nv
     if M is None:

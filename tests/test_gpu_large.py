@@ -531,3 +531,34 @@ def test_minverse_large(ctx, name, monkeypatch):
             r32 = orc.minverse(np.asfortranarray(q[:, :500]))
             assert m32.dtype == np.float32 and np.abs(m32 - r32).max() <= (2e-3 if name == "talos_reduced_ff" else 2e-4) * np.abs(r32).max()
         pool.close()
+
+
+@pytest.mark.parametrize("name", ["simple_humanoid_ff", "talos_reduced_ff", "humanoid_hands"])
+def test_crba_host_threads_packed_transfer(ctx, name):
+    """crbaInParallel on host blocks with num_threads >= 2: only the entries inside the tree sparsity cross PCIe and the host threads
+    rebuild the caller's dense matrices (brbd_pool_set_host_threads, host_expand.cpp).  Same result as the plain dense copy — against
+    the oracle, exact zeros outside the sparsity, a padded leading dimension with a canary, several chunks with a ragged tail, FP32."""
+    import pinocchio_b200 as pb
+    model, _, orc = ctx(name)
+    nv, nn = model.nv, model.nv * model.nv
+    pool = pb.ModelPool(model, [0])
+    mask = structural_mask(model)
+    B = 40000 + 123
+    q, _, _ = random_inputs(model, B, 41)
+    cols = sample_columns(B, 9)
+    ref = orc.crba(np.asfortranarray(q[:, cols]), world=True)
+    big = np.full((nn + 3, B), -7.0, order="F")
+    n0 = pool.launch_count()
+    pb.crbaInParallel(8, pool, q, big[:nn])
+    assert pool.launch_count() - n0 >= 2  # several chunks
+    got = big[:nn][:, cols]
+    assert_close(got, ref, rtol=1e-10, atol=1e-12 + 1e-12 * np.abs(ref).max(axis=0, keepdims=True), what=f"crba[host threads] {name} B={B}")
+    assert not big[:nn][~mask].any(), "entries outside the tree sparsity must be exact zeros"
+    assert (big[nn:] == -7.0).all(), "wrote outside the caller's block"
+    dense = pb.crbaInParallel(1, pool, q)  # the plain path (dense copy)
+    assert_close(big[:nn], dense, rtol=1e-12, atol=1e-13 * np.abs(dense).max(), what=f"crba host threads vs dense copy {name}")
+    q32 = np.asfortranarray(q[:, :9000].astype(np.float32))
+    m32 = pb.crbaInParallel(4, pool, q32)
+    r32 = orc.crba(np.asfortranarray(q[:, :9000]), world=True)
+    assert m32.dtype == np.float32 and np.abs(m32 - r32).max() <= 2e-5 * np.abs(r32).max() and not m32[~mask].any()
+    pool.close()
