@@ -135,10 +135,9 @@ def host_threads():
 
 
 def column_range(B, world, rank):
-    """Contiguous column range of `rank` (the split brbd's own multi-device pool uses)."""
-    per = (B + world - 1) // world
-    c0 = min(B, rank * per)
-    return c0, min(B, c0 + per)
+    """Contiguous column range of `rank` (the split brbd's own multi-device pool uses): pinocchio_b200.sharding."""
+    from pinocchio_b200.sharding import column_range as cr
+    return cr(int(B), int(world), int(rank))
 
 
 def oracle_outputs(orc, algos, n):

@@ -134,6 +134,20 @@ std::string wrap_device(const std::string & body, const char * name, bool fp32, 
   os << "// generated by pinocchio_b200 codegen: " << name << (fp32 ? " (FP32)" : " (FP64)") << ", " << nrec << " record slots, "
      << st.tmem_slots << " tensor-memory + " << st.smem_slots << " shared-memory park slots per configuration\n";
   os << math_macros(fp32) << "#undef BRBD_SINCOS\n" << device_sincos(fp32) << ktable;
+  // record store: written in pass 2, read once in pass 3.  With L2 cache policies (experiment, BRBD_GEN_REC_POLICY=1) the stores
+  // ask L2 to keep the lines (evict_last) and the loads release them (evict_first), so that the 139 MB of records of a 65 536 x
+  // humanoid batch do not leave the 126 MB L2 between the passes.
+  // Measured (profiles/r2_aba_rec_policy.txt): ABA 0.155 -> 0.146 ms at 65 536 x simple_humanoid, 2.46 -> 2.34 ms at 2^20: the default.
+  // BRBD_GEN_REC_POLICY: 0 = off, 1 = records only, 2 = the input columns are also loaded evict_first (they are read once).
+  const int rec_policy_mode = std::getenv("BRBD_GEN_REC_POLICY") ? std::atoi(std::getenv("BRBD_GEN_REC_POLICY")) : 1;
+  const bool rec_policy = rec_policy_mode != 0;
+  const char * keep_fraction = std::getenv("BRBD_GEN_REC_KEEP") ? std::getenv("BRBD_GEN_REC_KEEP") : "1.0";
+  if (rec_policy)
+    os << (fp32 ? "__device__ __forceinline__ real ld_rec(const real * p, unsigned long long pol) { real v; asm volatile(\"ld.global.cg.L2::cache_hint.f32 %0, [%1], %2;\" : \"=f\"(v) : \"l\"(p), \"l\"(pol) : \"memory\"); return v; }\n"
+                  "__device__ __forceinline__ void st_rec(real * p, real v, unsigned long long pol) { asm volatile(\"st.global.cg.L2::cache_hint.f32 [%0], %1, %2;\" ::\"l\"(p), \"f\"(v), \"l\"(pol) : \"memory\"); }\n"
+                : "__device__ __forceinline__ real ld_rec(const real * p, unsigned long long pol) { real v; asm volatile(\"ld.global.cg.L2::cache_hint.f64 %0, [%1], %2;\" : \"=d\"(v) : \"l\"(p), \"l\"(pol) : \"memory\"); return v; }\n"
+                  "__device__ __forceinline__ void st_rec(real * p, real v, unsigned long long pol) { asm volatile(\"st.global.cg.L2::cache_hint.f64 [%0], %1, %2;\" ::\"l\"(p), \"d\"(v), \"l\"(pol) : \"memory\"); }\n");
+  else
   os << (fp32 ? "__device__ __forceinline__ real ld_rec(const real * p) { real v; asm volatile(\"ld.global.cg.f32 %0, [%1];\" : \"=f\"(v) : \"l\"(p) : \"memory\"); return v; }\n"
               : "__device__ __forceinline__ real ld_rec(const real * p) { real v; asm volatile(\"ld.global.cg.f64 %0, [%1];\" : \"=d\"(v) : \"l\"(p) : \"memory\"); return v; }\n");
   // warp-cooperative tile copies: `rows` elements per configuration, configurations `ld` apart in global memory, `pitch` apart
@@ -153,7 +167,13 @@ std::string wrap_device(const std::string & body, const char * name, bool fp32, 
         "    for (int k = lane; k < 32 * rows; k += 32)\n    {\n      g[k] = t[c * pitch + r];\n      r += 32;\n"
         "      while (r >= rows) { r -= rows; ++c; }\n    }\n  }\n  else\n"
         "    for (int c = 0; c < nvalid; ++c)\n      for (int r = lane; r < rows; r += 32) g[c * ld + r] = t[c * pitch + r];\n}\n";
-  if (direct_io)
+  if (direct_io && rec_policy_mode == 2)
+  {
+    os << (fp32 ? "__device__ __forceinline__ real ld_in(const real * p, unsigned long long pol) { real v; asm volatile(\"ld.global.nc.L2::cache_hint.f32 %0, [%1], %2;\" : \"=f\"(v) : \"l\"(p), \"l\"(pol)); return v; }\n"
+                : "__device__ __forceinline__ real ld_in(const real * p, unsigned long long pol) { real v; asm volatile(\"ld.global.nc.L2::cache_hint.f64 %0, [%1], %2;\" : \"=d\"(v) : \"l\"(p), \"l\"(pol)); return v; }\n");
+    os << "#define BRBD_IN0(k) ld_in(tq + (k), pol_drop)\n#define BRBD_IN1(k) ld_in(tv + (k), pol_drop)\n#define BRBD_IN2(k) ld_in(tx + (k), pol_drop)\n";
+  }
+  else if (direct_io)
   {
     os << (fp32 ? "__device__ __forceinline__ real ld_in(const real * p) { real v; asm volatile(\"ld.global.nc.f32 %0, [%1];\" : \"=f\"(v) : \"l\"(p)); return v; }\n"
                 : "__device__ __forceinline__ real ld_in(const real * p) { real v; asm volatile(\"ld.global.nc.f64 %0, [%1];\" : \"=d\"(v) : \"l\"(p)); return v; }\n");
@@ -162,8 +182,16 @@ std::string wrap_device(const std::string & body, const char * name, bool fp32, 
   else
     os << "#define BRBD_IN0(k) tq[(k)]\n#define BRBD_IN1(k) tv[(k)]\n#define BRBD_IN2(k) tx[(k)]\n";
   // record store [CTA][slot][thread of the CTA]: a slot of a warp is one coalesced row, and the slot offset is an immediate
+  if (rec_policy)
+  {
+    os << "#define BRBD_REC_ST(k, val) st_rec(rec + (k) * " << nt << ", (val), pol_keep)\n";
+    os << "#define BRBD_REC_LD(k) ld_rec(rec + (k) * " << nt << ", pol_drop)\n";
+  }
+  else
+  {
   os << "#define BRBD_REC_ST(k, val) __stcg(rec + (k) * " << nt << ", (val))\n";
   os << "#define BRBD_REC_LD(k) ld_rec(rec + (k) * " << nt << ")\n";
+  }
   if (direct_io) os << "#define BRBD_OUT0(row, val) do { if (live) to[(row)] = (val); } while (0)\n#define BRBD_SYNC() __syncthreads()\n";
   else os << "#define BRBD_OUT0(row, val) tx[(row)] = (val)\n#define BRBD_SYNC() __syncthreads()\n";
   const int wpv = fp32 ? 1 : 2;
@@ -185,6 +213,10 @@ std::string wrap_device(const std::string & body, const char * name, bool fp32, 
         "     real * __restrict__ out, long long ldo, real * __restrict__ recbase, long long B)\n{\n";
   os << "  extern __shared__ __align__(16) unsigned char smem_raw[];\n  real * smem = reinterpret_cast<real *>(smem_raw);\n";
   os << "  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;\n";
+  if (rec_policy)
+    os << "  unsigned long long pol_keep, pol_drop;\n"
+          "  asm volatile(\"createpolicy.fractional.L2::evict_last.b64 %0, " << keep_fraction << ";\" : \"=l\"(pol_keep));\n"
+          "  asm volatile(\"createpolicy.fractional.L2::evict_first.b64 %0, 1.0;\" : \"=l\"(pol_drop));\n";
   if (!direct_io)
   {
     os << "  real * tile_q = smem + warp * " << tile << ";\n  real * tile_v = tile_q + " << 32 * qp << ";\n  real * tile_x = tile_v + " << 32 * vp << ";\n";
