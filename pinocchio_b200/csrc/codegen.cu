@@ -427,21 +427,25 @@ std::string wrap_device_crba_bulk(const std::string & body, bool fp32, int nt, i
               : "__device__ __forceinline__ real ld_in(const real * p) { real v; asm volatile(\"ld.global.nc.f64 %0, [%1];\" : \"=d\"(v) : \"l\"(p)); return v; }\n");
   os << "#define BRBD_IN0(k) ld_in(tq + (k))\n#define BRBD_SYNC()\n";
   // row[sh + e] -> g[e], e in [0, L): plain stores for the unaligned head / tail, one bulk copy for the rest
-  os << "__device__ __forceinline__ void bulk_flush(const real * row, int sh, real * __restrict__ g, int L, bool live)\n{\n"
+  // the copies carry an L2 evict_first policy — M is written once and never read again here (BRBD_GEN_CRBA_POLICY=0 turns it off;
+  // measured, profiles/r2_crba_out_policy.txt: 65 536 x simple_humanoid 0.161 -> 0.156 ms, talos 0.186 -> 0.167 ms, 2^20 unchanged)
+  const bool out_policy = !(std::getenv("BRBD_GEN_CRBA_POLICY") && std::atoi(std::getenv("BRBD_GEN_CRBA_POLICY")) == 0);
+  os << "__device__ __forceinline__ void bulk_flush(const real * row, int sh, real * __restrict__ g, int L, bool live" << (out_policy ? ", unsigned long long pol" : "") << ")\n{\n"
         "  const int e0 = (" << A << " - sh) & " << A - 1 << ", n = (L - e0) & ~" << A - 1 << ";\n"
         "  if (live)\n  {\n"
         "    for (int e = 0; e < e0; ++e) g[e] = row[sh + e];\n"
         "    for (int e = e0 + n; e < L; ++e) g[e] = row[sh + e];\n"
         "    asm volatile(\"fence.proxy.async.shared::cta;\" ::: \"memory\");\n"
         "    if (n > 0)\n"
-        "      asm volatile(\"cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\" ::\"l\"(g + e0), \"r\"((unsigned)__cvta_generic_to_shared(row + sh + e0)),\n"
-        "                   \"r\"(n * " << (fp32 ? 4 : 8) << ") : \"memory\");\n"
+     << (out_policy ? "      asm volatile(\"cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;\" ::\"l\"(g + e0), \"r\"((unsigned)__cvta_generic_to_shared(row + sh + e0)),\n"
+                      : "      asm volatile(\"cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\" ::\"l\"(g + e0), \"r\"((unsigned)__cvta_generic_to_shared(row + sh + e0)),\n")
+     << "                   \"r\"(n * " << (fp32 ? 4 : 8) << ")" << (out_policy ? ", \"l\"(pol)" : "") << " : \"memory\");\n"
         "  }\n"
         "  asm volatile(\"cp.async.bulk.commit_group;\" ::: \"memory\");\n}\n";
   os << "#define BRBD_OUT0(row, val) myrow[sh + (row)] = (val)\n#define BRBD_CLEAR(row) myrow[ps[buf] + (row)] = BRBD_C(0.0)\n";
   // the row is free again once the copy engine has read the group of nbuf flushes ago out of it
   os << "#define BRBD_COLBEGIN(col) do { asm volatile(\"cp.async.bulk.wait_group.read " << nbuf - 1 << ";\" ::: \"memory\"); sh = (par + ((col) & 0xffff) * " << nv << ") & " << A - 1 << "; } while (0)\n";
-  os << "#define BRBD_FLUSH(cc) do { bulk_flush(myrow, sh, gcfg + ((cc) & 0xffff) * " << nv << ", ((cc) >> 16) * " << nv << ", live); ps[buf] = sh; \\\n"
+  os << "#define BRBD_FLUSH(cc) do { bulk_flush(myrow, sh, gcfg + ((cc) & 0xffff) * " << nv << ", ((cc) >> 16) * " << nv << ", live" << (out_policy ? ", pol_out" : "") << "); ps[buf] = sh; \\\n"
         "    buf = buf + 1 == " << nbuf << " ? 0 : buf + 1; myrow = em + buf * " << 32 * pitch << " + lane * " << pitch << "; } while (0)\n";
   os << "extern \"C\" __global__ void __launch_bounds__(" << nt << ", 1)\nbrbd_gen_crba_0"
      << "(const real * __restrict__ q, long long ldq, const real * __restrict__ v, long long ldv, const real * __restrict__ x, long long ldx,\n"
@@ -451,6 +455,7 @@ std::string wrap_device_crba_bulk(const std::string & body, bool fp32, int nt, i
   os << "  real * em = smem + warp * " << nbuf * 32 * pitch << ";\n  real * myrow = em + lane * " << pitch << ";\n";
   os << "  for (int k = lane; k < " << nbuf * 32 * pitch << "; k += 32) em[k] = BRBD_C(0.0);\n  __syncwarp();\n";
   os << "  int ps[" << nbuf << "] = {0}, sh = 0, buf = 0;\n";
+  if (out_policy) os << "  unsigned long long pol_out;\n  asm volatile(\"createpolicy.fractional.L2::evict_first.b64 %0, 1.0;\" : \"=l\"(pol_out));\n";
   os << "  const long long nthreads = (long long)gridDim.x * " << nt << ";\n";
   os << "  const long long rounds = (B + nthreads - 1) / nthreads;\n";
   os << "  for (long long rd = 0; rd < rounds; ++rd)\n  {\n";
