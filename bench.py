@@ -50,10 +50,10 @@ KERNEL_NAME = {"rnea": "rnea_dfs_kernel<double>", "aba": "aba_rr_kernel<double>"
 # dram__bytes_read.sum + dram__bytes_write.sum per launch, RECORDED from the committed `ncu --set full` capture named in
 # `source` (not measured in this run); only quoted for the exact configuration / batch of that capture, null otherwise.
 NCU_TRAFFIC = {
-    ("C2", 65536, "crba"): {"bytes": 611.0e6, "source": "profiles/r2_v3_step_ncu_full.csv (brbd_gen_crba_0, 96 threads, bulk copies: 22.9 MB read + 588.1 MB written)"},
+    ("C2", 65536, "crba"): {"bytes": 608.6e6, "source": "profiles/r2_v3_step_ncu_full.csv (brbd_gen_crba_0, 96 threads, bulk copies: 21.6 MB read + 587.0 MB written)"},
     ("C2", 65536, "crba:generic"): {"bytes": 644.2e6, "source": "profiles/r2_v1_step_ncu_full.csv (crba_tma_kernel<double,224,1>: 47.3 MB read + 596.9 MB written)"},
     ("C2", 65536, "aba:generic"): {"bytes": 814.2e6, "source": "profiles/r1_v8_step_ncu_full.csv (aba_rr_kernel<double,224>: 388.1 MB read + 426.1 MB written)"},
-    ("C2", 65536, "aba"): {"bytes": 467.5e6, "source": "profiles/r2_v3_step_ncu_full.csv (brbd_gen_aba_0, 448 threads: 259.6 MB read + 207.9 MB written; "
+    ("C2", 65536, "aba"): {"bytes": 389.9e6, "source": "profiles/r2_v3_step_ncu_full.csv (brbd_gen_aba_0, 448 threads, L2 policies on the records: 233.4 MB read + 156.5 MB written; "
                                                        "the generic aba_rr_kernel: 814.2 MB, profiles/r1_v8_step_ncu_full.csv)"},
 }
 
@@ -379,7 +379,7 @@ def main():
         per_cfg_out = 8 * sum(out_rows[k] for k in algos)
         Be = int(min(B, max(4096, (6 << 30) // per_cfg_out)))  # host blocks capped at ~6 GB of pinned memory
         e2e_steps = max(3, min(args.steps, 5))
-        host_threads = max(1, (os.cpu_count() or 1) // max(1, world)) if "crba" in spec else 1
+        e2e_threads = max(1, host_threads() // max(1, world)) if "crba" in spec else 1
         hin = [torch.from_numpy(np.ascontiguousarray(t[:Be].cpu().numpy())).pin_memory() for t in sets[0]]
         hq, hv, hx = (t.numpy().T for t in hin)
         houts = {k: [torch.empty(tuple(o[:Be].shape), dtype=torch.float64).pin_memory() for o in outs[k]] for k in algos}
@@ -396,7 +396,7 @@ def main():
                 elif k == "crba":
                     # num_threads as the reference arm uses them: all host cores (here they rebuild the dense matrices from
                     # the packed PCIe transfer; the reference spends them on the algorithm)
-                    pb.crbaInParallel(host_threads, pool, hq, o[0])
+                    pb.crbaInParallel(e2e_threads, pool, hq, o[0])
                 elif k == "rnea_derivatives":
                     pb.computeRNEADerivativesInParallel(1, pool, hq, hv, hx, *o)
                 else:
@@ -416,12 +416,12 @@ def main():
                "h2d_bytes_per_step": int(8 * Be * sum(in_rows[k] for k in algos)),
                "d2h_bytes_per_step": int(Be * per_cfg_out), "steps": e2e_steps, "batch_per_gpu": Be,
                "result_bytes_per_step": int(Be * per_cfg_out),  # what lands in the caller's blocks
-               "host_threads": host_threads,
+               "host_threads": e2e_threads,
                "note": "pinned host buffers -> brbd_*_batch(BRBD_PTR_HOST): H2D + kernels + D2H, wall clock, max over ranks"
-                       + (f"; crba with num_threads = {host_threads}: only the entries inside the tree sparsity cross PCIe and the host threads rebuild the dense matrices" if host_threads >= 2 and "crba" in algos else "")
+                       + (f"; crba with num_threads = {e2e_threads}: only the entries inside the tree sparsity cross PCIe and the host threads rebuild the dense matrices" if e2e_threads >= 2 and "crba" in algos else "")
                        + ("" if Be == B else f"; host blocks capped at {Be} configurations per GPU (6 GB of pinned memory)")}
 
-        if host_threads >= 2 and "crba" in algos and Be >= 4096:
+        if e2e_threads >= 2 and "crba" in algos and Be >= 4096:
             try:  # bytes that actually cross PCIe: the pattern entries of M, not the dense matrices
                 e2e["d2h_bytes_per_step"] = int(Be * (per_cfg_out - 8 * (nv * nv - len(pool.crbaPattern()[0]))))
             except Exception:
