@@ -223,8 +223,10 @@ brbd_status brbd_codegen_source(const brbd_model * m, int algo, int flags, char 
 void brbd_codegen_free(char * source);
 /* Generate, compile (NVRTC, sm_100a) and load kernels specialised for the pool's model.  algo_mask: bit (1 << BRBD_GEN_*);
  * flags: BRBD_GEN_FP32 to specialise the float instantiation, BRBD_GEN_EXPLICIT_SLOTS.  Afterwards brbd_rnea_batch /
- * brbd_aba_batch (and the calls built on them) run the specialised kernel for batches of at least
- * brbd_pool_set_specialized_min_batch (default 8192) configurations per device; brbd_pool_update drops them. */
+ * brbd_aba_batch / brbd_crba_batch (and the calls built on them) run the specialised kernel from the batch size where it beats
+ * the small-batch paths (measured per algorithm: CRBA always, RNEA from 4096, ABA from 8192 configurations per device, models of
+ * at most 8 dofs always); brbd_pool_set_specialized_min_batch (>= 0) overrides that for every algorithm, -1 restores it;
+ * brbd_pool_update drops the kernels. */
 brbd_status brbd_pool_specialize(brbd_pool * p, int algo_mask, int flags);
 int brbd_pool_specialized(const brbd_pool * p); /* mask of algorithms that have a specialised kernel */
 brbd_status brbd_pool_set_specialized_min_batch(brbd_pool * p, int64_t min_batch);

@@ -113,7 +113,7 @@ struct brbd_pool
   void * host_stage[2] = {nullptr, nullptr};
   size_t host_stage_bytes[2] = {0, 0};
   bool packed_unavailable = false; // the compact-staging kernel could not be built (no NVRTC): dense transfers
-  int64_t gen_min_batch = 8192; // batches at least this large use a specialised kernel when there is one
+  int64_t gen_min_batch = -1; // batches at least this large use a specialised kernel when there is one; -1: per algorithm (use_generated)
   brbd_model model;
   std::vector<brbd::DeviceCtx> devs;
   int64_t launches = 0;
@@ -417,9 +417,19 @@ inline int crba_bulk_pitch(int nv, int group, bool fp32)
   if ((pitch / A) % 2 == 0) pitch += A;
   return pitch;
 }
+// From which batch size a specialised pool runs the generated kernel.  brbd_pool_set_specialized_min_batch overrides it; by default
+// (-1) per algorithm, from the measured crossover against the small-batch paths (profiles/r2_gen_small_batch.txt, time per
+// device-resident call): CRBA — always (35-dof humanoid: 34 us against 71 us from 128 configurations on); RNEA — from 4096
+// (24-38 us flat up to 16 384 against the cooperative kernel's 20 us up to 1024 and the generic thread kernel's 46-48 us from
+// 4096); ABA — from 8192 (86-117 us against 36-83 us below); a model of at most 8 dofs — always (6-dof arm: 17 / 20 / 14 us
+// against 19 / 24 / 20 us).
 template<class T> inline bool use_generated(const brbd_pool * p, int algo, int64_t B)
 {
-  return p->gen[algo][sizeof(T) == 4 ? 1 : 0].nvar > 0 && B >= p->gen_min_batch;
+  if (p->gen[algo][sizeof(T) == 4 ? 1 : 0].nvar == 0) return false;
+  if (p->gen_min_batch >= 0) return B >= p->gen_min_batch;
+  if (algo == BRBD_GEN_CRBA) return true;
+  if (p->model.pd.nv <= 8 && algo <= BRBD_GEN_ABA) return true;
+  return B >= (algo == BRBD_GEN_RNEA ? 4096 : 8192);
 }
 // BRBD_<ALGO>_V=<name> forces one device path of an algorithm (tests, experiments)
 inline bool forced_path(const char * var, const char * name)

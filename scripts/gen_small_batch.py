@@ -28,6 +28,6 @@ for name in (sys.argv[1:] or ["simple_humanoid_ff", "humanoid_random", "manipula
                 e0.record()
                 for _ in range(50): fn(out)
                 e1.record(); torch.cuda.synchronize()
-                line += f" {algo}[{mode[:4]}] {e0.elapsed_time(e1) / 50 * 1e3:6.1f} us |"
+                line += f" {algo}[{mode}] {e0.elapsed_time(e1) / 50 * 1e3:6.1f} us |"
         print(line, flush=True)
     for p in pools.values(): p.close()
