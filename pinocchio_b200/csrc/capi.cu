@@ -217,7 +217,10 @@ brbd_status run_crba_expand(brbd_pool * p, const T * q, int64_t ldq, T * M, int6
   const int64_t nnz = (int64_t)p->crba_idx.size();
   if (2 * nnz > nn) return BRBD_OK; // nothing to gain from packing (a chain: the upper triangle is the pattern)
   CUDA_TRY(cudaSetDevice(d.dev));
-  const int64_t chunk = std::min<int64_t>(B, std::max<int64_t>(4096, (((int64_t)(48u << 20) / (int64_t)(nnz * sizeof(T))) / 1024) * 1024));
+  // chunks of ~24 MB of packed entries (8192 configurations of a 35-dof humanoid; measured with 65 536 of them, 16 threads:
+  // 4096 / 8192 / 16 384 / 32 768 per chunk -> 7.05 / 5.85 / 6.14 / 7.32 ms, the dense copy 11.4 ms; profiles/r2_crba_host_sweep.txt)
+  int64_t chunk = std::min<int64_t>(B, std::max<int64_t>(4096, (((int64_t)(24u << 20) / (int64_t)(nnz * sizeof(T))) / 1024) * 1024));
+  if (const char * e = std::getenv("BRBD_EXPAND_CHUNK")) chunk = std::min<int64_t>(B, std::max<int64_t>(1024, std::atoll(e))); // experiments
   brbd_status st = BRBD_OK;
   for (int b = 0; b < 2 && st == BRBD_OK; ++b)
   {
