@@ -154,6 +154,11 @@ brbd_status brbd_crba_batch(brbd_pool * p, const void * q, int64_t ldq, void * M
  * Runs the kernel generated for the pool's model (specialises CRBA at the first call: needs NVRTC).  ldP >= nnz. */
 brbd_status brbd_crba_packed_batch(brbd_pool * p, const void * q, int64_t ldq, void * P, int64_t ldP,
                                    int64_t batch, int flags);
+/* Host utility for callers of brbd_crba_packed_batch that need data.M after all: M[:,i] = the dense column-major nv x nv matrix of
+ * P[:,i] (zeros outside the pattern), rebuilt by `threads` host threads with non-temporal stores.  Host blocks only; a copy,
+ * no arithmetic. */
+brbd_status brbd_crba_expand_packed(const brbd_model * m, const void * P, int64_t ldP, void * M, int64_t ldM,
+                                    int64_t batch, int threads, int flags);
 /* The pattern: rows / cols may be NULL (size query); otherwise `capacity` entries each. */
 brbd_status brbd_model_crba_pattern(const brbd_model * m, int32_t * rows, int32_t * cols, int64_t capacity,
                                     int64_t * nnz);

@@ -162,6 +162,7 @@ public:
     return nnz;
   }
   brbd_pool * handle() { return pool_; }
+  const brbd_model * model_handle() const { return model_; }
   // Unlike the reference (parallel/rnea.hpp:53 "The pool is too small"), num_threads is NOT checked against size(): the GPU
   // path has no per-thread replicas, any num_threads is accepted.
 
@@ -235,6 +236,14 @@ inline void crbaInParallel(size_t num_threads, DeviceModelPool & pool, ConstMatr
   // num_threads host threads rebuild the dense matrices from the packed transfer (brbd_pool_set_host_threads); 0 / 1: plain copy
   check_status(brbd_pool_set_host_threads(pool.handle(), (int)num_threads));
   check_status(brbd_crba_batch(pool.handle(), q.data, q.ld, M.data, M.ld, q.cols, BRBD_PTR_HOST | BRBD_FP64));
+}
+// M.col(i) = the dense matrix of the packed column P.col(i), rebuilt by num_threads host threads (brbd_crba_expand_packed)
+inline void expandPackedCrba(size_t num_threads, DeviceModelPool & pool, ConstMatrixView P, MatrixView M)
+{
+  detail::check_rows("P", P.rows, pool.crbaPatternSize());
+  detail::check_rows("M", M.rows, (int64_t)pool.nv() * pool.nv());
+  detail::check_cols("M", M.cols, P.cols);
+  check_status(brbd_crba_expand_packed(pool.model_handle(), P.data, P.ld, M.data, M.ld, P.cols, (int)num_threads, BRBD_PTR_HOST | BRBD_FP64));
 }
 // P.col(i) = the entries of crba(q.col(i)) inside the structural pattern (pool.crbaPattern), column-major — opt-in output format
 inline void crbaPackedInParallel(size_t num_threads, DeviceModelPool & pool, ConstMatrixView q, MatrixView P)

@@ -29,6 +29,7 @@ SYMBOLS = [
     "brbd_pool_device_id", "brbd_pool_workspace_bytes", "brbd_codegen_source", "brbd_codegen_free", "brbd_pool_specialize",
     "brbd_pool_specialized", "brbd_pool_set_specialized_min_batch", "brbd_model_from_urdf",
     "brbd_crba_packed_batch", "brbd_model_crba_pattern", "brbd_pool_set_host_threads",
+    "brbd_crba_expand_packed",
 ]
 
 
@@ -98,6 +99,7 @@ def lib():
     L.brbd_crba_batch.argtypes = [vp, vp, i64, vp, i64, i64, ci]
     L.brbd_crba_packed_batch.argtypes = [vp, vp, i64, vp, i64, i64, ci]
     L.brbd_pool_set_host_threads.argtypes = [vp, ci]
+    L.brbd_crba_expand_packed.argtypes = [vp, vp, i64, vp, i64, i64, ci, ci]
     L.brbd_model_crba_pattern.argtypes = [vp, vp, vp, i64, ctypes.POINTER(i64)]
     L.brbd_rnea_derivatives_batch.argtypes = [vp, vp, i64, vp, i64, vp, i64, vp, i64, vp, i64, vp, i64, vp, i64, i64, ci]
     L.brbd_aba_derivatives_batch.argtypes = [vp, vp, i64, vp, i64, vp, i64, vp, i64, vp, i64, vp, i64, vp, i64, i64, ci]

@@ -721,6 +721,23 @@ brbd_status brbd_aba_euler_step_batch(brbd_pool * p, const void * q, int64_t ldq
            })));
 }
 
+brbd_status brbd_crba_expand_packed(const brbd_model * m, const void * P, int64_t ldP, void * M, int64_t ldM, int64_t batch, int threads,
+                                    int flags)
+{
+  if (!m || !P || !M) return fail(BRBD_EINVAL, "null argument");
+  if (flags & BRBD_PTR_DEVICE) return fail(BRBD_EINVAL, "brbd_crba_expand_packed works on host blocks");
+  std::vector<int32_t> idx;
+  crba_pattern_index(*m, idx);
+  const int nv = m->pd.nv;
+  const int64_t nnz = (int64_t)idx.size(), nn = (int64_t)nv * nv;
+  if (batch < 0) return fail(BRBD_EINVAL, "negative batch size");
+  if (ldP < nnz) return fail(BRBD_EINVAL, "P: leading dimension " + std::to_string(ldP) + " smaller than the expected number of rows " + std::to_string(nnz));
+  if (ldM < nn) return fail(BRBD_EINVAL, "M: leading dimension " + std::to_string(ldM) + " smaller than the expected number of rows " + std::to_string(nn));
+  if (batch == 0) return BRBD_OK;
+  if (flags & BRBD_FP32) expand_packed<float>((float *)M, ldM, (const float *)P, nnz, idx.data(), (int)nn, batch, threads, ldP);
+  else expand_packed<double>((double *)M, ldM, (const double *)P, nnz, idx.data(), (int)nn, batch, threads, ldP);
+  return BRBD_OK;
+}
 brbd_status brbd_pool_set_host_threads(brbd_pool * p, int n)
 {
   if (!p) return fail(BRBD_EINVAL, "null pool");

@@ -403,7 +403,7 @@ int crba_pattern_nnz(const brbd_model & m);
 void crba_pattern_index(const brbd_model & m, std::vector<int32_t> & idx); // idx[k] = cols[k] * nv + rows[k]
 // host_expand.cpp
 template<class T>
-void expand_packed(T * dst, int64_t ld, const T * src, int64_t nnz, const int32_t * idx, int nn, int64_t count, int threads);
+void expand_packed(T * dst, int64_t ld, const T * src, int64_t nnz, const int32_t * idx, int nn, int64_t count, int threads, int64_t src_ld = 0);
 // generated computeRNEADerivatives / computeABADerivatives (small models): q, v, x -> three nv*nv blocks + an nv block
 template<class T>
 brbd_status launch_generated_derivs(brbd_pool * p, DeviceCtx & d, int algo, const T * q, int64_t ldq, const T * v, int64_t ldv, const T * x,

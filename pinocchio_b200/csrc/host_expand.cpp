@@ -34,15 +34,17 @@ inline void stream_out(float * d, const float * s, int64_t n) { std::memcpy(d, s
 // dst: the caller's block (configuration c at dst + c * ld, nn = nv * nv elements each); src: packed, nnz per configuration;
 // idx[k] = position of packed entry k inside a matrix
 template<class T>
-void expand_packed(T * dst, int64_t ld, const T * src, int64_t nnz, const int32_t * idx, int nn, int64_t count, int threads)
+void expand_packed(T * dst, int64_t ld, const T * src, int64_t nnz, const int32_t * idx, int nn, int64_t count, int threads, int64_t src_ld)
 {
+  if (src_ld <= 0) src_ld = nnz;
+  if (threads < 1) threads = 1;
 #pragma omp parallel num_threads(threads)
   {
     std::vector<T> buf((size_t)nn + 8, T(0));
 #pragma omp for schedule(static)
     for (int64_t c = 0; c < count; ++c)
     {
-      const T * s = src + c * nnz;
+      const T * s = src + c * src_ld;
       for (int64_t k = 0; k < nnz; ++k) buf[idx[k]] = s[k];
       stream_out(dst + c * ld, buf.data(), nn);
     }
@@ -51,6 +53,6 @@ void expand_packed(T * dst, int64_t ld, const T * src, int64_t nnz, const int32_
 #endif
   }
 }
-template void expand_packed<double>(double *, int64_t, const double *, int64_t, const int32_t *, int, int64_t, int);
-template void expand_packed<float>(float *, int64_t, const float *, int64_t, const int32_t *, int, int64_t, int);
+template void expand_packed<double>(double *, int64_t, const double *, int64_t, const int32_t *, int, int64_t, int, int64_t);
+template void expand_packed<float>(float *, int64_t, const float *, int64_t, const int32_t *, int, int64_t, int, int64_t);
 } // namespace brbd

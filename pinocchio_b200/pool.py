@@ -387,12 +387,23 @@ def crbaPackedInParallel(num_threads: int, pool: ModelPool, q, P=None, async_: b
     return P
 
 
-def expandPackedCrba(pool: ModelPool, P):
-    """Dense (nv*nv x B) block from a packed host block (numpy) — what a caller that wants data.M back does."""
-    rows, cols = pool.crbaPattern()
-    P = np.asarray(P)
-    M = np.zeros((pool.nv * pool.nv, P.shape[1]), dtype=P.dtype, order="F")
-    M[cols.astype(np.int64) * pool.nv + rows, :] = P
+def expandPackedCrba(pool: ModelPool, P, M=None, num_threads: int = 1):
+    """Dense (nv*nv x B) block from a packed host block (numpy, F-ordered) — what a caller that wants data.M back does
+    (brbd_crba_expand_packed: num_threads host threads, a copy)."""
+    aP = _describe(P, len(pool.crbaPattern()[0]), "P")
+    if aP.device:
+        raise ValueError("expandPackedCrba works on host blocks")
+    nn = pool.nv * pool.nv
+    if M is None:
+        M = np.empty((nn, aP.cols), dtype=np.float32 if aP.dtype is np.float32 else np.float64, order="F")
+    aM = _describe(M, nn, "M", out=True)
+    if aM.cols != aP.cols:
+        raise ValueError(f"wrong argument size: all blocks must have the same number of columns ({aM.cols} != {aP.cols})")
+    try:
+        _capi.check(_capi.lib().brbd_crba_expand_packed(pool._h_model, ctypes.c_void_p(aP.ptr), aP.ld, ctypes.c_void_p(aM.ptr), aM.ld, aP.cols,
+                                                        int(num_threads), BRBD_FP32 if aP.dtype is np.float32 else BRBD_FP64))
+    except EngineError as e:
+        _raise(e)
     return M
 
 

@@ -86,6 +86,13 @@ int main()
         if (!in_pattern[e])
           for (int c = 0; c < B; ++c) err = std::fmax(err, std::fabs(M(e, c)));
       if (!(err < 1e-12)) { std::printf("FAIL packed crba, %.3e\n", err); return 1; }
+      // and back to the dense layout on the host: exactly M's pattern entries, zeros elsewhere
+      Eigen::MatrixXd M2(nv * nv, B);
+      pb::expandPackedCrba(2, *pool, pb::ConstMatrixView{P.data(), (int64_t)P.rows(), (int64_t)P.cols(), (int64_t)P.outerStride()},
+                           pb::MatrixView{M2.data(), (int64_t)M2.rows(), (int64_t)M2.cols(), (int64_t)M2.outerStride()});
+      for (int e = 0; e < nv * nv; ++e)
+        for (int c = 0; c < B; ++c)
+          if (in_pattern[e] ? std::fabs(M2(e, c) - M(e, c)) > 1e-12 : M2(e, c) != 0.0) { std::printf("FAIL expandPackedCrba\n"); return 1; }
     }
     // a block of columns with the parent's outer stride, as q.middleCols(5, 7) would be
     Eigen::MatrixXd tau2(nv, B);

@@ -281,3 +281,46 @@ def test_cpp_urdf_loader_matches_the_python_one():
     assert L.brbd_model_from_urdf(bad.encode(), -1, ctypes.byref(h)) == _capi.BRBD_EUNSUPPORTED_JOINT
     assert b"mimic" in L.brbd_last_error_string()
     assert L.brbd_model_from_urdf(b"/no/such/file.urdf", -1, ctypes.byref(h)) == _capi.BRBD_EINVAL
+
+
+@pytest.mark.parametrize("name", ["simple_humanoid_ff", "talos_reduced_ff", "manipulator"])
+def test_crba_expand_packed_on_the_host(name):
+    """brbd_crba_expand_packed (csrc/host_expand.cpp): packed pattern entries -> dense column-major matrices, by host threads with
+    non-temporal stores.  A copy, checked against a numpy scatter: dense and padded leading dimensions (an odd nv * nv puts every
+    other matrix 8 bytes off a 16-byte boundary), a block that starts off a 16-byte boundary, one and several threads, FP32, a
+    canary around the destination."""
+    import ctypes
+    from pinocchio_b200 import _capi
+    from conftest import load_model
+    model = load_model(name)
+    L = _capi.lib()
+    fm, keep = _capi.make_flat(model.flat())
+    h = ctypes.c_void_p()
+    _capi.check(L.brbd_model_create(ctypes.byref(fm), ctypes.byref(h)))
+    try:
+        n = ctypes.c_int64()
+        _capi.check(L.brbd_model_crba_pattern(h, None, None, 0, ctypes.byref(n)))
+        rows, cols = np.zeros(n.value, dtype=np.int32), np.zeros(n.value, dtype=np.int32)
+        _capi.check(L.brbd_model_crba_pattern(h, rows.ctypes.data_as(ctypes.c_void_p), cols.ctypes.data_as(ctypes.c_void_p), n.value, ctypes.byref(n)))
+        nv, nnz = model.nv, n.value
+        nn = nv * nv
+        key = cols.astype(np.int64) * nv + rows
+        rng = np.random.default_rng(3)
+        B = 257
+        for dt, flag in ((np.float64, _capi.BRBD_FP64), (np.float32, _capi.BRBD_FP32)):
+            for padP, padM, shift, threads in ((0, 0, 0, 1), (3, 0, 1, 4), (0, 3, 0, 3), (1, 2, 1, 8)):
+                Pbuf = rng.standard_normal((nnz + padP) * B).astype(dt)
+                P = Pbuf.reshape(B, nnz + padP)[:, :nnz]  # configuration per row = column-major (nnz x B) with ld = nnz + padP
+                flat = np.full((B + 1) * (nn + padM) + 4, -7.0, dtype=dt)
+                ref = np.zeros((B, nn), dtype=dt)
+                ref[:, key] = P
+                dst = flat[shift:]
+                _capi.check(L.brbd_crba_expand_packed(h, Pbuf.ctypes.data_as(ctypes.c_void_p), nnz + padP, dst.ctypes.data_as(ctypes.c_void_p),
+                                                      nn + padM, B, threads, flag))
+                got = flat[shift:shift + B * (nn + padM)].reshape(B, nn + padM)
+                assert np.array_equal(got[:, :nn], ref), (name, dt, padP, padM, shift, threads)
+                assert (got[:, nn:] == -7.0).all() and (flat[:shift] == -7.0).all() and (flat[shift + B * (nn + padM):] == -7.0).all()
+        with pytest.raises(_capi.EngineError):
+            _capi.check(L.brbd_crba_expand_packed(h, Pbuf.ctypes.data_as(ctypes.c_void_p), nnz - 1, flat.ctypes.data_as(ctypes.c_void_p), nn, B, 1, 0))
+    finally:
+        L.brbd_model_destroy(h)
