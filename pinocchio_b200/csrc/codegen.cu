@@ -248,6 +248,14 @@ std::string wrap_device(const std::string & body, const char * name, bool fp32, 
     os << "    const long long cfg_raw = cfg0 + lane;\n    const bool live = cfg_raw < B;\n    const long long cfg = live ? cfg_raw : B - 1;\n";
     os << "    const real * __restrict__ tq = q + cfg * ldq;\n    const real * __restrict__ tv = v + cfg * ldv;\n"
           "    const real * __restrict__ tx = x + cfg * ldx;\n    real * __restrict__ to = out + cfg * ldo;\n";
+    if (const char * e = std::getenv("BRBD_GEN_PREFETCH"))
+    { // experiment: this round's input columns into L2 (1) / L1 (2) before the straight-line body touches them one by one
+      const char * lvl = std::atoi(e) == 2 ? "L1" : "L2";
+      const int es = fp32 ? 4 : 8, step = 128 / es;
+      for (int k = 0; k < nq; k += step) os << "    asm volatile(\"prefetch.global." << lvl << " [%0];\" ::\"l\"(tq + " << k << "));\n";
+      for (int k = 0; k < nv; k += step)
+        os << "    asm volatile(\"prefetch.global." << lvl << " [%0];\" ::\"l\"(tv + " << k << "));\n    asm volatile(\"prefetch.global." << lvl << " [%0];\" ::\"l\"(tx + " << k << "));\n";
+    }
   }
   else
   {
@@ -416,7 +424,7 @@ std::string wrap_device_crba(const std::string & body, bool fp32, const cg::Emit
 // A bulk copy needs 16-byte aligned source, destination and size: the row is filled `sh` elements in, sh = the destination's
 // misalignment in elements (odd nv: every other configuration / column group), so that source and destination are congruent;
 // the few elements before / after the aligned interior leave through plain stores.
-std::string wrap_device_crba_bulk(const std::string & body, bool fp32, int nt, int nv, const std::string & ktable, int nbuf, int group)
+std::string wrap_device_crba_bulk(const std::string & body, bool fp32, int nt, int nq, int nv, const std::string & ktable, int nbuf, int group)
 {
   std::ostringstream os;
   const int A = fp32 ? 4 : 2; // elements per 16 bytes
@@ -463,6 +471,22 @@ std::string wrap_device_crba_bulk(const std::string & body, bool fp32, int nt, i
   os << "    if (cfg0 >= B) continue; // warp-uniform\n";
   os << "    const bool live = cfg0 + lane < B;\n    const long long cfg = live ? cfg0 + lane : B - 1;\n";
   os << "    const real * __restrict__ tq = q + cfg * ldq;\n    real * __restrict__ gcfg = out + cfg * ldM;\n";
+  if (const char * e = std::getenv("BRBD_GEN_PREFETCH")) // experiment: the lane's q column of the next round into L2 (1) / of this round into L1 (2)
+  {
+    const int mode = std::atoi(e);
+    const int es = fp32 ? 4 : 8, step = 128 / es;
+    if (mode == 1)
+    {
+      os << "    if (cfg + nthreads < B)\n    {\n      const real * nq_ = q + (cfg + nthreads) * ldq;\n";
+      for (int k = 0; k < nq; k += step) os << "      asm volatile(\"prefetch.global.L2 [%0];\" ::\"l\"(nq_ + " << k << "));\n";
+      os << "      asm volatile(\"prefetch.global.L2 [%0];\" ::\"l\"(nq_ + " << nq - 1 << "));\n    }\n";
+    }
+    else if (mode == 2)
+    {
+      for (int k = 0; k < nq; k += step) os << "    asm volatile(\"prefetch.global.L1 [%0];\" ::\"l\"(tq + " << k << "));\n";
+      os << "    asm volatile(\"prefetch.global.L1 [%0];\" ::\"l\"(tq + " << nq - 1 << "));\n";
+    }
+  }
   os << "    const int par = (int)((reinterpret_cast<unsigned long long>(gcfg) / " << (fp32 ? 4 : 8) << "ull) & " << A - 1 << "ull);\n";
   os << "    {\n" << body << "    }\n  }\n";
   os << "  asm volatile(\"cp.async.bulk.wait_group 0;\" ::: \"memory\");\n}\n";
@@ -680,7 +704,7 @@ brbd_status brbd_codegen_source(const brbd_model * m, int algo, int flags, char 
   }
   const std::string src = (algo >= BRBD_GEN_RNEA_DERIVATIVES && !(flags & BRBD_GEN_HOST))
                             ? wrap_device_derivs(body, algo_name(algo), fp32, nt, K.definition("__constant__"), m->pd.nv, derivs_staged)
-                            : crba_bulk ? wrap_device_crba_bulk(body, fp32, nt, m->pd.nv, K.definition("__constant__"), crba_nbuf, crba_group)
+                            : crba_bulk ? wrap_device_crba_bulk(body, fp32, nt, m->pd.nq, m->pd.nv, K.definition("__constant__"), crba_nbuf, crba_group)
                             : (algo == BRBD_GEN_CRBA && !(flags & BRBD_GEN_HOST))
                             ? wrap_device_crba(body, fp32, st, nt, m->pd.nq, m->pd.nv, K.definition("__constant__"), crba_nbuf, crba_group, crba_compact ? &pat : nullptr)
                             : (flags & BRBD_GEN_HOST) ? wrap_host(body, algo_name(algo), fp32, st, K.definition("static const"), m->pd.nv, crba_compact ? &pat : nullptr)
