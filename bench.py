@@ -53,8 +53,8 @@ NCU_TRAFFIC = {
     ("C2", 65536, "crba"): {"bytes": 608.6e6, "source": "profiles/r2_v3_step_ncu_full.csv (brbd_gen_crba_0, 96 threads, bulk copies: 21.6 MB read + 587.0 MB written)"},
     ("C2", 65536, "crba:generic"): {"bytes": 644.2e6, "source": "profiles/r2_v1_step_ncu_full.csv (crba_tma_kernel<double,224,1>: 47.3 MB read + 596.9 MB written)"},
     ("C2", 65536, "aba:generic"): {"bytes": 814.2e6, "source": "profiles/r1_v8_step_ncu_full.csv (aba_rr_kernel<double,224>: 388.1 MB read + 426.1 MB written)"},
-    ("C3", 1 << 20, "rnea_derivatives"): {"bytes": 1659.4e6, "source": "profiles/r2_C3_ncu_full.csv (brbd_gen_rnea_derivatives_0: 151.1 MB read + 1508.3 MB written; 288-byte result rows end in partial sectors)"},
-    ("C3", 1 << 20, "aba_derivatives"): {"bytes": 3611.6e6, "source": "profiles/r2_C3_ncu_full.csv (brbd_gen_aba_derivatives_0: 171.7 MB read + 3440.0 MB written, of which the 2.3 KB of local-memory spills per thread)"},
+    ("C3", 1 << 20, "rnea_derivatives"): {"bytes": 1565.4e6, "source": "profiles/r2_C3_ncu_full.csv (brbd_gen_rnea_derivatives_0: 151.2 MB read + 1414.2 MB written, of which the 1.0 KB of local-memory spill stores per configuration)"},
+    ("C3", 1 << 20, "aba_derivatives"): {"bytes": 3089.9e6, "source": "profiles/r2_C3_ncu_full.csv (brbd_gen_aba_derivatives_0: 161.4 MB read + 2928.5 MB written, of which the 3.9 KB of local-memory spill stores per configuration)"},
     ("C4", 4 << 20, "rnea"): {"bytes": 5826.4e6, "source": "profiles/r2_C4_ncu_full.csv (brbd_gen_rnea_0: 3866.1 MB read + 1960.3 MB written)"},
     ("C4", 4 << 20, "aba"): {"bytes": 33485.0e6, "source": "profiles/r2_C4_ncu_full.csv (brbd_gen_aba_0: 18776.0 MB read + 14709.1 MB written: the pass-3 records, 2.1 KB per configuration each way)"},
     ("C4", 4 << 20, "crba"): {"bytes": 49730.1e6, "source": "profiles/r2_C4_ncu_full.csv (brbd_gen_crba_0: 1323.9 MB read + 48406.2 MB written)"},
