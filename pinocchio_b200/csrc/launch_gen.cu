@@ -157,7 +157,8 @@ brbd_status build_variant(brbd_pool * p, int algo, bool fp32, int nt, bool direc
   }
   k.smem_bytes = (size_t)info.dynamic_smem_bytes;
   cudaKernel_t kern_tma = nullptr;
-  if (algo == BRBD_GEN_CRBA && cudaLibraryGetKernel(&kern_tma, lib, "brbd_gen_crba_tma") != cudaSuccess)
+  // (only the single-column warp-store source carries the tensor-store variant)
+  if (algo == BRBD_GEN_CRBA && !bulk && !compact && group == 1 && cudaLibraryGetKernel(&kern_tma, lib, "brbd_gen_crba_tma") != cudaSuccess)
   { // grouped columns: the source has no tensor-store variant
     kern_tma = nullptr;
     (void)cudaGetLastError();

@@ -323,9 +323,10 @@ BRBD_DI void minv_chol_blocked_config(int nv, const MinvCholBlockedLayout & L, T
     }
   }
   // ---- forward substitution L z = e_c by blocks of 4 rows (lanes own columns c; z = row c of Y) ----
+  // lanes beyond the matrix shadow row 0 of S (read-only by now: nobody writes what they read) and store nothing
   T * ycol[R];
 #pragma unroll
-  for (int t = 0; t < R; ++t) ycol[t] = Y + (row[t] < nvp ? row[t] : 0) * ld;
+  for (int t = 0; t < R; ++t) ycol[t] = row[t] < nvp ? Y + row[t] * ld : S;
   for (int ib = 0; ib < nvp; ib += 4)
   {
     T acc[R][4];
