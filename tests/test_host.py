@@ -324,3 +324,22 @@ def test_crba_expand_packed_on_the_host(name):
             _capi.check(L.brbd_crba_expand_packed(h, Pbuf.ctypes.data_as(ctypes.c_void_p), nnz - 1, flat.ctypes.data_as(ctypes.c_void_p), nn, B, 1, 0))
     finally:
         L.brbd_model_destroy(h)
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (the CPU arm the driver runs beside the GPU arm) needs no GPU: one JSON line with the keys of the
+    bench contract, the metric / unit / config of the GPU arm, `impl: reference`, an `e2e` that repeats the value with no copies."""
+    import json
+    import subprocess
+    import sys
+    from conftest import ROOT
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1"],
+                         capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["unit"] == "evals/s" and line["higher_is_better"] is True
+    assert line["metric"] == "batched dynamics evals/sec (aba + crba)" and line["dtype"] == "f64" and line["n_gpus"] == 1
+    assert line["value"] > 0 and line["e2e"]["value"] == line["value"]
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1 and line["cpu_baseline"]["value"] == line["value"]
+    assert "65536" in line["config"]["workload"] and "simple_humanoid" in line["config"]["workload"]
