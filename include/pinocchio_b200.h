@@ -245,7 +245,8 @@ brbd_status brbd_host_register(void * ptr, uint64_t bytes);
  * reference spends on the algorithm itself.  Here they serve one purpose: with n >= 2 (and a single-device pool, NVRTC available),
  * a host-pointer brbd_crba_batch moves only the entries inside the structural pattern over PCIe (brbd_crba_packed_batch's
  * format, a third of nv * nv for a humanoid) and n threads rebuild the caller's dense matrices while the next chunk is in
- * flight.  Results are bit-identical to the packed kernel's; 0 or 1 (default): the dense block is copied as it is. */
+ * flight.  Results are bit-identical to the packed kernel's; 0 or 1 (default): the dense block is copied as it is.  Applies to
+ * batches of at least 4096 configurations; the first such call generates and compiles the packed kernel (about a second). */
 brbd_status brbd_pool_set_host_threads(brbd_pool * p, int n);
 brbd_status brbd_host_unregister(void * ptr);
 
