@@ -16,7 +16,8 @@ class CodegenInfo(ctypes.Structure):
 
 
 def codegen_source(model, algo: str, explicit_slots: bool = False, host: bool = False, nt: int = 0, minb: int = 0,
-                   direct_io: bool = False, fp32: bool = False, crba_compact: bool = False, crba_group: int = 0):
+                   direct_io: bool = False, fp32: bool = False, crba_compact: bool = False, crba_group: int = 0, crba_bulk: bool = False,
+                   crba_nbuf: int = 1):
     """Returns (source text, info dict) for `model` (a Model or a flat dict) and `algo` in {"rnea", "aba"}."""
     L = _capi.lib()
     flat = model.flat() if hasattr(model, "flat") else model
@@ -25,7 +26,7 @@ def codegen_source(model, algo: str, explicit_slots: bool = False, host: bool = 
     _capi.check(L.brbd_model_create(ctypes.byref(fm), ctypes.byref(h)))
     try:
         flags = (1 if explicit_slots else 0) | (2 if host else 0) | (4 if fp32 else 0) | (8 if direct_io else 0) | ((nt & 0xfff) << 8) | ((minb & 0xf) << 20) \
-            | (16 if crba_compact else 0) | ((crba_group & 0x1f) << 24)
+            | (16 if crba_compact else 0) | ((crba_group & 0x1f) << 24) | ((32 | (((crba_nbuf - 1) & 3) << 29)) if crba_bulk else 0)
         src = ctypes.c_char_p()
         info = CodegenInfo()
         L.brbd_codegen_source.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_char_p), ctypes.POINTER(CodegenInfo)]

@@ -628,6 +628,30 @@ std::string wrap_host(const std::string & body, const char * name, bool fp32, co
   os << body << "}\n";
   return os.str();
 }
+
+// Host emulation of ONE LANE of wrap_device_crba_bulk (tests of the generator only): the staging rows persist from call to call as
+// a lane's rows do from round to round of the persistent grid, every call may find its matrix at another misalignment
+// (brbd_gen_crba_host_par, set by the test: the `par` of the device wrapper), a group is staged `sh` elements in and leaves as
+// row[sh .. sh + L), and what a row still holds from `nbuf` groups ago — written at THAT group's shift — is cleared first.
+std::string wrap_host_crba_bulk(const std::string & body, bool fp32, const std::string & ktable, int nv, int nbuf, int group)
+{
+  std::ostringstream os;
+  const int A = fp32 ? 4 : 2, pitch = crba_bulk_pitch(nv, group, fp32);
+  os << "#define BRBD_NV " << nv << "\n// generated by pinocchio_b200 codegen (host emulation of the bulk-copy CRBA wrapper, tests only)\n#include <math.h>\n";
+  os << math_macros(fp32) << ktable;
+  os << "#define BRBD_IN0(k) qc[(k)]\n#define BRBD_IN1(k) vc[(k)]\n#define BRBD_IN2(k) xc[(k)]\n";
+  os << "extern \"C\" { int brbd_gen_crba_host_par = 0; }\n";
+  os << "static real em[" << nbuf << "][" << pitch << "];\nstatic int ps[" << nbuf << "], buf = 0;\n";
+  os << "#define BRBD_OUT0(row, val) myrow[sh + (row)] = (val)\n#define BRBD_CLEAR(row) myrow[ps[buf] + (row)] = BRBD_C(0.0)\n";
+  os << "#define BRBD_COLBEGIN(col) sh = (brbd_gen_crba_host_par + ((col) & 0xffff) * BRBD_NV) & " << A - 1 << "\n";
+  os << "#define BRBD_FLUSH(cc) do { const int lo_ = (cc) & 0xffff, len_ = ((cc) >> 16) * BRBD_NV; \\\n"
+        "    for (int e_ = 0; e_ < len_; ++e_) oc[lo_ * BRBD_NV + e_] = myrow[sh + e_]; \\\n"
+        "    ps[buf] = sh; buf = buf + 1 == " << nbuf << " ? 0 : buf + 1; myrow = em[buf]; } while (0)\n";
+  os << "extern \"C\" void brbd_gen_crba_host(const real * qc, const real * vc, const real * xc, real * oc, real * rec, real * park)\n{\n"
+        "  real * myrow = em[buf];\n  int sh = 0;\n";
+  os << body << "  (void)sh; (void)myrow;\n}\n";
+  return os.str();
+}
 } // namespace
 
 namespace brbd
@@ -658,7 +682,7 @@ brbd_status brbd_codegen_source(const brbd_model * m, int algo, int flags, char 
   if (flags & BRBD_GEN_HOST) crba_nbuf = 1;
   // CRBA: adjacent columns per flush (see trace_crba); the host variant and the TMA variant take one column at a time
   int crba_group = (flags >> 24) & 0x1f ? (flags >> 24) & 0x1f : 1;
-  if ((flags & BRBD_GEN_HOST) && !(flags & BRBD_GEN_CRBA_COMPACT)) crba_group = 1;
+  if ((flags & BRBD_GEN_HOST) && !(flags & (BRBD_GEN_CRBA_COMPACT | BRBD_GEN_CRBA_BULK))) crba_group = 1;
   // CRBA, compact staging: only the entries of the structural pattern are staged (see CrbaPattern); one staging tile per warp
   const bool crba_compact = algo == BRBD_GEN_CRBA && (flags & BRBD_GEN_CRBA_COMPACT) != 0;
   // (the flags' group field then counts ENTRIES per group, in units of 8, instead of columns)
@@ -669,6 +693,9 @@ brbd_status brbd_codegen_source(const brbd_model * m, int algo, int flags, char 
   // CRBA, bulk-copy variant: `group` adjacent columns per lane and copy, rotating over bits 29..30 (+1) staging rows
   const bool crba_bulk = algo == BRBD_GEN_CRBA && !crba_compact && (flags & BRBD_GEN_CRBA_BULK) != 0 && !(flags & BRBD_GEN_HOST);
   if (crba_bulk) crba_nbuf = ((flags >> 29) & 3) + 1;
+  // host emulation of the bulk-copy wrapper's staging (tests of the generator): same groups, same rotation of staging rows
+  const bool crba_bulk_host = algo == BRBD_GEN_CRBA && !crba_compact && (flags & BRBD_GEN_CRBA_BULK) != 0 && (flags & BRBD_GEN_HOST) != 0;
+  if (crba_bulk_host) crba_nbuf = ((flags >> 29) & 3) + 1;
   cg::Tracer T(m->pd, (flags & BRBD_GEN_EXPLICIT_SLOTS) != 0);
   if (algo == BRBD_GEN_ABA) cg::trace_aba(T);
   else if (algo == BRBD_GEN_CRBA) cg::trace_crba(T, crba_nbuf, crba_group, crba_compact, crba_budget);
@@ -710,6 +737,7 @@ brbd_status brbd_codegen_source(const brbd_model * m, int algo, int flags, char 
                             : crba_bulk ? wrap_device_crba_bulk(body, fp32, nt, m->pd.nq, m->pd.nv, K.definition("__constant__"), crba_nbuf, crba_group)
                             : (algo == BRBD_GEN_CRBA && !(flags & BRBD_GEN_HOST))
                             ? wrap_device_crba(body, fp32, st, nt, m->pd.nq, m->pd.nv, K.definition("__constant__"), crba_nbuf, crba_group, crba_compact ? &pat : nullptr)
+                            : crba_bulk_host ? wrap_host_crba_bulk(body, fp32, K.definition("static const"), m->pd.nv, crba_nbuf, crba_group)
                             : (flags & BRBD_GEN_HOST) ? wrap_host(body, algo_name(algo), fp32, st, K.definition("static const"), m->pd.nv, crba_compact ? &pat : nullptr)
                                                   : wrap_device(body, algo_name(algo), fp32, T.nrec, st, nt, minb, tmem_cols, m->pd.nq, m->pd.nv, copies,
                                                                 direct_io, K.definition("__constant__"));

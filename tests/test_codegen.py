@@ -118,6 +118,38 @@ def test_generated_crba_compact_staging(oracle_cls, name, group):
     assert np.array_equal(packed, dense[key])  # the two output modes carry the same values
 
 
+@pytest.mark.parametrize("name", ["simple_humanoid_ff", "talos_reduced_ff", "mixed", "double_ff", "humanoid_hands"])
+@pytest.mark.parametrize("group,nbuf", [(1, 1), (3, 1), (8, 1), (3, 2), (2, 3)])
+def test_generated_crba_bulk_staging(oracle_cls, name, group, nbuf):
+    """The staging logic of the bulk-copy CRBA wrapper, emulated for one lane on the host: `nbuf` staging rows that persist from
+    configuration to configuration (as a lane's rows do from round to round), groups of adjacent columns staged `sh` elements in
+    with `sh` changing from call to call (the destination's misalignment), stale entries cleared at the shift they were written
+    with.  Every configuration must come out as the oracle's matrix with exact zeros outside the sparsity — a stale entry of an
+    earlier group or configuration shows up as a non-zero there."""
+    from conftest import structural_mask
+    model = EXTRA[name] if name in EXTRA else load_model(name)
+    orc = oracle_cls(model)
+    nv = model.nv
+    q, v, x = random_inputs(model, 7, 13)
+    ref = orc.crba(q, world=True)
+    mask = structural_mask(model)
+    with tempfile.TemporaryDirectory() as tmp:
+        fn, info = build_host(model, "crba", False, tmp, crba_bulk=True, crba_group=group, crba_nbuf=nbuf)
+        lib = fn._objects if hasattr(fn, "_objects") else None
+        so = [f for f in os.listdir(tmp) if f.endswith(".so")][0]
+        par = ctypes.c_int.in_dll(ctypes.CDLL(os.path.join(tmp, so)), "brbd_gen_crba_host_par")
+        P = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+        rec, park = np.zeros(1), np.zeros(1)
+        for i in range(q.shape[1]):
+            par.value = (3 * i + 1) % 2  # another misalignment every call
+            qi = np.ascontiguousarray(q[:, i])
+            oi = np.full(nv * nv, np.nan)
+            fn(P(qi), P(qi), P(qi), P(oi), P(rec), P(park))
+            assert np.isfinite(oi).all(), (name, i)
+            assert np.abs(oi - ref[:, i]).max() <= 1e-12 * max(1.0, np.abs(ref).max()), (name, group, nbuf, i)
+            assert not oi[~mask].any(), (name, group, nbuf, i, "stale staging entries")
+
+
 def test_constant_folding_shrinks_the_program(oracle_cls):
     """simple_humanoid's placements are identity rotations: the generated ABA executes far fewer operations than the
     algorithm's count on a general model (26 103, the oracle's counting scalar), and the model's constants never appear as loads."""
