@@ -11,6 +11,7 @@
 //              contiguous column ranges over the pool's devices; there is no inter-device exchange.
 // There is no CPU fallback anywhere in this file.
 #include "host_ctx.hpp"
+#include <nvtx3/nvToolsExt.h>
 #include "model_build.hpp"
 
 using namespace brbd;
@@ -30,6 +31,14 @@ brbd_status fail(brbd_status s, const std::string & msg)
 
 namespace
 {
+// NVTX range around every batched entry point of the C ABI (tracing): shows up by name in Nsight Systems / as an
+// ncu --nvtx-include filter; a no-op when no tool is attached.
+struct NvtxRange
+{
+  explicit NvtxRange(const char * name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+};
+#define BRBD_NVTX(name) NvtxRange nvtx_range__(name)
 // ------------------------------------------------------------------------------------------------
 // Generic call wrapper: argument checks, device/host pointer handling, sharding over devices.
 // ------------------------------------------------------------------------------------------------
@@ -513,6 +522,7 @@ brbd_status brbd_pool_update(brbd_pool * p, const brbd_model * m)
 }
 brbd_status brbd_pool_specialize(brbd_pool * p, int algo_mask, int flags)
 {
+  BRBD_NVTX("brbd_pool_specialize");
   if (!p) return fail(BRBD_EINVAL, "null pool");
   brbd_status st = brbd_pool_synchronize(p);
   if (st != BRBD_OK) return st;
@@ -570,6 +580,7 @@ double brbd_pool_last_kernel_ms(const brbd_pool * p) { return p ? p->last_ms : 0
 brbd_status brbd_rnea_batch(brbd_pool * p, const void * q, int64_t ldq, const void * v, int64_t ldv, const void * a,
                             int64_t lda, void * tau, int64_t ldtau, int64_t batch, int flags)
 {
+  BRBD_NVTX("brbd_rnea_batch");
   if (!p) return fail(BRBD_EINVAL, "null pool");
   const int nq = p->model.pd.nq, nv = p->model.pd.nv;
   std::vector<Arg> args = {{q, nullptr, ldq, nq, false}, {v, nullptr, ldv, nv, false}, {a, nullptr, lda, nv, false}, {nullptr, tau, ldtau, nv, false}};
@@ -582,6 +593,7 @@ brbd_status brbd_rnea_batch(brbd_pool * p, const void * q, int64_t ldq, const vo
 brbd_status brbd_aba_batch(brbd_pool * p, const void * q, int64_t ldq, const void * v, int64_t ldv, const void * tau,
                            int64_t ldtau, void * a, int64_t lda, int64_t batch, int flags)
 {
+  BRBD_NVTX("brbd_aba_batch");
   if (!p) return fail(BRBD_EINVAL, "null pool");
   const int nq = p->model.pd.nq, nv = p->model.pd.nv;
   std::vector<Arg> args = {{q, nullptr, ldq, nq, false}, {v, nullptr, ldv, nv, false}, {tau, nullptr, ldtau, nv, false}, {nullptr, a, lda, nv, false}};
@@ -593,6 +605,7 @@ brbd_status brbd_aba_batch(brbd_pool * p, const void * q, int64_t ldq, const voi
 
 brbd_status brbd_crba_batch(brbd_pool * p, const void * q, int64_t ldq, void * M, int64_t ldM, int64_t batch, int flags)
 {
+  BRBD_NVTX("brbd_crba_batch");
   if (!p) return fail(BRBD_EINVAL, "null pool");
   const int nq = p->model.pd.nq, nv = p->model.pd.nv;
   std::vector<Arg> args = {{q, nullptr, ldq, nq, false}, {nullptr, M, ldM, (int64_t)nv * nv, false}};
@@ -612,6 +625,7 @@ brbd_status brbd_crba_batch(brbd_pool * p, const void * q, int64_t ldq, void * M
 
 brbd_status brbd_crba_packed_batch(brbd_pool * p, const void * q, int64_t ldq, void * P, int64_t ldP, int64_t batch, int flags)
 {
+  BRBD_NVTX("brbd_crba_packed_batch");
   if (!p) return fail(BRBD_EINVAL, "null pool");
   const int nq = p->model.pd.nq;
   const int64_t nnz = crba_pattern_nnz(p->model);
@@ -626,6 +640,7 @@ brbd_status brbd_rnea_derivatives_batch(brbd_pool * p, const void * q, int64_t l
                                         int64_t ld_dv, void * dtau_da, int64_t ld_da, void * tau, int64_t ldtau,
                                         int64_t batch, int flags)
 {
+  BRBD_NVTX("brbd_rnea_derivatives_batch");
   if (!p) return fail(BRBD_EINVAL, "null pool");
   const int nq = p->model.pd.nq, nv = p->model.pd.nv;
   const int64_t nn = (int64_t)nv * nv;
@@ -644,6 +659,7 @@ brbd_status brbd_aba_derivatives_batch(brbd_pool * p, const void * q, int64_t ld
                                        int64_t ld_dv, void * ddq_dtau, int64_t ld_dtau, void * ddq, int64_t ldddq,
                                        int64_t batch, int flags)
 {
+  BRBD_NVTX("brbd_aba_derivatives_batch");
   if (!p) return fail(BRBD_EINVAL, "null pool");
   const int nq = p->model.pd.nq, nv = p->model.pd.nv;
   const int64_t nn = (int64_t)nv * nv;
@@ -660,6 +676,7 @@ brbd_status brbd_aba_derivatives_batch(brbd_pool * p, const void * q, int64_t ld
 brbd_status brbd_nle_batch(brbd_pool * p, const void * q, int64_t ldq, const void * v, int64_t ldv, void * nle, int64_t ldn,
                            int64_t batch, int flags)
 {
+  BRBD_NVTX("brbd_nle_batch");
   if (!p) return fail(BRBD_EINVAL, "null pool");
   const int nq = p->model.pd.nq, nv = p->model.pd.nv;
   std::vector<Arg> args = {{q, nullptr, ldq, nq, false}, {v, nullptr, ldv, nv, false}, {nullptr, nle, ldn, nv, false}};
@@ -671,6 +688,7 @@ brbd_status brbd_nle_batch(brbd_pool * p, const void * q, int64_t ldq, const voi
 
 brbd_status brbd_gravity_batch(brbd_pool * p, const void * q, int64_t ldq, void * g, int64_t ldg, int64_t batch, int flags)
 {
+  BRBD_NVTX("brbd_gravity_batch");
   if (!p) return fail(BRBD_EINVAL, "null pool");
   const int nq = p->model.pd.nq, nv = p->model.pd.nv;
   std::vector<Arg> args = {{q, nullptr, ldq, nq, false}, {nullptr, g, ldg, nv, false}};
@@ -682,6 +700,7 @@ brbd_status brbd_gravity_batch(brbd_pool * p, const void * q, int64_t ldq, void 
 
 brbd_status brbd_minverse_batch(brbd_pool * p, const void * q, int64_t ldq, void * Minv, int64_t ldM, int64_t batch, int flags)
 {
+  BRBD_NVTX("brbd_minverse_batch");
   if (!p) return fail(BRBD_EINVAL, "null pool");
   const int nq = p->model.pd.nq, nv = p->model.pd.nv;
   std::vector<Arg> args = {{q, nullptr, ldq, nq, false}, {nullptr, Minv, ldM, (int64_t)nv * nv, false}};
@@ -693,6 +712,7 @@ brbd_status brbd_minverse_batch(brbd_pool * p, const void * q, int64_t ldq, void
 brbd_status brbd_integrate_batch(brbd_pool * p, const void * q, int64_t ldq, const void * v, int64_t ldv, void * qout, int64_t ldqo,
                                  int64_t batch, int flags)
 {
+  BRBD_NVTX("brbd_integrate_batch");
   if (!p) return fail(BRBD_EINVAL, "null pool");
   const int nq = p->model.pd.nq, nv = p->model.pd.nv;
   std::vector<Arg> args = {{q, nullptr, ldq, nq, false}, {v, nullptr, ldv, nv, false}, {nullptr, qout, ldqo, nq, false}};
@@ -706,6 +726,7 @@ brbd_status brbd_aba_euler_step_batch(brbd_pool * p, const void * q, int64_t ldq
                                       int64_t ldtau, double dt, void * q_next, int64_t ldqn, void * v_next, int64_t ldvn,
                                       int64_t batch, int flags)
 {
+  BRBD_NVTX("brbd_aba_euler_step_batch");
   if (!p) return fail(BRBD_EINVAL, "null pool");
   const int nq = p->model.pd.nq, nv = p->model.pd.nv;
   std::vector<Arg> args = {{q, nullptr, ldq, nq, false},          {v, nullptr, ldv, nv, false},         {tau, nullptr, ldtau, nv, false},
