@@ -628,7 +628,8 @@ brbd_status brbd_crba_packed_batch(brbd_pool * p, const void * q, int64_t ldq, v
   BRBD_NVTX("brbd_crba_packed_batch");
   if (!p) return fail(BRBD_EINVAL, "null pool");
   const int nq = p->model.pd.nq;
-  const int64_t nnz = crba_pattern_nnz(p->model);
+  if (p->crba_idx.empty()) crba_pattern_index(p->model, p->crba_idx); // computed once per model (brbd_pool_update clears it)
+  const int64_t nnz = (int64_t)p->crba_idx.size();
   std::vector<Arg> args = {{q, nullptr, ldq, nq, false}, {nullptr, P, ldP, nnz, false}};
   DISPATCH(flags, (run_call<T>(p, args, batch, flags, [&](DeviceCtx & d, std::vector<void *> & PP, int64_t B) {
              return launch_crba_packed<T>(p, d, (const T *)PP[0], args[0].ld, (T *)PP[1], args[1].ld, B);
